@@ -1,0 +1,414 @@
+"""CPU oracle for the KAN-convolution hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-PyTorch (CPU, fp32 or fp64) restatement of the arithmetic of the
+reference's four convolutional KAN layers.  It is the *checker* for the CUDA path in
+``convolutional-kan-for-image-classification_b200/``; it is never imported by the product
+package.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.
+
+Parity status: **pinned** against the live reference.  ``tests/golden/make_golden.py`` imports
+the unmodified reference from ``/root/reference`` (possible only in the dev container), runs it in
+fp64 and fp32 on seeded inputs and stores inputs / weights / outputs / gradients under
+``tests/golden/*.npz``; ``tests/test_oracle.py`` checks every function here against those
+fixtures (and against the SURVEY Appendix-E checksums).  The reference itself ships no tests
+or golden vectors.
+
+Reference call sites restated here (paths relative to the reference tree):
+  * B-spline basis, Cox-de Boor recursion ........ layers/kan_layers.py:203-233
+  * KANConvNDLayer.forward_kan / forward ......... layers/kan_layers.py:197-258
+  * ChebyKANConvNDLayer.forward_ChebyKAN ......... layers/cheby_kan_layers.py:91-111
+  * GRAMKANConvNDLayer.beta/gram_poly/forward_kag  layers/gram_kan_layers.py:150-199
+  * FastKANConvNDLayer.forward_fast_kan .......... layers/fast_kan_layers.py:100-120
+  * RadialBasisFunction.forward .................. utils/utils.py:19-33
+  * VGG.make_layers / forward .................... models/kan_vgg.py:40-188
+
+The third-party arithmetic underneath (conv2d, instance/batch norm, PReLU, GELU/SiLU) lives in
+PyTorch itself (the reference pins no version; the oracle runs on the torch of this image).
+Backward is autograd-derived here exactly as in the reference (it has no hand-written backward).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+__all__ = [
+    "make_knots", "bspline_basis", "cheby_basis", "gram_basis", "rbf_basis",
+    "kan_conv2d", "cheby_conv2d", "gram_conv2d", "fastkan_conv2d",
+    "OracleKANConv2D", "OracleChebyKANConv2D", "OracleGRAMKANConv2D", "OracleFastKANConv2D",
+    "OracleVGG", "VGG_CFGS", "conv_flops",
+]
+
+IntOr2 = Union[int, Tuple[int, int]]
+
+
+# ----------------------------------------------------------------------------------------------
+# basis functions
+# ----------------------------------------------------------------------------------------------
+def make_knots(grid_size: int, spline_order: int, grid_range: Sequence[float]) -> torch.Tensor:
+    """fp32 knot vector of kan_layers.py:184-190 (G + 2K + 1 uniformly spaced knots)."""
+    lo, hi = float(grid_range[0]), float(grid_range[1])
+    h = (hi - lo) / grid_size
+    return torch.linspace(lo - h * spline_order, hi + h * spline_order,
+                          grid_size + 2 * spline_order + 1, dtype=torch.float32)
+
+
+def bspline_basis(x: torch.Tensor, knots: torch.Tensor, order: int) -> torch.Tensor:
+    """Cox-de Boor recursion of kan_layers.py:209-233.  Returns [..., G+K] (trailing basis axis).
+
+    Order-0 indicators are half-open [t_i, t_{i+1}); the recursion keeps the reference's operation
+    order ``(x - t_i) / (t_{i+k} - t_i) * B`` and its zero-denominator guards.
+    """
+    # The reference keeps the knot vector as an fp32 attribute even when the module is .double()'d, so
+    # knot differences are formed in the knots' own dtype and only then promoted against x.
+    t = knots.to(device=x.device)
+    xe = x.unsqueeze(-1)
+    b = ((xe >= t[:-1]) & (xe < t[1:])).to(x.dtype)
+    for k in range(1, order + 1):
+        d_left = t[k:-1] - t[:-(k + 1)]
+        d_right = t[k + 1:] - t[1:-k]
+        d_left = torch.where(d_left == 0, torch.ones_like(d_left), d_left)
+        d_right = torch.where(d_right == 0, torch.ones_like(d_right), d_right)
+        b = (xe - t[:-(k + 1)]) / d_left * b[..., :-1] + (t[k + 1:] - xe) / d_right * b[..., 1:]
+    return b
+
+
+def cheby_basis(x: torch.Tensor, degree: int, eps: float = 1e-7) -> torch.Tensor:
+    """cos(d * acos(clamp(tanh x))) for d = 0..degree (cheby_kan_layers.py:93-96).  [..., D+1]."""
+    theta = torch.acos(torch.clamp(torch.tanh(x), -1 + eps, 1 - eps))
+    d = torch.arange(0, degree + 1, device=x.device)
+    return torch.cos(theta.unsqueeze(-1) * d)
+
+
+def gram_beta(n: int, m: int, beta_weights: torch.Tensor) -> torch.Tensor:
+    """gram_kan_layers.py:150-153."""
+    return (((m + n) * (m - n) * n ** 2) / (m ** 2 / (4.0 * n ** 2 - 1.0))) * beta_weights[n]
+
+
+def gram_basis(t: torch.Tensor, degree: int, beta_weights: torch.Tensor) -> List[torch.Tensor]:
+    """Gram three-term recurrence of gram_kan_layers.py:155-170; list of D+1 tensors shaped like t."""
+    p0 = torch.ones_like(t)
+    if degree == 0:
+        return [p0]
+    p1 = t
+    out = [p0, p1]
+    for i in range(2, degree + 1):
+        p2 = t * p1 - gram_beta(i - 1, i, beta_weights) * p0
+        out.append(p2)
+        p0, p1 = p1, p2
+    return out
+
+
+def rbf_basis(u: torch.Tensor, grid: torch.Tensor, denominator: float) -> torch.Tensor:
+    """exp(-((u - g_j) / den)^2), utils/utils.py:32-33.  [..., G]."""
+    return torch.exp(-((u.unsqueeze(-1) - grid.to(u.dtype)) / denominator) ** 2)
+
+
+def _act(name: Optional[str]) -> Callable[[torch.Tensor], torch.Tensor]:
+    if name is None or name == "identity":
+        return lambda v: v
+    if name == "gelu":
+        return F.gelu            # exact erf GELU == nn.GELU() default
+    if name == "silu":
+        return F.silu
+    raise ValueError(f"unsupported base activation {name!r}")
+
+
+def _norm(z: torch.Tensor, kind: str, eps: float, weight, bias, running=None, training=True):
+    if kind == "instance":
+        return F.instance_norm(z, None, None, weight, bias, True, 0.1, eps)
+    if kind == "batch":
+        rm, rv = running if running is not None else (None, None)
+        return F.batch_norm(z, rm, rv, weight, bias, training or rm is None, 0.1, eps)
+    if kind == "none":
+        return z
+    raise ValueError(kind)
+
+
+def _expand(basis: torch.Tensor) -> torch.Tensor:
+    """[N, C, H, W, nb] -> [N, C*nb, H, W] with expanded channel c*nb + j (kan_layers.py:236-237)."""
+    return basis.movedim(-1, 2).flatten(1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# one-group layer functions
+# ----------------------------------------------------------------------------------------------
+def kan_conv2d(x, w_base, w_spline, prelu_weight, knots, spline_order, act="gelu",
+               stride: IntOr2 = 1, padding: IntOr2 = 0, dilation: IntOr2 = 1,
+               norm="instance", eps=1e-5, norm_weight=None, norm_bias=None):
+    """One group of KANConvNDLayer.forward_kan (kan_layers.py:197-247), ndim = 2, no dropout."""
+    base = F.conv2d(_act(act)(x), w_base, None, stride, padding, dilation)
+    phi = _expand(bspline_basis(x, knots, spline_order))
+    z = base + F.conv2d(phi, w_spline, None, stride, padding, dilation)
+    return F.prelu(_norm(z, norm, eps, norm_weight, norm_bias), prelu_weight)
+
+
+def cheby_conv2d(x, w_poly, degree, stride=1, padding=0, dilation=1,
+                 norm="instance", eps=1e-5, norm_weight=None, norm_bias=None):
+    """One group of ChebyKANConvNDLayer.forward_ChebyKAN (cheby_kan_layers.py:91-101)."""
+    phi = _expand(cheby_basis(x, degree))
+    return _norm(F.conv2d(phi, w_poly, None, stride, padding, dilation), norm, eps, norm_weight, norm_bias)
+
+
+def gram_conv2d(x, w_base, w_poly, beta_weights, degree, stride=1, padding=0, dilation=1,
+                norm="instance", eps=1e-5, norm_weight=None, norm_bias=None):
+    """One group of GRAMKANConvNDLayer.forward_kag (gram_kan_layers.py:172-189); SiLU everywhere."""
+    base = F.conv2d(F.silu(x), w_base, None, stride, padding, dilation)
+    polys = gram_basis(torch.tanh(x), degree, beta_weights)
+    phi = F.silu(torch.cat(polys, dim=1))               # degree-major: channel d*C + c
+    z = F.conv2d(phi, w_poly, None, stride, padding, dilation) + base
+    return F.silu(_norm(z, norm, eps, norm_weight, norm_bias))
+
+
+def fastkan_conv2d(x, w_base, w_spline, grid, denominator, act="silu", stride=1, padding=0, dilation=1,
+                   norm="instance", eps=1e-5, norm_weight=None, norm_bias=None, running=None,
+                   training=True):
+    """One group of FastKANConvNDLayer.forward_fast_kan (fast_kan_layers.py:100-111).
+
+    NB the normalisation is applied to the *input* of the RBF branch; there is no output norm/act.
+    """
+    base = F.conv2d(_act(act)(x), w_base, None, stride, padding, dilation)
+    u = _norm(x, norm, eps, norm_weight, norm_bias, running, training)
+    phi = _expand(rbf_basis(u, grid, denominator))
+    return base + F.conv2d(phi, w_spline, None, stride, padding, dilation)
+
+
+# ----------------------------------------------------------------------------------------------
+# oracle modules (state_dict keys == reference keys)
+# ----------------------------------------------------------------------------------------------
+def _pair(v: IntOr2) -> Tuple[int, int]:
+    return (v, v) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _act_name(base_activation) -> Optional[str]:
+    if base_activation is None:
+        return None
+    if isinstance(base_activation, str):
+        return base_activation.lower()
+    n = getattr(base_activation, "__name__", type(base_activation).__name__).lower()
+    if n in ("gelu", "silu", "identity"):
+        return n
+    raise ValueError(f"oracle supports GELU/SiLU/Identity base activations, got {base_activation}")
+
+
+def _norm_kind(norm_layer) -> str:
+    if norm_layer is None:
+        return "none"
+    n = getattr(norm_layer, "__name__", str(norm_layer))
+    if "InstanceNorm" in n:
+        return "instance"
+    if "BatchNorm" in n:
+        return "batch"
+    raise ValueError(f"oracle supports InstanceNorm2d/BatchNorm2d, got {norm_layer}")
+
+
+class _Weight(nn.Module):
+    """Holder exposing ``.weight`` so keys read ``base_conv.0.weight`` like nn.Conv2d's."""
+
+    def __init__(self, shape):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(*shape))
+        # nn.Conv2d's own reset_parameters() draw, so that a same-seed construction consumes the RNG exactly
+        # like the reference ctor does before its explicit re-initialisation (kan_layers.py:159-195).
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+
+
+class _OracleBase(nn.Module):
+    def _check_groups(self, cin, cout, groups):
+        if groups <= 0:
+            raise ValueError("groups must be a positive integer")
+        if cin % groups != 0:
+            raise ValueError("input_dim must be divisible by groups")
+        if cout % groups != 0:
+            raise ValueError("output_dim must be divisible by groups")
+
+    def _make_norm(self, ch, kind, affine, groups):
+        mods = []
+        for _ in range(groups):
+            if kind == "instance":
+                mods.append(nn.InstanceNorm2d(ch, affine=affine))
+            elif kind == "batch":
+                mods.append(nn.BatchNorm2d(ch))
+            else:
+                mods.append(nn.Identity())
+        return nn.ModuleList(mods)
+
+    @staticmethod
+    def _nw(norm_mod):
+        return getattr(norm_mod, "weight", None), getattr(norm_mod, "bias", None)
+
+
+class OracleKANConv2D(_OracleBase):
+    def __init__(self, input_dim, output_dim, kernel_size, spline_order=3, groups=1, padding=0, stride=1,
+                 dilation=1, grid_size=5, base_activation="gelu", grid_range=(-1, 1), norm_layer=nn.InstanceNorm2d,
+                 affine=False):
+        super().__init__()
+        self._check_groups(input_dim, output_dim, groups)
+        kh, kw = _pair(kernel_size)
+        cg, og = input_dim // groups, output_dim // groups
+        self.groups, self.cg, self.og = groups, cg, og
+        self.spline_order, self.act = spline_order, _act_name(base_activation)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.norm_kind = _norm_kind(norm_layer)
+        self.base_conv = nn.ModuleList([_Weight((og, cg, kh, kw)) for _ in range(groups)])
+        self.spline_conv = nn.ModuleList([_Weight((og, cg * (grid_size + spline_order), kh, kw)) for _ in range(groups)])
+        self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
+        self.prelus = nn.ModuleList([nn.PReLU() for _ in range(groups)])
+        self.knots = make_knots(grid_size, spline_order, grid_range)   # plain attribute, like the reference
+        for m in list(self.base_conv) + list(self.spline_conv):
+            nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nw, nb = self._nw(self.layer_norm[g])
+            outs.append(kan_conv2d(xg, self.base_conv[g].weight, self.spline_conv[g].weight,
+                                   self.prelus[g].weight, self.knots, self.spline_order, self.act,
+                                   self.stride, self.padding, self.dilation, self.norm_kind,
+                                   1e-5, nw, nb))
+        return torch.cat(outs, dim=1)
+
+
+class OracleChebyKANConv2D(_OracleBase):
+    def __init__(self, input_dim, output_dim, kernel_size, degree=3, groups=1, padding=0, stride=1, dilation=1,
+                 norm_layer=nn.InstanceNorm2d, affine=False):
+        super().__init__()
+        self._check_groups(input_dim, output_dim, groups)
+        kh, kw = _pair(kernel_size)
+        cg, og = input_dim // groups, output_dim // groups
+        self.groups, self.cg, self.og, self.degree = groups, cg, og, degree
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.norm_kind = _norm_kind(norm_layer)
+        self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
+        self.poly_conv = nn.ModuleList([_Weight((og, (degree + 1) * cg, kh, kw)) for _ in range(groups)])
+        self.register_buffer("arange", torch.arange(0, degree + 1, 1).view(1, 1, -1, 1, 1))
+        for m in self.poly_conv:
+            nn.init.normal_(m.weight, mean=0.0, std=1 / (input_dim * (degree + 1) * kh * kw))   # overwritten next line
+            nn.init.kaiming_normal_(m.weight, mode="fan_in", nonlinearity="relu")
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nw, nb = self._nw(self.layer_norm[g])
+            outs.append(cheby_conv2d(xg, self.poly_conv[g].weight, self.degree, self.stride, self.padding,
+                                     self.dilation, self.norm_kind, 1e-5, nw, nb))
+        return torch.cat(outs, dim=1)
+
+
+class OracleGRAMKANConv2D(_OracleBase):
+    def __init__(self, input_dim, output_dim, kernel_size, degree=3, groups=1, padding=0, stride=1, dilation=1,
+                 norm_layer=nn.InstanceNorm2d, affine=False):
+        super().__init__()
+        self._check_groups(input_dim, output_dim, groups)
+        kh, kw = _pair(kernel_size)
+        cg, og = input_dim // groups, output_dim // groups
+        self.groups, self.cg, self.og, self.degree = groups, cg, og, degree
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.norm_kind = _norm_kind(norm_layer)
+        self.base_conv = nn.ModuleList([_Weight((og, cg, kh, kw)) for _ in range(groups)])
+        self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
+        self.poly_weights = nn.Parameter(torch.randn(groups, og, cg * (degree + 1), kh, kw))
+        self.beta_weights = nn.Parameter(torch.zeros(degree + 1))
+        for m in self.base_conv:
+            nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
+        nn.init.kaiming_uniform_(self.poly_weights, nonlinearity="linear")
+        nn.init.normal_(self.beta_weights, 0.0, 1.0 / (kh * kw * input_dim * (degree + 1.0)))
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nw, nb = self._nw(self.layer_norm[g])
+            outs.append(gram_conv2d(xg, self.base_conv[g].weight, self.poly_weights[g], self.beta_weights,
+                                    self.degree, self.stride, self.padding, self.dilation, self.norm_kind,
+                                    1e-5, nw, nb))
+        return torch.cat(outs, dim=1)
+
+
+class _RBF(nn.Module):
+    def __init__(self, lo, hi, n):
+        super().__init__()
+        self.grid = nn.Parameter(torch.linspace(lo, hi, n), requires_grad=False)
+        self.denominator = (hi - lo) / (n - 1)
+
+
+class OracleFastKANConv2D(_OracleBase):
+    def __init__(self, input_dim, output_dim, kernel_size, groups=1, padding=0, stride=1, dilation=1,
+                 grid_size=8, base_activation="silu", grid_range=(-2, 2), norm_layer=nn.InstanceNorm2d,
+                 affine=False):
+        super().__init__()
+        self._check_groups(input_dim, output_dim, groups)
+        kh, kw = _pair(kernel_size)
+        cg, og = input_dim // groups, output_dim // groups
+        self.groups, self.cg, self.og = groups, cg, og
+        self.act = _act_name(base_activation)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.norm_kind = _norm_kind(norm_layer)
+        self.base_conv = nn.ModuleList([_Weight((og, cg, kh, kw)) for _ in range(groups)])
+        self.spline_conv = nn.ModuleList([_Weight((og, grid_size * cg, kh, kw)) for _ in range(groups)])
+        self.layer_norm = self._make_norm(cg, self.norm_kind, affine, groups)   # sized by INPUT channels
+        self.rbf = _RBF(float(grid_range[0]), float(grid_range[1]), grid_size)
+        for m in list(self.base_conv) + list(self.spline_conv):
+            nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nm = self.layer_norm[g]
+            nw, nb = self._nw(nm)
+            running = None
+            if isinstance(nm, nn.BatchNorm2d):
+                running = (nm.running_mean, nm.running_var)
+            outs.append(fastkan_conv2d(xg, self.base_conv[g].weight, self.spline_conv[g].weight, self.rbf.grid,
+                                       self.rbf.denominator, self.act, self.stride, self.padding, self.dilation,
+                                       self.norm_kind, 1e-5, nw, nb, running, self.training))
+        return torch.cat(outs, dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# KAN-VGG (models/kan_vgg.py:29-188, 'kanconv' + Linear head) for the CPU baseline
+# ----------------------------------------------------------------------------------------------
+VGG_CFGS: Dict[str, List[Union[str, int]]] = {
+    # reference cfgs (models/kan_vgg.py:20-26) ...
+    "VGG16_small": [16, 16, "M", 32, 32, "M", 64, 64, 64, "M", 128, 128, 128, "M", 128, 128, 128],
+    "VGG16_kansmall": [8, 8, "M", 16, 16, "M", 32, 32, 32, "M", 64, 64, 64, "M", 64, 64, 64],
+    "VGG19_small": [16, 16, "M", 32, 32, "M", 64, 64, 64, 64, "M", 128, 128, 128, 128, "M", 128, 128, 128, 128],
+    "VGG16": [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512],
+    "VGG19": [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512],
+    # ... plus the VGG11 cfg BASELINE config 3 needs (absent upstream)
+    "VGG11": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512],
+}
+
+
+class OracleVGG(nn.Module):
+    """KAN-VGG with B-spline KAN convs (k=3, pad=1, SiLU base activation, InstanceNorm) + Linear head."""
+
+    def __init__(self, input_channels=3, num_classes=10, arch="VGG16", spline_order=3, grid_size=5,
+                 grid_range=(-1, 1), expected_feature_shape=(1, 1), dropout_linear=0.5, width_scale=1):
+        super().__init__()
+        layers: List[nn.Module] = []
+        c = input_channels
+        for v in VGG_CFGS[arch]:
+            if v == "M":
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                oc = int(v) * width_scale
+                layers.append(OracleKANConv2D(c, oc, 3, spline_order=spline_order, padding=1, grid_size=grid_size,
+                                              base_activation="silu", grid_range=grid_range))
+                c = oc
+        self.features = nn.ModuleList(layers)
+        self.avgpool = nn.AdaptiveAvgPool2d(expected_feature_shape)
+        self.classifier = nn.Sequential(nn.Dropout(p=dropout_linear),
+                                        nn.Linear(c * expected_feature_shape[0] * expected_feature_shape[1], num_classes))
+
+    def forward(self, x):
+        for m in self.features:
+            x = m(x)
+        return self.classifier(torch.flatten(self.avgpool(x), 1))
+
+
+def conv_flops(n, cin, cout, ho, wo, kh, kw, width, groups=1) -> float:
+    """SURVEY 8(d) shared formula: dense-equivalent FLOPs of ONE direction of one KAN conv layer."""
+    return 2.0 * n * ho * wo * cout * (cin // groups) * width * kh * kw

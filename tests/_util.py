@@ -1,0 +1,63 @@
+"""Shared helpers for the test-suite: golden-fixture loading and oracle construction."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from oracle import kan_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d}
+ORACLE_CTORS = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram": O.OracleGRAMKANConv2D,
+                "fast": O.OracleFastKANConv2D}
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        meta = json.loads(bytes(z["meta"]).decode())
+        self.name, self.kind, self.kwargs = name, meta["kind"], meta["kwargs"]
+        self.x = torch.from_numpy(z["x"])
+        self.g = torch.from_numpy(z["g"])
+        self.sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+        self.y64, self.dx64 = torch.from_numpy(z["y64"]), torch.from_numpy(z["dx64"])
+        self.y32, self.dx32 = torch.from_numpy(z["y32"]), torch.from_numpy(z["dx32"])
+        self.grad64 = {k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad64/")}
+        self.grad32 = {k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad32/")}
+
+    def ctor_kwargs(self, for_oracle):
+        kw = dict(self.kwargs)
+        if "norm_layer" in kw:
+            kw["norm_layer"] = NORMS[kw["norm_layer"]]
+        if not for_oracle and "base_activation" in kw:
+            kw["base_activation"] = {"gelu": nn.GELU, "silu": nn.SiLU, None: None}[kw["base_activation"]]
+        return kw
+
+    def oracle(self, dtype=torch.float64):
+        m = ORACLE_CTORS[self.kind](**self.ctor_kwargs(True))
+        m.load_state_dict(self.sd)
+        return m.to(dtype).train()
+
+
+def run_fwd_bwd(m, x, g):
+    for p in m.parameters():
+        p.grad = None
+    xx = x.detach().clone().requires_grad_(True)
+    y = m(xx)
+    y.backward(g)
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    return y.detach(), xx.grad.detach(), grads
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| (scale-relative max error)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    denom = float(b.abs().max())
+    return float((a - b).abs().max()) / (denom if denom > 0 else 1.0)

@@ -1,0 +1,118 @@
+"""The oracle (oracle/kan_oracle.py) against the golden fixtures generated from the live reference."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import kan_oracle as O
+from _util import GOLDEN, Golden, golden_names, rel_err, run_fwd_bwd
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_reference_fp64(name):
+    gd = Golden(name)
+    m = gd.oracle(torch.float64)
+    y, dx, grads = run_fwd_bwd(m, gd.x.double(), gd.g.double())
+    assert rel_err(y, gd.y64) < 1e-12
+    assert rel_err(dx, gd.dx64) < 1e-11
+    assert set(grads) == set(gd.grad64)
+    for k, v in gd.grad64.items():
+        assert rel_err(grads[k], v) < 1e-11, k
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_reference_fp32(name):
+    gd = Golden(name)
+    m = gd.oracle(torch.float32)
+    y, dx, grads = run_fwd_bwd(m, gd.x, gd.g)
+    assert rel_err(y, gd.y32) < 2e-6
+    assert rel_err(dx, gd.dx32) < 2e-5
+    for k, v in gd.grad32.items():
+        assert rel_err(grads[k], v) < 2e-5, k
+
+
+def test_state_dict_keys_match_reference():
+    for name in golden_names():
+        gd = Golden(name)
+        m = gd.oracle()
+        assert set(m.state_dict()) == set(gd.sd), name
+
+
+def test_bspline_known_answers():
+    knots = O.make_knots(5, 3, (-1, 1))
+    ref = torch.tensor([-2.2000000477, -1.8000000715, -1.4000000954, -1.0, -0.6000000238, -0.2000000179,
+                        0.2000000179, 0.6000000238, 1.0, 1.4000000954, 1.8000000715, 2.2000000477])
+    assert torch.allclose(knots, ref, atol=0, rtol=0)
+    x = torch.linspace(-1, 1, 101, dtype=torch.float64)
+    b = O.bspline_basis(x, knots, 3)
+    assert b.shape == (101, 8)
+    assert torch.allclose(b.sum(-1), torch.ones_like(x), atol=1e-6)       # partition of unity on [a, b]
+    b0 = O.bspline_basis(torch.tensor([0.0], dtype=torch.float64), knots, 3)[0]
+    assert torch.allclose(b0[2:6], torch.tensor([1 / 48, 23 / 48, 23 / 48, 1 / 48], dtype=torch.float64), atol=1e-6)
+    out = O.bspline_basis(torch.tensor([-2.3, 2.2000000477, 5.0], dtype=torch.float32), knots, 3)
+    assert float(out.abs().max()) == 0.0                                   # outside the half-open support
+    kn = O.bspline_basis(knots[3:4].double(), knots, 3)[0]                   # exactly on a knot: 1/6, 2/3, 1/6
+    assert torch.allclose(kn[0:3], torch.tensor([1 / 6, 2 / 3, 1 / 6], dtype=torch.float64), atol=1e-6)
+    assert torch.isnan(O.bspline_basis(torch.tensor([float("nan")]), knots, 3)).all()
+
+
+def test_cheby_closed_form():
+    x = torch.linspace(-3, 3, 61, dtype=torch.float64)
+    t = torch.tanh(x)
+    b = O.cheby_basis(x, 3)
+    assert torch.allclose(b[..., 0], torch.ones_like(t))
+    assert torch.allclose(b[..., 1], t, atol=1e-6)
+    assert torch.allclose(b[..., 2], 2 * t * t - 1, atol=1e-6)
+    assert torch.allclose(b[..., 3], 4 * t ** 3 - 3 * t, atol=1e-6)
+
+
+CONFIG1 = {
+    "kan_gelu": (lambda: O.OracleKANConv2D(3, 16, 3, spline_order=3, grid_size=5, padding=1, base_activation="gelu"), 3),
+    "kan_silu": (lambda: O.OracleKANConv2D(3, 16, 3, spline_order=3, grid_size=5, padding=1, base_activation="silu"), 3),
+    "cheby": (lambda: O.OracleChebyKANConv2D(8, 16, 3, degree=3, padding=1), 8),
+    "gram": (lambda: O.OracleGRAMKANConv2D(8, 16, 3, degree=3, padding=1), 8),
+    "fast": (lambda: O.OracleFastKANConv2D(8, 16, 3, padding=1), 8),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(CONFIG1))
+def test_config1_checksums(tag):
+    """BASELINE config 1 (README usage example) known-answer checksums, SURVEY Appendix E recipe.
+
+    Same seed => same weights as the reference ctor (RNG consumption order is mirrored)."""
+    with open(os.path.join(GOLDEN, "config1_checksums.json")) as f:
+        c = json.load(f)[tag]
+    ctor, cin = CONFIG1[tag]
+    torch.manual_seed(0)
+    m = ctor()
+    torch.manual_seed(1)
+    x = torch.randn(16, cin, 32, 32)
+    torch.manual_seed(2)
+    g = torch.randn(16, 16, 32, 32)
+    y, dx, grads = run_fwd_bwd(m.double(), x.double(), g.double())
+    assert abs(float(y.sum()) - c["y_sum"]) < 1e-7 * max(abs(c["y_sum"]), 1.0)
+    assert abs(float(y.norm()) - c["y_norm"]) < 1e-9 * c["y_norm"]
+    assert abs(float(dx.norm()) - c["dx_norm"]) < 1e-9 * c["dx_norm"]
+    for k, (s, n) in c["grads"].items():
+        assert abs(float(grads[k].norm()) - n) < 1e-8 * max(n, 1e-30), k
+    if tag == "kan_gelu":      # survey-published values (Appendix E) for the same recipe
+        assert abs(float(y.sum()) - 7.785452738e+04) < 1e-3
+        assert abs(float(dx.norm()) - 5.755363489e+02) < 1e-5
+
+
+def test_group_validation_errors():
+    with pytest.raises(ValueError):
+        O.OracleKANConv2D(4, 4, 3, groups=0)
+    with pytest.raises(ValueError):
+        O.OracleKANConv2D(3, 4, 3, groups=2)
+    with pytest.raises(ValueError):
+        O.OracleChebyKANConv2D(4, 3, 3, groups=2)
+
+
+def test_oracle_vgg_shapes():
+    torch.manual_seed(0)
+    m = O.OracleVGG(3, 10, arch="VGG16_kansmall", dropout_linear=0.0)
+    y = m(torch.randn(2, 3, 32, 32))
+    assert y.shape == (2, 10)
+    y.sum().backward()
