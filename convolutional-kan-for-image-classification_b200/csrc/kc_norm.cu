@@ -1,0 +1,322 @@
+// kc_norm.cu - Instance/Batch normalisation fused with the output activation (PReLU / SiLU), forward and backward.
+// Replaces native_batch_norm + prelu/silu (+ their backward ops) of kan_layers.py:241-243, gram_kan_layers.py:187,
+// cheby_kan_layers.py:98 and the input norm of fast_kan_layers.py:106.  HBM-bound: each plane is read from HBM once
+// (the later passes over the same plane hit L2, the plane is <= 200 KB) and written once; 16-byte accesses,
+// warp-shuffle + shared-memory block reductions.
+#include "kc_common.cuh"
+
+namespace {
+
+constexpr int kNT = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  // all threads of the block must call; returns the total to every thread
+  v = kc_warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0f;
+  if (wid == 0) {
+    t = kc_warp_sum(t);
+    if (lane == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__device__ __forceinline__ float out_act(int kind, float v, float alpha) {
+  if (kind == KC_OUT_PRELU) return v > 0.0f ? v : alpha * v;
+  if (kind == KC_OUT_SILU) return kc_silu(v);
+  return v;
+}
+__device__ __forceinline__ float out_act_grad(int kind, float v, float alpha) {
+  if (kind == KC_OUT_PRELU) return v > 0.0f ? 1.0f : alpha;
+  if (kind == KC_OUT_SILU) return kc_silu_grad(v);
+  return 1.0f;
+}
+
+// ---- generic strided plane iteration helpers (vectorised when aligned) ----------------------------------
+template <typename F>
+__device__ __forceinline__ void plane_foreach(const float* __restrict__ p, int hw, bool vec, F f) {
+  if (vec) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    for (int i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
+      float4 v = p4[i];
+      f(v.x); f(v.y); f(v.z); f(v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) f(p[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plane statistics: mean and M2 = sum (z-mean)^2 of plane (n, c).   One block per plane.
+// Instance norm: finalised in the same kernel (and y written).  Batch norm: plane stats are combined per channel.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT)
+kc_instnorm_fwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ z,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* __restrict__ alpha_p, float* __restrict__ y, float* __restrict__ mean_out,
+                       float* __restrict__ rstd_out) {
+  __shared__ float sh[32];
+  const int plane = blockIdx.x;              // n * c + ch
+  const int n = plane / d.c, ch = plane % d.c;
+  const long long off = (long long)n * d.batch_stride + (long long)ch * d.hw;
+  const float* zp = z + off;
+  float* yp = y + off;
+  const bool vec = ((d.hw & 3) == 0) && ((off & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  float mean = 0.0f, rstd = 1.0f;
+  if (d.norm == KC_NORM_INSTANCE) {
+    float s = 0.0f;
+    plane_foreach(zp, d.hw, vec, [&](float v) { s += v; });
+    mean = block_sum(s, sh) / (float)d.hw;
+    float m2 = 0.0f;
+    plane_foreach(zp, d.hw, vec, [&](float v) { float t = v - mean; m2 = fmaf(t, t, m2); });
+    float var = block_sum(m2, sh) / (float)d.hw;     // biased variance, like F.instance_norm
+    rstd = rsqrtf(var + d.eps);
+    if (threadIdx.x == 0) { mean_out[plane] = mean; rstd_out[plane] = rstd; }
+  } else if (d.norm == KC_NORM_BATCH) {
+    mean = mean_out[ch]; rstd = rstd_out[ch];
+  }
+  const float g = (d.affine && gamma) ? gamma[ch] : 1.0f;
+  const float b = (d.affine && beta) ? beta[ch] : 0.0f;
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  const float sc = rstd * g, sh0 = b - mean * rstd * g;
+  if (vec) {
+    const float4* z4 = reinterpret_cast<const float4*>(zp);
+    float4* y4 = reinterpret_cast<float4*>(yp);
+    for (int i = threadIdx.x; i < (d.hw >> 2); i += blockDim.x) {
+      float4 v = z4[i], o;
+      o.x = out_act(d.out_act, fmaf(v.x, sc, sh0), alpha);
+      o.y = out_act(d.out_act, fmaf(v.y, sc, sh0), alpha);
+      o.z = out_act(d.out_act, fmaf(v.z, sc, sh0), alpha);
+      o.w = out_act(d.out_act, fmaf(v.w, sc, sh0), alpha);
+      y4[i] = o;
+    }
+  } else {
+    for (int i = threadIdx.x; i < d.hw; i += blockDim.x) yp[i] = out_act(d.out_act, fmaf(zp[i], sc, sh0), alpha);
+  }
+}
+
+// Batch norm step 1: per-plane mean and M2 (block per plane) -> partials[0][plane], partials[1][plane]
+__global__ void __launch_bounds__(kNT)
+kc_plane_stats_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ z, float* __restrict__ pmean,
+                      float* __restrict__ pm2) {
+  __shared__ float sh[32];
+  const int plane = blockIdx.x, n = plane / d.c, ch = plane % d.c;
+  const long long off = (long long)n * d.batch_stride + (long long)ch * d.hw;
+  const float* zp = z + off;
+  const bool vec = ((d.hw & 3) == 0) && ((off & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+  float s = 0.0f;
+  plane_foreach(zp, d.hw, vec, [&](float v) { s += v; });
+  float mean = block_sum(s, sh) / (float)d.hw;
+  float m2 = 0.0f;
+  plane_foreach(zp, d.hw, vec, [&](float v) { float t = v - mean; m2 = fmaf(t, t, m2); });
+  m2 = block_sum(m2, sh);
+  if (threadIdx.x == 0) { pmean[plane] = mean; pm2[plane] = m2; }
+}
+
+// Batch norm step 2: combine the n plane statistics of each channel (Chan et al.), one warp per channel.
+__global__ void kc_batch_stats_combine_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ pmean,
+                                              const float* __restrict__ pm2, float* __restrict__ mean_out,
+                                              float* __restrict__ rstd_out) {
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (ch >= d.c) return;
+  float s = 0.0f;
+  for (int n = lane; n < d.n; n += 32) s += pmean[n * d.c + ch];
+  float gmean = kc_warp_sum(s) / (float)d.n;
+  float m2 = 0.0f;
+  for (int n = lane; n < d.n; n += 32) {
+    float dm = pmean[n * d.c + ch] - gmean;
+    m2 += pm2[n * d.c + ch] + dm * dm * (float)d.hw;
+  }
+  float var = kc_warp_sum(m2) / ((float)d.n * (float)d.hw);
+  if (lane == 0) { mean_out[ch] = gmean; rstd_out[ch] = rsqrtf(var + d.eps); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward.  v = gamma*zhat + beta, y = act(v).   dv = dy*act'(v);  dzhat = dv*gamma;
+//   dz = rstd * (dzhat - mean_G(dzhat) - zhat * mean_G(dzhat*zhat)),  G = plane (instance) | channel over n (batch)
+//   partials[0][plane] = sum dv*zhat (-> dgamma), [1] = sum dv (-> dbeta), [2] = sum dy*v*[v<=0] (-> dalpha)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT)
+kc_norm_bwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ dy, const float* __restrict__ z,
+                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha_p,
+                   float* __restrict__ dz, float* __restrict__ partials, const float* __restrict__ chan_sums,
+                   int phase) {
+  // phase 0: instance norm, everything in one kernel.  phase 1: batch norm, partial sums only.
+  // phase 2: batch norm, write dz using the per-channel sums in chan_sums[0][c] (sum dzhat), [1][c] (sum dzhat*zhat).
+  __shared__ float sh[32];
+  const int plane = blockIdx.x, n = plane / d.c, ch = plane % d.c;
+  const long long off = (long long)n * d.batch_stride + (long long)ch * d.hw;
+  const float* zp = z + off;
+  const float* gp = dy + off;
+  float* dzp = dz + off;
+  const int NP = d.n * d.c;
+  const bool vec = ((d.hw & 3) == 0) && ((off & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dz) & 15) == 0);
+  float mean = 0.0f, rstd = 1.0f;
+  if (d.norm == KC_NORM_INSTANCE) { mean = mean_in[plane]; rstd = rstd_in[plane]; }
+  else if (d.norm == KC_NORM_BATCH) { mean = mean_in[ch]; rstd = rstd_in[ch]; }
+  const float g = (d.affine && gamma) ? gamma[ch] : 1.0f;
+  const float b = (d.affine && beta) ? beta[ch] : 0.0f;
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  const int kind = d.out_act;
+
+  float s_dvz = 0.0f, s_dv = 0.0f, s_da = 0.0f;
+  if (phase != 2) {
+    auto accum = [&](float zz, float gg) {
+      float zh = (zz - mean) * rstd;
+      float v = fmaf(zh, g, b);
+      float dv = gg * out_act_grad(kind, v, alpha);
+      s_dvz = fmaf(dv, zh, s_dvz);
+      s_dv += dv;
+      if (kind == KC_OUT_PRELU && !(v > 0.0f)) s_da = fmaf(gg, v, s_da);
+    };
+    if (vec) {
+      const float4* z4 = reinterpret_cast<const float4*>(zp);
+      const float4* g4 = reinterpret_cast<const float4*>(gp);
+      for (int i = threadIdx.x; i < (d.hw >> 2); i += blockDim.x) {
+        float4 a = z4[i], c = g4[i];
+        accum(a.x, c.x); accum(a.y, c.y); accum(a.z, c.z); accum(a.w, c.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < d.hw; i += blockDim.x) accum(zp[i], gp[i]);
+    }
+    s_dvz = block_sum(s_dvz, sh);
+    s_dv = block_sum(s_dv, sh);
+    s_da = block_sum(s_da, sh);
+    if (threadIdx.x == 0) {
+      partials[plane] = s_dvz;
+      partials[NP + plane] = s_dv;
+      partials[2 * NP + plane] = s_da;
+    }
+    if (phase == 1) return;
+  }
+  float m1, m2;     // mean_G(dzhat), mean_G(dzhat*zhat)
+  if (d.norm == KC_NORM_NONE) { m1 = 0.0f; m2 = 0.0f; }
+  else if (phase == 0) { m1 = s_dv * g / (float)d.hw; m2 = s_dvz * g / (float)d.hw; }
+  else {
+    float cnt = (float)d.n * (float)d.hw;
+    m1 = chan_sums[ch] * g / cnt; m2 = chan_sums[d.c + ch] * g / cnt;
+  }
+  auto grad = [&](float zz, float gg) -> float {
+    float zh = (zz - mean) * rstd;
+    float v = fmaf(zh, g, b);
+    float dzh = gg * out_act_grad(kind, v, alpha) * g;
+    return rstd * (dzh - m1 - zh * m2);
+  };
+  if (vec) {
+    const float4* z4 = reinterpret_cast<const float4*>(zp);
+    const float4* g4 = reinterpret_cast<const float4*>(gp);
+    float4* o4 = reinterpret_cast<float4*>(dzp);
+    for (int i = threadIdx.x; i < (d.hw >> 2); i += blockDim.x) {
+      float4 a = z4[i], c = g4[i], o;
+      o.x = grad(a.x, c.x); o.y = grad(a.y, c.y); o.z = grad(a.z, c.z); o.w = grad(a.w, c.w);
+      o4[i] = o;
+    }
+  } else {
+    for (int i = threadIdx.x; i < d.hw; i += blockDim.x) dzp[i] = grad(zp[i], gp[i]);
+  }
+}
+
+// Reduce per-plane partials over n: out[0][c] = sum_n partials[0][n][c], out[1][c] likewise, out[2][0] = sum all [2].
+// One block per channel, plus block index c for the alpha total.  Fixed summation order (deterministic).
+__global__ void __launch_bounds__(kNT)
+kc_partials_reduce_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ partials,
+                          float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2) {
+  __shared__ float sh[32];
+  const int NP = d.n * d.c;
+  if ((int)blockIdx.x < d.c) {
+    const int ch = blockIdx.x;
+    float a = 0.0f, b = 0.0f;
+    for (int n = threadIdx.x; n < d.n; n += blockDim.x) {
+      a += partials[n * d.c + ch];
+      b += partials[NP + n * d.c + ch];
+    }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) {
+      if (out0) out0[ch] = a;
+      if (out1) out1[ch] = b;
+    }
+  } else {
+    float a = 0.0f;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) a += partials[2 * NP + i];
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0 && out2) out2[0] = a;
+  }
+}
+
+int check_norm_desc(const kc_norm_desc* d) {
+  if (!d) KC_FAIL(KC_ERR_INVALID, "null kc_norm_desc");
+  if (d->n <= 0 || d->c <= 0 || d->hw <= 0) KC_FAIL(KC_ERR_INVALID, "kc_norm_desc: n, c, hw must be positive");
+  if (d->batch_stride < (long long)d->c * d->hw) KC_FAIL(KC_ERR_INVALID, "kc_norm_desc: batch_stride < c*hw");
+  if (d->norm < KC_NORM_NONE || d->norm > KC_NORM_BATCH) KC_FAIL(KC_ERR_INVALID, "kc_norm_desc: bad norm kind");
+  if (d->out_act < KC_OUT_NONE || d->out_act > KC_OUT_SILU) KC_FAIL(KC_ERR_INVALID, "kc_norm_desc: bad out_act kind");
+  return KC_OK;
+}
+
+}  // namespace
+
+extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const float* gamma, const float* beta,
+                               const float* alpha, float* y, float* mean, float* rstd, float* scratch, void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc != KC_OK) return rc;
+  if (!z || !y) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: null pointer");
+  if (d->norm != KC_NORM_NONE && (!mean || !rstd)) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: mean/rstd buffers required");
+  if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: PReLU needs alpha");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = d->n * d->c;
+  if (d->norm == KC_NORM_BATCH) {
+    if (!scratch) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: batch norm needs a 2*n*c float scratch buffer");
+    float* pmean = scratch;
+    float* pm2 = scratch + planes;
+    kc_plane_stats_kernel<<<planes, kNT, 0, st>>>(*d, z, pmean, pm2);
+    KC_LAUNCH_CHECK("kc_plane_stats_kernel");
+    kc_batch_stats_combine_kernel<<<(d->c + 7) / 8, 256, 0, st>>>(*d, pmean, pm2, mean, rstd);
+    KC_LAUNCH_CHECK("kc_batch_stats_combine_kernel");
+  }
+  kc_instnorm_fwd_kernel<<<planes, kNT, 0, st>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
+  KC_LAUNCH_CHECK("kc_instnorm_fwd_kernel");
+  return KC_OK;
+}
+
+extern "C" int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, const float* mean,
+                               const float* rstd, const float* gamma, const float* beta, const float* alpha,
+                               float* dz, float* dgamma, float* dbeta, float* dalpha, float* partials, void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc != KC_OK) return rc;
+  if (!dy || !z || !dz || !partials) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: null pointer");
+  if (d->norm != KC_NORM_NONE && (!mean || !rstd)) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: mean/rstd required");
+  if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: PReLU needs alpha");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = d->n * d->c;
+  if (d->norm == KC_NORM_BATCH) {
+    // partials layout: [3][planes] plane sums, then [2][c] channel sums
+    float* chan = partials + 3 * (size_t)planes;
+    kc_norm_bwd_kernel<<<planes, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 1);
+    KC_LAUNCH_CHECK("kc_norm_bwd_kernel(phase1)");
+    // chan[0][c] = sum dv*zhat, chan[1][c] = sum dv ; kernel phase 2 expects [0] = sum dzhat (=dv) and [1] = sum dzhat*zhat,
+    // both up to the factor gamma applied inside the kernel -> pass them swapped.
+    kc_partials_reduce_kernel<<<d->c + 1, kNT, 0, st>>>(*d, partials, chan + d->c, chan, dalpha);
+    KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
+    kc_norm_bwd_kernel<<<planes, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, chan, 2);
+    KC_LAUNCH_CHECK("kc_norm_bwd_kernel(phase2)");
+    if (dgamma || dbeta) {
+      kc_partials_reduce_kernel<<<d->c, kNT, 0, st>>>(*d, partials, dgamma, dbeta, nullptr);
+      KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
+    }
+  } else {
+    kc_norm_bwd_kernel<<<planes, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 0);
+    KC_LAUNCH_CHECK("kc_norm_bwd_kernel");
+    if (dgamma || dbeta || dalpha) {
+      kc_partials_reduce_kernel<<<d->c + 1, kNT, 0, st>>>(*d, partials, dgamma, dbeta, dalpha);
+      KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
+    }
+  }
+  return KC_OK;
+}

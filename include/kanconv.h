@@ -1,0 +1,153 @@
+/* kanconv.h - C ABI of libkanconv.so: the KAN-convolution hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (GadGadGad/Convolutional-KAN-for-Image-Classification) is pure eager PyTorch and has NO native
+ * interface of its own.  This header therefore defines the boundary a native replacement
+ * has to offer underneath the reference's Python plugin API (layers/kan_conv.py:726-745, CONV_KAN_FACTORY):
+ * each entry point below replaces the arithmetic of the reference lines cited next to it.  All pointers are raw
+ * device pointers owned by the caller (PyTorch's caching allocator in the Python binding); the library allocates
+ * nothing persistent, is re-entrant, takes the CUDA stream explicitly and never throws across the ABI.
+ *
+ * Conventions
+ *   - activations are fp32 NCHW; one call handles ONE group of a grouped layer: `cin`/`cout` are per-group
+ *     channel counts and `x_batch_stride` / `z_batch_stride` (in elements) let the caller point into the
+ *     channel slice of the full tensor (the reference loops over groups in Python, kan_layers.py:249-258).
+ *   - weights are fp32 in the reference's own parameter layout, so state_dicts are
+ *     interchangeable.  `w_basis` inner index: c*nb+j (B-spline, Chebyshev, RBF) or j*cin+c (Gram).
+ *   - return value: KC_OK, or a negative kc_status; kc_last_error() gives the message of the calling thread.
+ *     KC_ERR_UNSUPPORTED means "this entry point cannot run this shape" - the binding raises NotImplementedError;
+ *     there is no CPU or library fallback behind any entry point.
+ */
+#ifndef KANCONV_H_
+#define KANCONV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_ABI_VERSION 1
+#define KC_MAX_BASIS 16   /* max basis width nb  (G+K, D+1 or G)      */
+#define KC_MAX_PARAMS 40  /* knots / rbf grid etc. carried in kc_desc */
+
+typedef enum kc_status {
+  KC_OK = 0,
+  KC_ERR_INVALID = -1,      /* bad argument (binding raises ValueError)           */
+  KC_ERR_UNSUPPORTED = -2,  /* shape not covered by this entry point               */
+  KC_ERR_CUDA = -3          /* CUDA runtime error, message in kc_last_error()      */
+} kc_status;
+
+typedef enum kc_basis_kind {
+  KC_BASIS_BSPLINE = 0, /* KANConvNDLayer      layers/kan_layers.py:203-233  (Cox-de Boor)               */
+  KC_BASIS_CHEBY = 1,   /* ChebyKANConvNDLayer layers/cheby_kan_layers.py:93-96                          */
+  KC_BASIS_GRAM = 2,    /* GRAMKANConvNDLayer  layers/gram_kan_layers.py:150-181 (SiLU of Gram polys)    */
+  KC_BASIS_RBF = 3      /* FastKANConvNDLayer  utils/utils.py:19-33 (Gaussian RBF)                       */
+} kc_basis_kind;
+
+typedef enum kc_act_kind {
+  KC_ACT_NONE = -1,    /* layer has no base branch (Chebyshev)                              */
+  KC_ACT_IDENTITY = 0, /* base_activation=None -> nn.Identity  (kan_layers.py:132)          */
+  KC_ACT_GELU = 1,     /* exact erf GELU (layer default, kan_layers.py:276)                 */
+  KC_ACT_SILU = 2      /* model default (models/kan_vgg.py:47)                              */
+} kc_act_kind;
+
+typedef enum kc_norm_kind { KC_NORM_NONE = 0, KC_NORM_INSTANCE = 1, KC_NORM_BATCH = 2 } kc_norm_kind;
+typedef enum kc_out_act_kind { KC_OUT_NONE = 0, KC_OUT_PRELU = 1, KC_OUT_SILU = 2 } kc_out_act_kind;
+
+/* Geometry + basis description of ONE group of one KAN convolution layer (plain data, no pointers). */
+typedef struct kc_desc {
+  int32_t basis;              /* kc_basis_kind                                                     */
+  int32_t act;                /* kc_act_kind of the base branch                                    */
+  int32_t n, cin, h, w;       /* input  [n, cin, h, w]   (cin per group)                           */
+  int32_t cout, ho, wo;       /* output [n, cout, ho, wo] (cout per group)                         */
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int32_t nb;                 /* basis width: G+K | D+1 | G                                        */
+  int32_t order;              /* spline order K | polynomial degree D | unused                     */
+  int32_t nparams;            /* B-spline: G+2K+1 knots; RBF: G grid points then the denominator   */
+  int64_t x_batch_stride;     /* elements between images of x   (>= cin*h*w)                       */
+  int64_t z_batch_stride;     /* elements between images of z/dz (>= cout*ho*wo)                   */
+  float params[KC_MAX_PARAMS];
+} kc_desc;
+
+/* Row-wise normalisation + output activation over [n, c, hw] planes (kan_layers.py:241-243). */
+typedef struct kc_norm_desc {
+  int32_t norm;        /* kc_norm_kind     */
+  int32_t out_act;     /* kc_out_act_kind  */
+  int32_t n, c, hw;
+  int32_t affine;      /* gamma/beta present */
+  int64_t batch_stride;/* elements between images (>= c*hw) for z, y, dy, dz alike */
+  float eps;
+} kc_norm_desc;
+
+int kc_version(void);
+const char* kc_last_error(void);
+/* Number of SMs / compute capability of the current device, for the binding's sanity check (returns KC_OK). */
+int kc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * FP32 path (CUDA-core FFMA, fp32 accumulate): any kernel size / stride / dilation / padding, nb <= 16.
+ * Parity target: <= 1e-5 relative to the reference fp32 modules.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* z = conv(act(x_base), w_base) + conv(basis(x_basis), w_basis)       [kan_layers.py:199-241; cheby:93-97;
+ * gram:173-186; fast:103-109].  x_basis == x_base except for FastKAN (basis of the normalised input).
+ * w_base may be NULL iff desc->act == KC_ACT_NONE.  `beta` = GRAM beta_weights[D+1] (device), else NULL. */
+int kc_conv_fwd_f32(const kc_desc* d, const float* x_base, const float* x_basis, const float* w_base,
+                    const float* w_basis, const float* beta, float* z, void* stream);
+
+/* Input gradient.  dx_base/dx_basis receive the base-branch and basis-branch parts; if they are the same pointer
+ * the sum is written once.  `dbeta` (GRAM only, [D+1], must be zeroed by the caller) accumulates d/d beta_weights.
+ * Replaces autograd's backward of kan_layers.py:199-239 (the reference has no hand-written backward). */
+int kc_conv_dgrad_f32(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
+                      const float* w_base, const float* w_basis, const float* beta, float* dx_base,
+                      float* dx_basis, float* dbeta, void* stream);
+
+/* Weight gradients in the reference layouts.  `workspace` must hold kc_wgrad_workspace_bytes(d) bytes. */
+size_t kc_wgrad_workspace_bytes(const kc_desc* d);
+int kc_conv_wgrad_f32(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
+                      const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Normalisation + output activation (memory-bound, vectorised):  y = out_act(gamma * (z-mean)*rstd + beta)
+ * [kan_layers.py:242-243, gram:187, cheby:98; fast:106 uses it on the INPUT with out_act = NONE].
+ * mean/rstd are [n*c] (instance) or [c] (batch) and are outputs of fwd / inputs of bwd.
+ * alpha = PReLU weight (1 element, device).  bwd writes dz and per-plane partials that it then reduces into
+ * dgamma[c], dbeta[c], dalpha[1] (any of which may be NULL).  `partials` needs 3*n*c + 2*c floats.
+ * fwd `scratch` (2*n*c floats) is only used for KC_NORM_BATCH (per-plane statistics) and may be NULL otherwise.
+ * ------------------------------------------------------------------------------------------------------- */
+int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const float* gamma, const float* beta,
+                    const float* alpha, float* y, float* mean, float* rstd, float* scratch, void* stream);
+int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, const float* alpha, float* dz, float* dgamma,
+                    float* dbeta, float* dalpha, float* partials, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BF16 tensor-core path (tcgen05.mma, fp32 accumulate in TMEM).  Stride 1, dilation 1, nb in {4, 8},
+ * cin % 8 == 0 after the binding's zero padding.  kc_tc_supported() tells the binding which path a shape takes.
+ * Parity target: <= 2e-2 relative / 1e-3 absolute to the reference fp32 modules.
+ * ------------------------------------------------------------------------------------------------------- */
+int kc_tc_supported(const kc_desc* d);
+/* Bytes of the packed bf16 weight images for the forward (which=0), dgrad (1) kernels, and of the wgrad split
+ * workspace (2). */
+size_t kc_tc_bytes(const kc_desc* d, int which);
+/* fp32 reference-layout weights -> bf16 UMMA-canonical K-block images (once per optimizer step). */
+int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const float* w_basis, void* packed_fwd,
+                       void* packed_dgrad, void* stream);
+int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float* x_basis, const void* packed_fwd,
+                   const float* beta, float* z, void* stream);
+int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
+                     const void* packed_dgrad, const float* beta, float* dx_base, float* dx_basis, float* dbeta,
+                     void* workspace, void* stream);
+int kc_conv_wgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
+                     const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream);
+
+/* Self-test of the tcgen05 shared-memory descriptor conventions this library relies on: runs a 128xNx64 bf16 GEMM
+ * through the same UMMA helpers as the convolution kernels and returns the max abs error against a CUDA-core
+ * evaluation of the same product (expected < 1e-2).  mode 0 = K-major A/B, 1 = MN-major A/B. */
+int kc_tc_selftest(int mode, float* max_abs_err, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KANCONV_H_ */

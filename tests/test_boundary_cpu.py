@@ -1,0 +1,112 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol of include/kanconv.h,
+descriptor structs match the header, modules mirror the reference's state_dict / RNG behaviour, errors are raised
+like upstream, and the product refuses CPU tensors (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+
+import kanconv_b200 as K
+from kanconv_b200 import _lib as L
+from _util import Golden, golden_names
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer}
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    header = open(os.path.join(ROOT, "include", "kanconv.h")).read()
+    declared = set(re.findall(r"\b(kc_[a-z0-9_]+)\s*\(", header))
+    declared -= {"kc_desc", "kc_norm_desc"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libkanconv.so does not export {name}"
+    assert set(L.EXPORTED_SYMBOLS) == declared
+    assert lib.kc_version() == 1
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(L.KcDesc) == 20 * 4 + 2 * 8 + 4 * L.KC_MAX_PARAMS
+    assert L.KcDesc.x_batch_stride.offset == 80
+    assert ctypes.sizeof(L.KcNormDesc) == 40
+    assert L.KcNormDesc.batch_stride.offset == 24
+
+
+def test_desc_validation_through_abi():
+    lib = L.load()
+    d = L.KcDesc()
+    assert lib.kc_tc_supported(ctypes.byref(d)) == 0          # all-zero descriptor is invalid
+    assert lib.kc_wgrad_workspace_bytes(ctypes.byref(d)) == 0
+    rc = lib.kc_conv_fwd_f32(ctypes.byref(d), None, None, None, None, None, None, None)
+    assert rc == L.KC_ERR_INVALID and b"kc_desc" in lib.kc_last_error()
+    with pytest.raises(ValueError):
+        L.check(rc, "kc_conv_fwd_f32")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_state_dict_compatible_with_reference(name):
+    gd = Golden(name)
+    m = CTORS[gd.kind](**gd.ctor_kwargs(False))
+    sd = m.state_dict()
+    assert set(sd) == set(gd.sd)
+    for k, v in gd.sd.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    m.load_state_dict(gd.sd)                                   # strict
+
+
+@pytest.mark.parametrize("name", ["kan_small", "kan_silu_groups_s2", "cheby_small", "fast_small", "kan_c8_16"])
+def test_same_seed_same_weights_as_reference(name):
+    """Construction consumes the RNG like the reference ctor, so seed 0 reproduces the fixture's weights exactly."""
+    gd = Golden(name)
+    torch.manual_seed(0)
+    m = CTORS[gd.kind](**gd.ctor_kwargs(False))
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, gd.sd[k]), k
+
+
+def test_reference_error_conventions():
+    with pytest.raises(ValueError, match="groups must be a positive integer"):
+        K.KANConv2DLayer(4, 4, 3, groups=0)
+    with pytest.raises(ValueError, match="input_dim must be divisible by groups"):
+        K.ChebyKANConv2DLayer(3, 4, 3, groups=2)
+    with pytest.raises(ValueError, match="output_dim must be divisible by groups"):
+        K.FastKANConv2DLayer(4, 3, 3, groups=2)
+    with pytest.raises(ValueError):
+        K.GRAMKANConv2DLayer(4, 3, 3, groups=2)
+
+
+def test_no_cpu_fallback():
+    m = K.KANConv2DLayer(3, 4, 3, padding=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 3, 5, 5))
+
+
+def test_factory_mirrors_reference():
+    import sys
+    _same_padding = sys.modules["kanconv_b200.layers.kan_conv"]._calculate_same_padding
+    f = K.CONV_KAN_FACTORY
+    for key in ("KAN", "FastKAN", "GRAMKAN", "ChebyKAN", "conv"):
+        assert key in f
+    layer = f["KAN"](3, 8, 3)                                   # padding=None -> 'same'
+    assert isinstance(layer, K.KANConv2DLayer) and layer.padding == 1
+    assert _same_padding(3, 1) == 1 and _same_padding((3, 5), 1) == (1, 2)
+    assert _same_padding(3, 2) == 2
+    wrapped = f["ChebyKAN"](4, 4, 3, l1_decay=1e-4)
+    assert type(wrapped).__name__ == "L1" and isinstance(wrapped.module, K.ChebyKANConv2DLayer)
+    # extra kwargs are swallowed by **norm_kwargs and filtered against the norm signature, like upstream
+    layer = f["KAN"](3, 8, 3, affine=True, degree=7, base_activation=nn.SiLU)
+    assert layer.layer_norm[0].affine
+    with pytest.raises(NotImplementedError):
+        f["LegendreKAN"](3, 8, 3)
+    assert isinstance(f["conv"](3, 8, 3), nn.Conv2d)
+
+
+def test_modules_are_picklable():
+    import pickle
+    m = K.FastKANConv2DLayer(4, 4, 3, padding=1)
+    m2 = pickle.loads(pickle.dumps(m))
+    assert set(m2.state_dict()) == set(m.state_dict())

@@ -1,0 +1,122 @@
+"""GPU parity: the CUDA path (through the nn.Module drop-ins -> ctypes -> C ABI) against the golden fixtures generated
+from the reference and against the CPU oracle.  Tolerances (BASELINE north_star): FP32 path <= 1e-5, BF16 tensor-core
+path <= 2e-2, both as max|a-b| / max|b| (scale-relative max error) on outputs, dX and every parameter gradient."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn as nn
+
+import kanconv_b200 as K
+from kanconv_b200 import _lib as L
+from oracle import kan_oracle as O
+from _util import Golden, golden_names, rel_err, run_fwd_bwd
+
+pytestmark = pytest.mark.gpu
+CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer}
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+def _module(gd, precision):
+    m = CTORS[gd.kind](**gd.ctor_kwargs(False))
+    m.load_state_dict(gd.sd)
+    m = m.cuda().train()
+    m.precision = precision
+    return m
+
+
+def test_device_is_blackwell():
+    lib = L.load()
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.kc_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)) == 0
+    assert major.value == 10, f"expected an sm_100 device, got {major.value}.{minor.value}"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_umma_descriptor_selftest(mode):
+    lib = L.load()
+    err = ctypes.c_float(-1.0)
+    L.check(lib.kc_tc_selftest(mode, ctypes.byref(err), None), "kc_tc_selftest")
+    print(f"selftest mode {mode}: max abs err {err.value}")
+    assert 0.0 <= err.value < 1e-2
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp32_path_matches_reference_golden(name):
+    gd = Golden(name)
+    m = _module(gd, "fp32")
+    y, dx, grads = run_fwd_bwd(m, gd.x.cuda(), gd.g.cuda())
+    assert rel_err(y, gd.y64) < FP32_TOL
+    assert rel_err(dx, gd.dx64) < FP32_TOL
+    assert set(grads) == set(gd.grad64)
+    for k, v in gd.grad64.items():
+        assert rel_err(grads[k], v) < FP32_TOL, k
+
+
+TC_CASES = ["kan_small", "kan_c8_16", "kan_batchnorm", "cheby_small", "gram_small", "fast_small", "kan_g3k2_1x1",
+            "fast_bn_g5_1x1"]
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_bf16_tensor_core_forward_matches_reference_golden(name):
+    gd = Golden(name)
+    m = _module(gd, "auto")
+    lib = L.load()
+    with torch.no_grad():
+        y = m(gd.x.cuda())
+    e = rel_err(y, gd.y64)
+    print(f"{name}: bf16 forward rel err {e:.3e}")
+    assert e < BF16_TOL
+
+
+def _oracle_and_module(kind, okw, mkw):
+    torch.manual_seed(0)
+    mod = CTORS[kind](**mkw)
+    ora = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram": O.OracleGRAMKANConv2D,
+           "fast": O.OracleFastKANConv2D}[kind](**okw)
+    ora.load_state_dict(mod.state_dict())
+    return ora.double(), mod.cuda()
+
+
+def test_baseline_config1_fp32():
+    """BASELINE config 1: KANConv2DLayer(3,16,k=3,spline_order=3,grid_size=5,padding=1) fwd+bwd on 16x3x32x32."""
+    ora, mod = _oracle_and_module("kan", dict(input_dim=3, output_dim=16, kernel_size=3, padding=1, base_activation="gelu"),
+                                  dict(input_dim=3, output_dim=16, kernel_size=3, spline_order=3, grid_size=5, padding=1))
+    mod.precision = "fp32"
+    torch.manual_seed(1)
+    x = torch.randn(16, 3, 32, 32)
+    torch.manual_seed(2)
+    g = torch.randn(16, 16, 32, 32)
+    yo, dxo, go = run_fwd_bwd(ora, x.double(), g.double())
+    y, dx, gr = run_fwd_bwd(mod, x.cuda(), g.cuda())
+    assert rel_err(y, yo) < FP32_TOL and rel_err(dx, dxo) < FP32_TOL
+    for k in go:
+        assert rel_err(gr[k], go[k]) < FP32_TOL, k
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,n", [("kan", 64, 128, 32, 2), ("kan", 16, 320, 20, 3), ("kan", 24, 40, 9, 5),
+                                               ("cheby", 32, 64, 16, 2), ("gram", 32, 64, 16, 2), ("fast", 16, 32, 14, 2)])
+def test_bf16_tensor_core_forward_vs_oracle(kind, cin, cout, hw, n):
+    okw = dict(input_dim=cin, output_dim=cout, kernel_size=3, padding=1)
+    mkw = dict(okw)
+    if kind == "kan":
+        okw["base_activation"] = "silu"
+        mkw["base_activation"] = nn.SiLU
+    ora, mod = _oracle_and_module(kind, okw, mkw)
+    mod.precision = "bf16"
+    torch.manual_seed(3)
+    x = torch.randn(n, cin, hw, hw + 3)
+    with torch.no_grad():
+        yo = ora(x.double())
+        y = mod(x.cuda())
+    e = rel_err(y, yo)
+    print(f"{kind} {cin}->{cout} @{hw}: bf16 forward rel err {e:.3e}")
+    assert e < BF16_TOL
+
+
+def test_l1_wrapper_hook_fires():
+    layer = K.CONV_KAN_FACTORY["KAN"](4, 4, 3, l1_decay=1e-3).cuda()
+    x = torch.randn(2, 4, 6, 6, device="cuda", requires_grad=True)
+    layer(x).sum().backward()
+    assert all(p.grad is not None for p in layer.parameters())
