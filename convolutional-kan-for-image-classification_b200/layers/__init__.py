@@ -1,4 +1,4 @@
-from .kan_layers import KANConvNDLayer, KANConv1DLayer, KANConv2DLayer, KANConv3DLayer  # noqa: F401
+from .kan_layers import KANConvNDLayer, KANConv1DLayer, KANConv2DLayer, KANConv3DLayer, KANLayer  # noqa: F401
 from .cheby_kan_layers import (ChebyKANConvNDLayer, ChebyKANConv1DLayer, ChebyKANConv2DLayer,  # noqa: F401
                                ChebyKANConv3DLayer)
 from .gram_kan_layers import GRAMKANConvNDLayer, GRAMKANConv1DLayer, GRAMKANConv2DLayer, GRAMKANConv3DLayer  # noqa: F401

@@ -87,3 +87,40 @@ class KANConv1DLayer(KANConvNDLayer):
         super().__init__(nn.Conv1d, norm_layer, input_dim, output_dim, spline_order, kernel_size, groups=groups,
                          padding=padding, stride=stride, dilation=dilation, ndim=1, grid_size=grid_size,
                          base_activation=base_activation, grid_range=grid_range, dropout=dropout, **norm_kwargs)
+
+
+class KANLayer(nn.Module):
+    """B-spline KAN fully-connected layer - drop-in for the reference's ``KANLayer`` (kan_layers.py:8-114).
+
+    SURVEY 8(f) rank 2 ("next"): the basis expansion + contraction runs through the same CUDA op as the convolution
+    (a 1x1 convolution over a 1x1 map, reusing ``spline_weight [out, in, nb]`` viewed as ``[out, in*nb, 1, 1]``);
+    the LayerNorm + PReLU tail of this <0.01 %-of-FLOPs head uses torch's own ops."""
+
+    def __init__(self, input_features, output_features, grid_size=5, spline_order=3, base_activation=nn.GELU,
+                 grid_range=[-1, 1]):
+        super().__init__()
+        self.input_features, self.output_features = input_features, output_features
+        self.grid_size, self.spline_order, self.grid_range = grid_size, spline_order, grid_range
+        self.base_activation = base_activation() if base_activation is not None else nn.Identity()
+        self.base_weight = nn.Parameter(torch.randn(output_features, input_features))
+        self.spline_weight = nn.Parameter(torch.randn(output_features, input_features, grid_size + spline_order))
+        self.layer_norm = nn.LayerNorm(output_features)
+        self.prelu = nn.PReLU()
+        h = (grid_range[1] - grid_range[0]) / grid_size
+        knots = torch.linspace(grid_range[0] - h * spline_order, grid_range[1] + h * spline_order,
+                               grid_size + 2 * spline_order + 1, dtype=torch.float32)
+        self.grid = knots.expand(input_features, -1).contiguous()
+        nn.init.kaiming_uniform_(self.base_weight, nonlinearity='linear')
+        nn.init.kaiming_uniform_(self.spline_weight, nonlinearity='linear')
+        self._spec = KF.ConvSpec(basis=L.BASIS_BSPLINE, act=act_kind(self.base_activation), nb=grid_size + spline_order,
+                                 order=spline_order, params=tuple(float(v) for v in knots.tolist()), kernel=(1, 1),
+                                 stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1)
+        self.precision = None
+
+    def forward(self, x):
+        lead = x.shape[:-1]
+        x4 = x.reshape(-1, self.input_features, 1, 1)
+        z = KF.kan_conv(self._spec, x4, None, None, [self.base_weight[:, :, None, None]],
+                        [self.spline_weight.reshape(self.output_features, -1, 1, 1)], self.precision)
+        z = z.reshape(*lead, self.output_features)
+        return self.prelu(self.layer_norm(z))
