@@ -2,16 +2,20 @@
 //
 // "Flat-shift" implicit GEMM.  With stride 1 / dilation 1 the padded input of the whole batch is viewed as ONE flat
 // sequence with row pitch P = W + pad_w and (H + pad_h) rows per image; the gap positions are zero.  Output position m
-// and filter tap (r, s) then read input position  m + (r - pad_h) * P + (s - pad_w)  - a pure shift.  A CTA owns 128
-// consecutive flat positions (the MMA M dimension).  Producer warps evaluate the basis functions (or the base activation)
-// ONCE per needed input position and channel into shared memory as bf16 "planes" [k-core][row][8 x bf16]; because the
-// no-swizzle UMMA layout accepts any 16-byte aligned start address, the A operand of tap (r, s) is just the same buffer
-// viewed from row r*SS + s.  The expanded tensor of the reference (kan_layers.py:236-239) never reaches HBM, and the
-// basis is evaluated (kh*SEG)/(128) ~ 3x per input element instead of 9x.  B (packed bf16 weights) streams in through
-// cp.async.bulk (TMA engine) behind an mbarrier ring; tcgen05.mma accumulates fp32 in TMEM; 4 epilogue warps read TMEM
-// with tcgen05.ld and write z (fp32 NCHW) coalesced.
+// and filter tap (r, s) then read input position  m + (r - pad_h) * P + (s - pad_w)  - a pure shift.  A CTA owns
+// nsub * 128 consecutive flat positions (nsub MMA M-tiles, nsub * N <= 512 TMEM columns).  Producer warps evaluate the
+// basis functions (or the base activation) ONCE per needed input position and channel into shared memory as bf16
+// "planes" [k-core][row][8 x bf16]; because the no-swizzle UMMA layout accepts any 16-byte aligned start address, the
+// A operand of (sub-tile i, tap (r, s)) is just the same buffer viewed from row r*SS + s + 128*i.  The expanded tensor
+// of the reference (kan_layers.py:236-239) never reaches HBM and the basis is evaluated ~(M + 2P)/M times per input
+// element instead of 9 times.  B (packed bf16 weights, K = 32 per ring step) streams in through cp.async.bulk (TMA
+// engine) behind a deep mbarrier ring - measured: the MMA-completion -> commit -> refill -> MMA round trip is ~3.6k
+// cycles, so every B stage feeds nsub*2 MMAs and the ring holds up to 16 stages; tcgen05.mma accumulates fp32 in TMEM;
+// 4 warps read TMEM with tcgen05.ld and write z (fp32 NCHW) coalesced.
 //
-// Warp roles (448 threads): 0-3 epilogue | 4 MMA issuer + TMEM allocator | 5 weight loader | 6-13 basis producers.
+// Warp roles (576 threads): 0-15 producers (0-3 also run the epilogue) | 16 weight loader | 17 MMA issuer + TMEM allocator.
+// The MMA issuer is the highest warp id on purpose: the scheduler arbitrates highest-warp-id-first, and the single issuing
+// thread must never wait behind the 16 ALU-heavy producer warps (measured: 245 -> ~50 cycles per tcgen05.mma).
 #include <string.h>
 
 #include "kc_common.cuh"
@@ -21,19 +25,25 @@ namespace {
 
 using namespace kc;
 
-constexpr int kTcThreads = 448;
-constexpr int kProdThreads = 256;
-constexpr int kProdWarp0 = 6;
+constexpr int kTcThreads = 576;        // 18 warps
+constexpr int kProdThreads = 512;      // warps 0-15
+constexpr int kLoaderWarp = 16, kMmaWarp = 17;
+constexpr int kRowThreads = 256;       // producer thread t owns rows (t & 255) + 256*k and plane half (t >> 8)
+constexpr int kRB = 4;                 // rows per producer thread  (nrows <= 1024)
+constexpr int kPL = 4;                 // k-cores ("planes") per chunk: K = 32 per ring step
 constexpr int kTileM = 128;
-constexpr int kMaxBStages = 4;
+constexpr int kMaxA = 3;
+constexpr int kMaxBStages = 16;
+constexpr int kNumBars = 2 * kMaxA + 2 * kMaxBStages + 1;
 constexpr size_t kSmemLimit = 227 * 1024;
 
 struct TcGeom {
   int Cp, cps, nsc, ngroups, nbc, last_base_cols;
   int P, IMG, ph, pw;          // flat pitch, flat size of one image, effective padding of THIS gemm
   long long L;                 // flat length of the batch
-  int seglen, SS, nrows, plane_bytes;
-  int ntile, n_ntiles, tmem_cols, bstages;
+  int nsub, mcta;              // M sub-tiles per CTA, rows per CTA
+  int SS, nrows, plane_bytes;
+  int ntile, n_ntiles, tmem_cols, bstages, na;
   long long mtiles;
   long long wimg_bytes_per_ntile;
   size_t smem_bytes;
@@ -53,44 +63,87 @@ struct TcFwdArgs {
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// ---- optional timeline trace (debug): kc_debug_trace() points g_trace at a device buffer of 4 x 1024 clock stamps;
+// one CTA records one stamp per pipeline event of representative threads.  nullptr (default) = disabled.
+__device__ long long* g_trace = nullptr;
+struct Tracer {
+  long long* p; int n;
+  __device__ Tracer(int role, bool on) {
+    long long* t = g_trace;
+    p = (on && t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? t + role * 1024 : nullptr; n = 0;
+  }
+  __device__ __forceinline__ void stamp() { if (p != nullptr && n < 1024) p[n++] = clock64(); }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // basis -> 8 packed bf16
 // ---------------------------------------------------------------------------------------------------------
 // Uniform cubic B-spline, closed form: the 4 non-zero weights land at j = i0-3 .. i0.
-__device__ __forceinline__ uint4 cubic8(float x, float t0, float inv_h, int nintervals) {
-  float u = (x - t0) * inv_h;
-  uint4 out = make_uint4(0u, 0u, 0u, 0u);
-  if (!(u >= 0.0f) || !(u < (float)nintervals)) return out;     // outside the knot span (or NaN): all-zero row
-  float fi = floorf(u);
-  float f = u - fi, omf = 1.0f - f;
-  int i0 = (int)fi;
-  float f2 = f * f, f3 = f2 * f;
-  const float s = 1.0f / 6.0f;
-  float w0 = omf * omf * omf * s;
-  float w1 = (3.0f * f3 - 6.0f * f2 + 4.0f) * s;
-  float w2 = (-3.0f * f3 + 3.0f * f2 + 3.0f * f + 1.0f) * s;
-  float w3 = f3 * s;
+// Branch-free: the 4 weights are packed into 64 bits and moved to their slots with clamped PTX shifts (shift
+// amounts >= 64, including "negative" ones, yield 0), so independent evaluations can be interleaved by the compiler.
+__device__ __forceinline__ unsigned long long shl64(unsigned long long v, int s) {
+  unsigned long long r;
+  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
+  return r;
+}
+__device__ __forceinline__ unsigned long long shr64(unsigned long long v, int s) {
+  unsigned long long r;
+  asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
+  return r;
+}
+__device__ __forceinline__ uint4 cubic8(float x, float t0, float inv_h, int nintervals, bool valid) {
+  const float u = (x - t0) * inv_h;
+  const bool ok = valid && (u >= 0.0f) && (u < (float)nintervals);    // outside the knot span / NaN: all-zero row
+  const float fi = floorf(u);
+  const float f = u - fi;
+  const int i0 = min(max((int)fi, 0), 15);
+  const float s6 = 1.0f / 6.0f;
+  const float w0 = fmaf(fmaf(fmaf(-s6, f, 0.5f), f, -0.5f), f, s6);
+  const float w1 = fmaf(fmaf(0.5f, f, -1.0f) * f, f, 4.0f * s6);
+  const float w2 = fmaf(fmaf(fmaf(-0.5f, f, 0.5f), f, 0.5f), f, s6);
+  const float w3 = f * f * f * s6;
   unsigned long long v = (unsigned long long)pack_bf16(w0, w1) | ((unsigned long long)pack_bf16(w2, w3) << 32);
-  int sh = 16 * (i0 - 3);
-  unsigned long long lo, hi;
-  if (sh < 0) { lo = v >> (-sh); hi = 0ull; }
-  else if (sh == 0) { lo = v; hi = 0ull; }
-  else if (sh < 64) { lo = v << sh; hi = v >> (64 - sh); }
-  else { lo = 0ull; hi = (sh < 128) ? (v << (sh - 64)) : 0ull; }
-  out.x = (unsigned)lo; out.y = (unsigned)(lo >> 32); out.z = (unsigned)hi; out.w = (unsigned)(hi >> 32);
-  return out;
+  v = ok ? v : 0ull;
+  const int sh = 16 * (i0 - 3);
+  const unsigned long long lo = shl64(v, sh) | shr64(v, -sh);
+  const unsigned long long hi = shr64(v, 64 - sh) | shl64(v, sh - 64);
+  return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
 }
 
-__device__ __forceinline__ uint4 basis8(const KcBasisCtx& B, const TcGeom& g, float x) {
-  if (g.fast_cubic) return cubic8(x, g.t0, g.inv_h, B.nparams - 1);
+// generic (any family) evaluators are kept out of line so that their local arrays do not inflate the register
+// allocation of the closed-form cubic fast path
+__device__ __noinline__ uint4 basis8_generic(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
   kc_eval_basis(B, x, phi, nullptr, 1);
   return make_uint4(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]), pack_bf16(phi[4], phi[5]), pack_bf16(phi[6], phi[7]));
 }
-__device__ __forceinline__ uint2 basis4(const KcBasisCtx& B, float x) {
+__device__ __forceinline__ uint4 basis8(const KcBasisCtx& B, const TcGeom& g, float x, bool valid) {
+  if (g.fast_cubic) return cubic8(x, g.t0, g.inv_h, B.nparams - 1, valid);
+  return valid ? basis8_generic(B, x) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __noinline__ uint2 basis4(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
   kc_eval_basis(B, x, phi, nullptr, 1);
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
+}
+
+__device__ __forceinline__ int chunk_cols(const TcGeom& g, int q) {
+  return (q < g.nsc || q - g.nsc != g.nbc - 1) ? kPL : g.last_base_cols;
+}
+
+// Straight-line issue of the NSUB x (K/16) MMAs of one ring step.  a_lo / b_lo are complete low descriptor words
+// (LBO field | start address >> 4) of sub-tile 0, k-core pair 0; all other descriptors differ by small constants, so
+// the issuing thread executes ~2 integer adds per tcgen05.mma and no branches.
+template <int NSUB>
+__device__ __forceinline__ void issue_step(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_k2,
+                                           uint32_t b_k2, uint32_t desc_hi, uint32_t idesc, uint32_t first, bool two) {
+#pragma unroll
+  for (int i = 0; i < NSUB; ++i) {
+    const uint32_t al = a_lo + (uint32_t)(i * kTileM);
+    const uint32_t td = tmem_base + (uint32_t)i * ntile;
+    tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | al, ((uint64_t)desc_hi << 32) | b_lo, idesc, first);
+    if (two) tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | (al + a_k2), ((uint64_t)desc_hi << 32) | (b_lo + b_k2), idesc, 1u);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -101,157 +154,222 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
   // ---- carve shared memory ---------------------------------------------------------------------------
-  const int abuf_bytes = 8 * g.plane_bytes;
-  const int bstage_bytes = 8 * g.ntile * 16;
+  const int abuf_bytes = kPL * g.plane_bytes;
+  const int bstage_bytes = kPL * g.ntile * 16;
   unsigned char* abuf0 = smem;
-  unsigned char* bst0 = abuf0 + 2 * abuf_bytes;
-  int* rowoff = reinterpret_cast<int*>(bst0 + g.bstages * bstage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(rowoff) + round_up(g.nrows * 4, 16));
-  uint64_t* a_full = bars;                 // [2]
-  uint64_t* a_empty = bars + 2;            // [2]
-  uint64_t* b_full = bars + 4;             // [kMaxBStages]
-  uint64_t* b_empty = bars + 4 + kMaxBStages;
-  uint64_t* acc_full = bars + 4 + 2 * kMaxBStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kMaxBStages);
+  unsigned char* bst0 = abuf0 + g.na * abuf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bst0 + g.bstages * bstage_bytes);
+  uint64_t* a_full = bars;                       // [kMaxA]
+  uint64_t* a_empty = bars + kMaxA;              // [kMaxA]
+  uint64_t* b_full = bars + 2 * kMaxA;           // [kMaxBStages]
+  uint64_t* b_empty = b_full + kMaxBStages;      // [kMaxBStages]
+  uint64_t* acc_full = b_empty + kMaxBStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kNumBars);
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long m0 = (long long)blockIdx.x * kTileM;
+  const long long m0 = (long long)blockIdx.x * g.mcta;
   const int nt = blockIdx.y;
   const int T = d.kh * d.kw, HW = d.h * d.w;
   const bool has_base = d.act != KC_ACT_NONE;
   const int nchunks = g.nsc + (has_base ? g.nbc : 0);
 
   if (threadIdx.x == 0) {
-    mbar_init(&a_full[0], kProdThreads); mbar_init(&a_full[1], kProdThreads);
-    mbar_init(&a_empty[0], 1); mbar_init(&a_empty[1], 1);
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], kProdThreads); mbar_init(&a_empty[i], 1); }
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
   kc_load_basis_ctx(B, d, a.beta);        // ends with __syncthreads()
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= kProdWarp0) {
+  if (warp < kLoaderWarp) {
     // ================================ basis / activation producers ====================================
-    const int tp = threadIdx.x - kProdWarp0 * 32;
+    const int tp = threadIdx.x;                                      // 0 .. 511
+    const int r0 = tp & (kRowThreads - 1), half = tp >> 8;
     const long long qbase = m0 - (long long)g.ph * g.P - g.pw;
-    for (int b = tp; b < g.nrows; b += kProdThreads) {
-      int r = min(b / g.SS, d.kh - 1);
-      long long q = qbase + (long long)r * g.P + (b - r * g.SS);
-      int off = -1;
-      if (q >= 0 && q < g.L) {
-        int n = (int)(q / g.IMG);
-        int rem = (int)(q - (long long)n * g.IMG);
-        int y = rem / g.P, x = rem - y * g.P;
-        if (y < d.h && x < d.w) off = (int)((long long)n * d.x_batch_stride + y * d.w + x);
+    int offs[kRB];                                                   // >=0 input offset | -1 zero (padding) row | -2 no row
+#pragma unroll
+    for (int k = 0; k < kRB; ++k) {
+      const int b = r0 + k * kRowThreads;
+      int off = -2;
+      if (b < g.nrows) {
+        off = -1;
+        int r = min(b / g.SS, d.kh - 1);
+        long long q = qbase + (long long)r * g.P + (b - r * g.SS);
+        if (q >= 0 && q < g.L) {
+          int n = (int)(q / g.IMG);
+          int rem = (int)(q - (long long)n * g.IMG);
+          int y = rem / g.P, x = rem - y * g.P;
+          if (y < d.h && x < d.w) off = (int)((long long)n * d.x_batch_stride + y * d.w + x);
+        }
       }
-      rowoff[b] = off;
+      offs[k] = off;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+    const int plane_bytes = g.plane_bytes, cin = d.cin, nb = d.nb;
+    // x values of the NEXT spline chunk are fetched while the current one is evaluated (nb == 8 path):
+    // this thread owns planes half*2 + {0,1} = channels q*4 + half*2 + {0,1}
+    float xnext[kRB][2];
+    auto fetch8 = [&](int q, float (&xv)[kRB][2]) {
+      const int c0 = q * 4 + half * 2;
+      const float* xc = a.x_basis + (long long)c0 * HW;
+#pragma unroll
+      for (int k = 0; k < kRB; ++k)
+#pragma unroll
+        for (int cl = 0; cl < 2; ++cl)
+          xv[k][cl] = (offs[k] >= 0 && c0 + cl < cin) ? __ldg(xc + (long long)cl * HW + offs[k]) : 0.0f;
+    };
+    Tracer trp(tp == 0 ? 0 : 3, tp == 0 || tp == 300);
+    if (nb == 8 && g.nsc > 0) fetch8(0, xnext);
+    int buf = 0;
+    uint32_t aphase = 0;
     for (int q = 0; q < nchunks; ++q) {
-      const int buf = q & 1;
       unsigned char* ab = abuf0 + buf * abuf_bytes;
-      mbar_wait(&a_empty[buf], ((q >> 1) & 1) ^ 1);
-      if (q < g.nsc) {
-        if (d.nb == 8) {
-          for (int cl = 0; cl < 8; ++cl) {
-            const int c = q * 8 + cl;
-            const float* xc = a.x_basis + (long long)c * HW;
-            uint4* plane = reinterpret_cast<uint4*>(ab + cl * g.plane_bytes);
-            for (int b = tp; b < g.nrows; b += kProdThreads) {
-              int off = rowoff[b];
-              uint4 v = make_uint4(0u, 0u, 0u, 0u);
-              if (off >= 0 && c < d.cin) v = basis8(*B, g, __ldg(xc + off));
-              plane[b] = v;
-            }
-          }
-        } else {   // nb == 4: two channels share one 16-byte k-core
-          for (int pl = 0; pl < 8; ++pl) {
-            const int c = q * 16 + pl * 2;
-            const float* xc = a.x_basis + (long long)c * HW;
-            uint4* plane = reinterpret_cast<uint4*>(ab + pl * g.plane_bytes);
-            for (int b = tp; b < g.nrows; b += kProdThreads) {
-              int off = rowoff[b];
-              uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-              if (off >= 0) {
-                if (c < d.cin) lo = basis4(*B, __ldg(xc + off));
-                if (c + 1 < d.cin) hi = basis4(*B, __ldg(xc + HW + off));
-              }
-              plane[b] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-            }
+      trp.stamp();                                   // chunk start
+      if (q < g.nsc && nb == 8) {
+        float xv[kRB][2];
+#pragma unroll
+        for (int k = 0; k < kRB; ++k) { xv[k][0] = xnext[k][0]; xv[k][1] = xnext[k][1]; }
+        if (q + 1 < g.nsc) fetch8(q + 1, xnext);
+        mbar_wait(&a_empty[buf], aphase ^ 1);
+        trp.stamp();                                 // buffer free
+#pragma unroll
+        for (int k = 0; k < kRB; ++k) {
+          const int b = r0 + k * kRowThreads;
+#pragma unroll
+          for (int cl = 0; cl < 2; ++cl) {
+            const int pl = half * 2 + cl;
+            uint4 v = basis8(*B, g, xv[k][cl], offs[k] >= 0 && q * 4 + pl < cin);
+            if (offs[k] != -2) reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v;
           }
         }
-      } else {
+      } else if (q < g.nsc) {   // nb == 4: two channels share one 16-byte k-core, 8 channels per chunk
+        float xv[kRB][4];
+        const int c0 = q * 8 + half * 4;
+        const float* xc = a.x_basis + (long long)c0 * HW;
+#pragma unroll
+        for (int k = 0; k < kRB; ++k)
+#pragma unroll
+          for (int cl = 0; cl < 4; ++cl)
+            xv[k][cl] = (offs[k] >= 0 && c0 + cl < cin) ? __ldg(xc + (long long)cl * HW + offs[k]) : 0.0f;
+        mbar_wait(&a_empty[buf], aphase ^ 1);
+        trp.stamp();
+#pragma unroll
+        for (int k = 0; k < kRB; ++k) {
+          if (offs[k] == -2) continue;
+          const int b = r0 + k * kRowThreads;
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int pl = half * 2 + pp, c = q * 8 + pl * 2;
+            uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+            if (offs[k] >= 0) {
+              if (c < cin) lo = basis4(*B, xv[k][2 * pp]);
+              if (c + 1 < cin) hi = basis4(*B, xv[k][2 * pp + 1]);
+            }
+            reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
+      } else {                  // base-activation chunk: k-core = 8 consecutive channels of one position
         const int bq = q - g.nsc;
-        const int ncols = (bq == g.nbc - 1) ? g.last_base_cols : 8;
-        for (int pl = 0; pl < ncols; ++pl) {
-          const int grp = bq * 8 + pl;
+        const int ncols = chunk_cols(g, q);
+        bool waited = false;
+        for (int pl = half; pl < ncols; pl += 2) {
+          const int grp = bq * kPL + pl;
           const float* xc = a.x_base + (long long)grp * 8 * HW;
-          uint4* plane = reinterpret_cast<uint4*>(ab + pl * g.plane_bytes);
-          for (int b = tp; b < g.nrows; b += kProdThreads) {
-            int off = rowoff[b];
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (off >= 0 && grp < g.ngroups) {
+#pragma unroll
+          for (int kk = 0; kk < kRB; kk += 2) {
+            float xv[2][8];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                xv[k][i] = (offs[kk + k] >= 0 && grp * 8 + i < cin) ? __ldg(xc + (long long)i * HW + offs[kk + k]) : 0.0f;
+            if (!waited) { mbar_wait(&a_empty[buf], aphase ^ 1); waited = true; trp.stamp(); }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (offs[kk + k] == -2) continue;
+              const int b = r0 + (kk + k) * kRowThreads;
               float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = (grp * 8 + i < d.cin) ? kc_act(d.act, __ldg(xc + (long long)i * HW + off)) : 0.0f;
-              v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              for (int i = 0; i < 8; ++i) f[i] = (offs[kk + k] >= 0 && grp * 8 + i < cin) ? kc_act(d.act, xv[k][i]) : 0.0f;
+              reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] =
+                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
             }
-            plane[b] = v;
           }
         }
+        if (!waited) { mbar_wait(&a_empty[buf], aphase ^ 1); trp.stamp(); }
       }
+      trp.stamp();                                   // stores done
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(&a_full[buf]);
+      trp.stamp();                                   // arrived
+      if (++buf == g.na) { buf = 0; aphase ^= 1; }
     }
-  } else if (warp == 4) {
+  }
+  if (warp == kMmaWarp) {
     // ================================ MMA issuer ======================================================
-    if (lane == 0) {
+    // The whole warp walks the pipeline with warp-uniform state; one elected lane issues tcgen05.mma / commit.
+    // Per MMA only the 14-bit start-address fields of the two descriptors change (a few uniform integer adds).
+    {
       const uint32_t idesc = make_idesc_bf16(kTileM, g.ntile, 0, 0);
-      int stage = 0;
-      uint32_t bphase = 0, accumulate = 0;
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version = 1
+      const uint32_t a_lo_c = ((uint32_t)(g.plane_bytes >> 4) & 0x3FFFu) << 16;         // LBO = plane pitch
+      const uint32_t b_lo_c = ((uint32_t)(g.ntile) & 0x3FFFu) << 16;                    // LBO = ntile * 16 B
+      const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * g.ntile);
+      const uint32_t abuf_u = smem_u32(abuf0) >> 4, bst_u = smem_u32(bst0) >> 4;
+      const uint32_t abuf_sz = (uint32_t)abuf_bytes >> 4, bst_sz = (uint32_t)bstage_bytes >> 4;
+      const int nsub = g.nsub, ntile = g.ntile, kw = d.kw, SS = g.SS;
+      int stage = 0, buf = 0;
+      uint32_t bphase = 0, aphase = 0;
+      Tracer trm(1, lane == 0);
       for (int q = 0; q < nchunks; ++q) {
-        const int buf = q & 1;
-        const int ncols = (q < g.nsc) ? 8 : ((q - g.nsc == g.nbc - 1) ? g.last_base_cols : 8);
-        mbar_wait(&a_full[buf], (q >> 1) & 1);
+        const int nk2 = chunk_cols(g, q) >> 1;
+        trm.stamp();                                 // before a_full wait
+        mbar_wait(&a_full[buf], aphase);
         tc_fence_after();
-        const uint32_t abase = smem_u32(abuf0 + buf * abuf_bytes);
+        trm.stamp();                                 // a_full acquired
+        uint32_t arow = abuf_u + (uint32_t)buf * abuf_sz;      // (address >> 4) of tap (0,0), sub-tile 0, k2 = 0
+        int s = 0;
         for (int t = 0; t < T; ++t) {
           mbar_wait(&b_full[stage], bphase);
           tc_fence_after();
-          const int r = t / d.kw, s = t - r * d.kw;
-          const uint32_t aaddr = abase + (uint32_t)(r * g.SS + s) * 16u;
-          const uint32_t baddr = smem_u32(bst0 + stage * bstage_bytes);
-          for (int i = 0; i < ncols / 2; ++i) {
-            uint64_t ad = make_smem_desc(aaddr + (uint32_t)(2 * i) * g.plane_bytes, (uint32_t)g.plane_bytes, 128u);
-            uint64_t bd = make_smem_desc(baddr + (uint32_t)(2 * i) * g.ntile * 16u, (uint32_t)g.ntile * 16u, 128u);
-            tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
-            accumulate = 1;
+          trm.stamp();                               // b_full acquired
+          const uint32_t b_lo = b_lo_c + bst_u + (uint32_t)stage * bst_sz;
+          const uint32_t first = (q | t) != 0 ? 1u : 0u;
+          const bool two = nk2 == 2;
+          if (elect_one_sync()) {
+            if (nsub == 4) issue_step<4>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+            else if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+            else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+            tc_commit(&b_empty[stage]);
+            if (t == T - 1) tc_commit(&a_empty[buf]);
           }
-          tc_commit(&b_empty[stage]);
+          __syncwarp();
           if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
+          // next tap: one position right, or first position of the next filter row (SS rows down)
+          if (++s == kw) { s = 0; arow += (uint32_t)(SS - (kw - 1)); } else { arow += 1u; }
         }
-        tc_commit(&a_empty[buf]);
+        if (++buf == g.na) { buf = 0; aphase ^= 1; }
       }
-      tc_commit(acc_full);
+      if (elect_one_sync()) tc_commit(acc_full);
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kLoaderWarp) {
     // ================================ weight loader (TMA engine bulk copies) ==========================
     if (lane == 0) {
       int stage = 0;
       uint32_t bphase = 0;
       const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
+      Tracer trl(2, true);
       for (int q = 0; q < nchunks; ++q) {
-        const int ncols = (q < g.nsc) ? 8 : ((q - g.nsc == g.nbc - 1) ? g.last_base_cols : 8);
-        const uint32_t bytes = (uint32_t)ncols * g.ntile * 16u;
+        const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u;
         for (int t = 0; t < T; ++t) {
           mbar_wait(&b_empty[stage], bphase ^ 1);
+          trl.stamp();                               // b_empty acquired
           mbar_arrive_expect_tx(&b_full[stage], bytes);
           bulk_g2s(bst0 + stage * bstage_bytes, wsrc, bytes, &b_full[stage]);
           wsrc += bytes;
@@ -260,43 +378,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
       }
     }
     __syncwarp();
-  } else {
+  }
+  if (warp < 4) {
     // ================================ epilogue: TMEM -> registers -> z (fp32 NCHW) =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const long long q = m0 + warp * 32 + lane;
-    bool valid = false;
-    long long zoff = 0;
     const int HoWo = d.ho * d.wo;
-    if (q < g.L) {
-      int n = (int)(q / g.IMG);
-      int rem = (int)(q - (long long)n * g.IMG);
-      int y = rem / g.P, x = rem - y * g.P;
-      if (y < d.ho && x < d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + y * d.wo + x; }
-    }
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int n0 = nt * g.ntile;
-    for (int c0 = 0; c0 < g.ntile; c0 += 32) {
-      uint32_t r[32];
-      if (g.ntile - c0 >= 32) {
-        tmem_ld32(trow + (uint32_t)c0, r);
-      } else {
-        tmem_ld16(trow + (uint32_t)c0, r);
-#pragma unroll
-        for (int i = 16; i < 32; ++i) r[i] = 0u;
+    for (int i = 0; i < g.nsub; ++i) {
+      const long long q = m0 + i * kTileM + warp * 32 + lane;
+      bool valid = false;
+      long long zoff = 0;
+      if (q < g.L) {
+        int n = (int)(q / g.IMG);
+        int rem = (int)(q - (long long)n * g.IMG);
+        int y = rem / g.P, x = rem - y * g.P;
+        if (y < d.ho && x < d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + y * d.wo + x; }
       }
-      tmem_ld_wait();
-      const int lim = min(32, g.ntile - c0);
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * g.ntile);
+      for (int c0 = 0; c0 < g.ntile; c0 += 32) {
+        uint32_t r[32];
+        if (g.ntile - c0 >= 32) {
+          tmem_ld32(trow + (uint32_t)c0, r);
+        } else {
+          tmem_ld16(trow + (uint32_t)c0, r);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        int co = n0 + c0 + i;
-        if (valid && i < lim && co < d.cout) a.z[zoff + (long long)co * HoWo] = __uint_as_float(r[i]);
+          for (int j = 16; j < 32; ++j) r[j] = 0u;
+        }
+        tmem_ld_wait();
+        const int lim = min(32, g.ntile - c0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int co = n0 + c0 + j;
+          if (valid && j < lim && co < d.cout) a.z[zoff + (long long)co * HoWo] = __uint_as_float(r[j]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -311,8 +432,8 @@ __global__ void __launch_bounds__(256) kc_pack_fwd_kernel(const __grid_constant_
   const bool has_base = d.act != KC_ACT_NONE;
   const long long vec_per_ntile = g.wimg_bytes_per_ntile / 16;
   const long long total = vec_per_ntile * g.n_ntiles;
-  const long long spline_vecs = (long long)g.nsc * T * 8 * g.ntile;
-  const long long full_chunk = (long long)T * 8 * g.ntile;
+  const long long full_chunk = (long long)T * kPL * g.ntile;
+  const long long spline_vecs = (long long)g.nsc * full_chunk;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
     const int nt = (int)(v / vec_per_ntile);
     long long vl = v - (long long)nt * vec_per_ntile;
@@ -322,15 +443,15 @@ __global__ void __launch_bounds__(256) kc_pack_fwd_kernel(const __grid_constant_
     if (vl < spline_vecs) {
       int q = (int)(vl / full_chunk);
       long long rem = vl - (long long)q * full_chunk;
-      int t = (int)(rem / (8 * g.ntile));
-      int rem2 = (int)(rem - (long long)t * 8 * g.ntile);
+      int t = (int)(rem / (kPL * g.ntile));
+      int rem2 = (int)(rem - (long long)t * kPL * g.ntile);
       int kc = rem2 / g.ntile, nl = rem2 - kc * g.ntile;
       int co = nt * g.ntile + nl;
       if (co < d.cout) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           int c, j;
-          if (nb == 8) { c = q * 8 + kc; j = e; } else { c = q * 16 + kc * 2 + (e >> 2); j = e & 3; }
+          if (nb == 8) { c = q * 4 + kc; j = e; } else { c = q * 8 + kc * 2 + (e >> 2); j = e & 3; }
           if (c < d.cin) f[e] = a.w_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + t];
         }
       }
@@ -338,11 +459,11 @@ __global__ void __launch_bounds__(256) kc_pack_fwd_kernel(const __grid_constant_
       long long vb = vl - spline_vecs;
       int bq = (int)min((long long)(g.nbc - 1), vb / full_chunk);
       long long rem = vb - (long long)bq * full_chunk;
-      int ncols = (bq == g.nbc - 1) ? g.last_base_cols : 8;
+      int ncols = (bq == g.nbc - 1) ? g.last_base_cols : kPL;
       int t = (int)(rem / (ncols * g.ntile));
       int rem2 = (int)(rem - (long long)t * ncols * g.ntile);
       int kc = rem2 / g.ntile, nl = rem2 - kc * g.ntile;
-      int co = nt * g.ntile + nl, grp = bq * 8 + kc;
+      int co = nt * g.ntile + nl, grp = bq * kPL + kc;
       if (co < d.cout && grp < g.ngroups) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -372,6 +493,8 @@ bool knots_uniform_cubic(const kc_desc* d, float* t0, float* inv_h) {
   return true;
 }
 
+size_t tc_fixed_smem() { return (size_t)kNumBars * 8 + 16 + sizeof(KcBasisCtx) + 128; }
+
 int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs stride 1 and dilation 1");
   if (d->nb != 8 && d->nb != 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs basis width 4 or 8 (got %d)", d->nb);
@@ -381,34 +504,48 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
   memset(g, 0, sizeof(*g));
   const bool has_base = d->act != KC_ACT_NONE;
   const int T = d->kh * d->kw;
-  g->cps = (d->nb == 8) ? 8 : 16;
-  g->Cp = round_up(d->cin, g->cps);
+  g->cps = (d->nb == 8) ? 4 : 8;
+  g->Cp = round_up(d->cin, 8);
   g->nsc = g->Cp / g->cps;
   g->ngroups = g->Cp / 8;
-  g->nbc = has_base ? (g->ngroups + 7) / 8 : 0;
-  g->last_base_cols = has_base ? round_up(g->ngroups - (g->nbc - 1) * 8, 2) : 0;
+  g->nbc = has_base ? (g->ngroups + kPL - 1) / kPL : 0;
+  g->last_base_cols = has_base ? round_up(g->ngroups - (g->nbc - 1) * kPL, 2) : 0;
   g->ph = d->pad_h; g->pw = d->pad_w;
   g->P = d->w + d->pad_w;
   g->IMG = (d->h + d->pad_h) * g->P;
   g->L = (long long)d->n * g->IMG;
-  g->seglen = round_up(kTileM + d->kw - 1, 8);
-  g->SS = g->P < g->seglen ? g->P : g->seglen;
-  g->nrows = (d->kh - 1) * g->SS + g->seglen;
-  g->plane_bytes = g->nrows * 16 + 16;       // +16 B: consecutive planes start 4 banks apart
   int want_tiles = (d->cout + 255) / 256;
   g->ntile = round_up((d->cout + want_tiles - 1) / want_tiles, 16);
   g->n_ntiles = (d->cout + g->ntile - 1) / g->ntile;
+  const size_t bstage = (size_t)kPL * g->ntile * 16;
+  // nsub: as many 128-row sub-tiles per CTA as TMEM (512 columns), the producer row mapping (1024 rows), shared memory
+  // and the wish for >= 2 waves of CTAs allow.
+  bool found = false;
+  for (int nsub = 4; nsub >= 1 && !found; nsub >>= 1) {
+    if (nsub * g->ntile > 512) continue;
+    const int mcta = nsub * kTileM;
+    const int seglen = round_up(mcta + d->kw - 1, 8);
+    const int SS = g->P < seglen ? g->P : seglen;
+    const int nrows = (d->kh - 1) * SS + seglen;
+    if (nrows > kRB * kRowThreads) continue;
+    const long long mtiles = (g->L + mcta - 1) / mcta;
+    if (nsub > 1 && mtiles * g->n_ntiles < 2 * 148) continue;
+    const int plane_bytes = nrows * 16 + 16;       // +16 B: consecutive planes start 4 banks apart
+    for (int na = kMaxA; na >= 2 && !found; --na) {
+      size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
+      if (fixed + 6 * bstage > kSmemLimit) continue;
+      int bst = (int)((kSmemLimit - fixed) / bstage);
+      if (bst > kMaxBStages) bst = kMaxBStages;
+      g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes;
+      g->na = na; g->bstages = bst; g->mtiles = mtiles; g->smem_bytes = fixed + bst * bstage;
+      found = true;
+    }
+  }
+  if (!found) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path: tile does not fit shared memory");
   g->tmem_cols = 32;
-  while (g->tmem_cols < g->ntile) g->tmem_cols *= 2;
-  g->mtiles = (g->L + kTileM - 1) / kTileM;
-  int base_cols = has_base ? (g->nbc - 1) * 8 + g->last_base_cols : 0;
-  g->wimg_bytes_per_ntile = (long long)T * g->ntile * 16 * (g->nsc * 8 + base_cols);
-  size_t fixed = 2 * 8 * (size_t)g->plane_bytes + round_up(g->nrows * 4, 16) + (5 + 2 * kMaxBStages) * 8 + 16 + sizeof(KcBasisCtx) + 128;
-  size_t bstage = 8 * (size_t)g->ntile * 16;
-  g->bstages = kMaxBStages;
-  while (g->bstages > 2 && fixed + g->bstages * bstage > kSmemLimit) --g->bstages;
-  g->smem_bytes = fixed + g->bstages * bstage;
-  if (g->smem_bytes > kSmemLimit) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path: tile does not fit shared memory");
+  while (g->tmem_cols < g->nsub * g->ntile) g->tmem_cols *= 2;
+  int base_cols = has_base ? (g->nbc - 1) * kPL + g->last_base_cols : 0;
+  g->wimg_bytes_per_ntile = (long long)T * g->ntile * 16 * (g->nsc * kPL + base_cols);
   g->fast_cubic = knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
   return KC_OK;
 }
@@ -567,6 +704,120 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const float* dz, const float* 
                                 const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream) {
   (void)d; (void)dz; (void)x_base; (void)x_basis; (void)beta; (void)dw_base; (void)dw_basis; (void)workspace; (void)stream;
   KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_wgrad_tc: not built yet");
+}
+
+// Debug only: raw tcgen05.mma rate from resident smem operands, with knobs that mimic the convolution main loop:
+// nsub accumulators used round-robin, a commit every `commit_every` MMAs (0 = only at the end), and `writers` extra
+// warps streaming 16-byte st.shared into an unrelated smem region while the MMAs run.
+__global__ void __launch_bounds__(576, 1) kc_mma_rate_kernel(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters,
+                                                              int a_rowshift, int nsub, int commit_every, int writers,
+                                                              float* out) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar, dummy[8];
+  __shared__ uint32_t tmem_ptr;
+  __shared__ volatile int done;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1000000); done = 0; fence_barrier_init(); }
+  if (warp == 17) tmem_alloc(&tmem_ptr, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_ptr;
+  if (tid == 17 * 32) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t abase = smem_u32(sm) + a_rowshift * 16, bbase = smem_u32(sm) + 96 * 1024;
+    long long t0 = clock64();
+    int cnt = 0;
+    for (int it = 0; it < iters; ++it) {
+      for (int s = 0; s < nsub; ++s) {
+        for (int i = 0; i < 2; ++i) {
+          uint64_t ad = make_smem_desc(abase + s * 2048 + i * 2 * a_lbo, a_lbo, a_sbo);
+          uint64_t bd = make_smem_desc(bbase + i * 2 * b_lbo, b_lbo, b_sbo);
+          tc_mma_bf16(tb + s * N, ad, bd, idesc, 1u);
+          if (commit_every > 0 && (++cnt % commit_every) == 0) tc_commit(&dummy[(cnt / commit_every) & 7]);
+        }
+      }
+    }
+    tc_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    out[0] = (float)(t1 - t0) / (float)(iters * nsub * 2);
+    done = 1;
+  } else if (warp < writers) {
+    uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + tid;
+    uint4 v = make_uint4(tid, 1, 2, 3);
+    while (!done) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k * 512 % 1024] = v;
+      v.x += 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc(tb, 512);
+}
+
+extern "C" int kc_debug_mma_rate(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters, int a_rowshift, int nsub,
+                                 int commit_every, int writers, float* cycles) {
+  float* dev = nullptr;
+  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  kc_mma_rate_kernel<<<1, 576, 160 * 1024>>>(N, a_lbo, a_sbo, b_lbo, b_sbo, iters, a_rowshift, nsub, commit_every, writers, dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate: %s", cudaGetErrorString(e));
+  return KC_OK;
+}
+
+// Debug only: latency / throughput of cp.async.bulk global->shared.  Each CTA issues `depth` copies of `bytes` back to back
+// (ring of `depth` buffers), `iters` rounds; same_addr != 0 makes every CTA read the same global range.
+__global__ void __launch_bounds__(32, 1) kc_bulk_bench_kernel(const unsigned char* src, int bytes, int depth, int iters,
+                                                               int same_addr, long long span, float* out) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bars[8];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned char* base = src + (same_addr ? 0 : ((long long)blockIdx.x * (long long)bytes * depth) % span);
+    long long off = 0;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < depth; ++k) {
+        mbar_arrive_expect_tx(&bars[k], (uint32_t)bytes);
+        bulk_g2s(sm + (size_t)k * bytes, base + off, (uint32_t)bytes, &bars[k]);
+        off = (off + bytes) % (span / 2);
+      }
+      for (int k = 0; k < depth; ++k) mbar_wait(&bars[k], it & 1);
+    }
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = (float)(t1 - t0) / (float)iters;
+  }
+}
+
+extern "C" int kc_debug_bulk_bench(const void* src, long long span, int bytes, int depth, int iters, int nctas, int same_addr,
+                                   float* cycles_per_round) {
+  float* dev = nullptr;
+  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_bulk_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes * depth));
+  kc_bulk_bench_kernel<<<nctas, 32, (size_t)bytes * depth>>>((const unsigned char*)src, bytes, depth, iters, same_addr, span, dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles_per_round, dev, sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_bulk_bench: %s", cudaGetErrorString(e));
+  return KC_OK;
+}
+
+// Debug only (not part of include/kanconv.h): enable/disable the timeline trace of kc_fwd_tc_kernel.
+extern "C" int kc_debug_trace(void* device_buffer) {
+  long long* p = (long long*)device_buffer;
+  KC_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+  return KC_OK;
 }
 
 extern "C" int kc_tc_selftest(int mode, float* max_abs_err, void* stream) {

@@ -1,0 +1,23 @@
+"""Summarise an ncu report's source page: top SASS instructions by stall samples.  usage: ncu_top.py rep [N]"""
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+hdr = rows[hi]
+col = {h: i for i, h in enumerate(hdr)}
+data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+tot = sum(int(r[col["# Samples"]]) for r in data)
+stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+agg = {s: sum(int(r[col[s]]) for r in data) for s in stalls}
+print("total samples", tot)
+print("stall mix:", ", ".join(f"{k[6:]}={v * 100 // max(tot, 1)}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
+data.sort(key=lambda r: -int(r[col["# Samples"]]))
+for r in data[:topn]:
+    s = int(r[col["# Samples"]])
+    top = sorted(((int(r[col[k]]), k[6:]) for k in stalls), reverse=True)[:2]
+    print(f"{s * 100.0 / tot:5.1f}%  {r[col['Source']].strip()[:70]:70s} exec={r[col['Instructions Executed']]:>9s} {top}")
