@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the KAN-convolution hot path: KAN-VGG training images/s on synthetic data.
+
+    python bench.py --gpus N --steps K --warmup W                      # this repo's CUDA path ("b200" arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference algorithm on the host CPU cores
+
+Metric (BASELINE.json): "KAN-VGG train images/sec" - one step = forward + CrossEntropy + backward + AdamW on one batch of
+synthetic images.  Default workload = BASELINE config 5: KAN-VGG16 (KANConv2D, spline_order 3, grid_size 5, SiLU base
+activation, InstanceNorm, Linear head, expected_feature_shape (7,7)) on 3x224x224, per-GPU batch 64, weak scaling.
+Prints ONE JSON line (rank 0).  For N > 1 launch with torch.distributed.run (one rank per GPU, NCCL).
+
+Keys beyond the base contract:
+  roofline      - dominant kernel of the step (by summed device time), measured live with CUDA events on the launching
+                  stream in a separate instrumented pass of the SAME step: achieved = algorithmic FLOPs per launch
+                  (2*N*Ho*Wo*Cout*Cin*(nb+1)*kh*kw) / mean launch duration; peak = MEASURED_PEAKS.json.
+  cpu_baseline  - the oracle port of the reference algorithm (oracle/kan_oracle.py, PyTorch CPU, all host cores) timed on
+                  a bounded sample of the same workload (rank 0, N = 1 only).
+  e2e           - same metric through the public nn.Module API with HOST inputs: every step copies its pinned-host batch
+                  to the device and reads the loss back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+WORKLOADS = {
+    # name: (arch, H=W, classes, default per-GPU batch, expected_feature_shape, cpu sample batch)
+    "kan_vgg16_224": ("VGG16", 224, 1000, 64, (7, 7), 1),
+    "kan_vgg11_32": ("VGG11", 32, 10, 512, (1, 1), 16),
+    "kan_vgg16_small_32": ("VGG16_small", 32, 10, 256, (1, 1), 32),
+}
+
+
+def vgg_conv_shapes(arch, hw, cin=3):
+    """[(cin, cout, h)] of the KAN conv layers of a KAN-VGG (models/kan_vgg.py:119-130 semantics)."""
+    from oracle.kan_oracle import VGG_CFGS
+    out, c, h = [], cin, hw
+    for v in VGG_CFGS[arch]:
+        if v == "M":
+            h //= 2
+        else:
+            out.append((c, int(v), h))
+            c = int(v)
+    return out
+
+
+def step_flops(arch, hw, batch):
+    """Dense-equivalent FLOPs of one training step: fwd F, bwd 2F, no dgrad for the first layer."""
+    total = 0.0
+    for i, (ci, co, h) in enumerate(vgg_conv_shapes(arch, hw)):
+        f = 2.0 * batch * h * h * co * ci * 9 * 9
+        total += f * (3 if i > 0 else 2)
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            p = [v.strip() for v in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup, sample_batch=None):
+    from oracle import kan_oracle as O
+    arch, hw, classes, _, feat, cpu_b = WORKLOADS[workload]
+    b = sample_batch or cpu_b
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = O.OracleVGG(3, classes, arch=arch, expected_feature_shape=feat, dropout_linear=0.5)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    lossf = nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(b, 3, hw, hw, generator=g)
+    y = torch.randint(0, classes, (b,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = lossf(model(x), y)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return {"value": b / mean, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of batch {b} ({workload}, fp32, torch {torch.__version__} CPU, {torch.get_num_threads()} threads)",
+            "ms_per_step": mean * 1e3, "batch": b}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arch, hw, classes, batch, feat, _ = WORKLOADS[args.workload]
+    r = cpu_reference_run(args.workload, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "KAN-VGG train images/sec", "value": r["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "arch": arch, "image": [3, hw, hw], "classes": classes,
+                       "per_gpu_batch": batch, "sampled_batch": r["batch"], "impl": "oracle port of the reference (CPU)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# b200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import kanconv_b200 as K
+    from kanconv_b200 import functional as KF
+    from kanconv_b200.models import vggkan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (b200 arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = K._lib.load()
+    K.set_precision(args.precision)
+
+    arch, hw, classes, def_batch, feat, _ = WORKLOADS[args.workload]
+    batch = args.batch or def_batch
+    torch.manual_seed(0)
+    model = vggkan(3, classes, arch=arch, classifier_type="Linear", expected_feature_shape=feat, spline_order=3,
+                   grid_size=5).to(dev)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=64)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    lossf = nn.CrossEntropyLoss()
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(batch, 3, hw, hw, generator=g).pin_memory()
+    y_host = torch.randint(0, classes, (batch,), generator=g).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        loss = lossf(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg -------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.kc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    launches = lib.kc_launch_count() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: host inputs, H2D per step, loss read back per step ----------------------------------------
+    for _ in range(min(2, args.warmup)):
+        step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item()
+    barrier()
+    t0 = time.perf_counter()
+    f0 = torch.cuda.Event(enable_timing=True)
+    f1 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        xb = x_host.to(dev, non_blocking=True)
+        yb = y_host.to(dev, non_blocking=True)
+        last = step(xb, yb).item()              # device -> host read of the loss
+    f1.record()
+    barrier()
+    ms_e2e = max_over_ranks(f0.elapsed_time(f1)) / args.steps
+    wall_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+
+    # ---- roofline of the dominant kernel (instrumented pass of the same step, CUDA events per library call) --------
+    KF.profile_begin()
+    step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    prof = KF.profile_end()
+    sust, burst, hbm, peak_src = measured_peaks()
+    roof = None
+    if prof:
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        name, st = top
+        total_ms = sum(v["ms"] for v in prof.values())
+        if st["flops"] > 0:
+            ach = st["flops"] / (st["ms"] * 1e-3) / 1e12
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": sust, "unit": "TFLOP/s", "frac": ach / sust,
+                    "traffic": None, "launches_per_step": st["calls"], "ms_per_launch": st["ms"] / st["calls"],
+                    "share_of_library_time": st["ms"] / total_ms, "peak_source": peak_src + " (bf16_tflops_sustained; burst %.0f)" % burst}
+        else:
+            ach = st["bytes"] / (st["ms"] * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                    "traffic": None, "launches_per_step": st["calls"], "ms_per_launch": st["ms"] / st["calls"],
+                    "share_of_library_time": st["ms"] / total_ms, "peak_source": peak_src}
+        roof["by_kernel_ms"] = {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_run(args.workload, 1, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    gb = batch * world
+    flops = step_flops(arch, hw, batch)
+    line = {
+        "metric": "KAN-VGG train images/sec", "value": gb / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "arch": arch, "image": [3, hw, hw], "classes": classes, "per_gpu_batch": batch,
+                   "global_batch": gb, "parallelism": f"dp{world}", "optimizer": "AdamW(fused)", "precision": args.precision,
+                   "l2": "inputs+activations per step >> L2 (no flush needed)",
+                   "step_tflops_dense_equiv": flops / 1e12, "achieved_tflops_per_gpu": flops / (ms * 1e-3) / 1e12},
+        "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e, "last_loss": last},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kan_vgg16_224", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "b200" and args.gpus != world:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torch.distributed.run with --nproc-per-node {args.gpus} (WORLD_SIZE={world})")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

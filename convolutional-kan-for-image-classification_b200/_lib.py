@@ -32,6 +32,7 @@ _SIGNATURES = {
     "kc_version": (ctypes.c_int, []),
     "kc_last_error": (ctypes.c_char_p, []),
     "kc_device_info": (ctypes.c_int, [_P(ctypes.c_int)] * 3),
+    "kc_launch_count": (ctypes.c_longlong, []),
     "kc_conv_fwd_f32": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 7),
     "kc_conv_dgrad_f32": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 10),
     "kc_wgrad_workspace_bytes": (c_sz, [_P(KcDesc)]),

@@ -4,9 +4,15 @@
 
 #include "kc_common.cuh"
 
+#include <atomic>
+
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 }
+
+void kc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long kc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void kc_set_error(const char* fmt, ...) {
   va_list ap;

@@ -25,8 +25,10 @@ void kc_set_error(const char* fmt, ...);
     cudaError_t e__ = (expr);                                                            \
     if (e__ != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
+void kc_count_launch();   // per-process counter of kernels launched by this library (kc_launch_count in the ABI)
 #define KC_LAUNCH_CHECK(name)                                                            \
   do {                                                                                   \
+    kc_count_launch();                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
   } while (0)

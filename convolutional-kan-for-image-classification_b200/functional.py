@@ -68,6 +68,46 @@ class NormSpec:
     use_batch_stats: bool = True    # BatchNorm only: False -> normalise with the provided (running) statistics
 
 
+# ---- optional per-call device timing (bench.py's roofline leg): CUDA events on the launching stream ----------------------
+_PROFILE = None
+
+
+def profile_begin() -> None:
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end():
+    """-> {kernel name: {"ms", "calls", "flops", "bytes"}} summed over the calls since profile_begin()."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, flops, nbytes, e0, e1 in rec or []:
+        st = out.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+        st["ms"] += e0.elapsed_time(e1)
+        st["calls"] += 1
+        st["flops"] += flops
+        st["bytes"] += nbytes
+    return out
+
+
+def _timed(name: str, flops: float, nbytes: float, call):
+    if _PROFILE is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = call()
+    e1.record()
+    _PROFILE.append((name, flops, nbytes, e0, e1))
+    return rc
+
+
+def _conv_flops(d) -> float:
+    wb = d.nb + (0 if d.act == L.ACT_NONE else 1)
+    return 2.0 * d.n * d.ho * d.wo * d.cout * d.cin * wb * d.kh * d.kw
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -140,11 +180,13 @@ class _KanConvFn(torch.autograd.Function):
             if tc:
                 nbytes = lib.kc_tc_bytes(ctypes.byref(d), 0)
                 packed = torch.empty(nbytes, device=xb.device, dtype=torch.uint8)
-                L.check(lib.kc_tc_pack_weights(ctypes.byref(d), _ptr(wbg), _ptr(wsg), _ptr(packed), None, stream), "kc_tc_pack_weights")
-                L.check(lib.kc_conv_fwd_tc(ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), stream), "kc_conv_fwd_tc")
+                L.check(_timed("kc_pack_fwd_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
+                    ctypes.byref(d), _ptr(wbg), _ptr(wsg), _ptr(packed), None, stream)), "kc_tc_pack_weights")
+                L.check(_timed("kc_fwd_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
+                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), stream)), "kc_conv_fwd_tc")
             else:
-                L.check(lib.kc_conv_fwd_f32(ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream),
-                        "kc_conv_fwd_f32")
+                L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
+                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream)), "kc_conv_fwd_f32")
         ctx.spec, ctx.alias, ctx.precision, ctx.used_tc = spec, alias, precision, used_tc
         ctx.save_for_backward(xb, xs if not alias else None, beta, *weights)
         return z
@@ -185,16 +227,18 @@ class _KanConvFn(torch.autograd.Function):
             wbg = None if w_base[g] is None else w_base[g].contiguous()
             wsg = w_basis[g].contiguous()
             if run_dgrad:
-                L.check(lib.kc_conv_dgrad_f32(ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
-                                              _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbeta), stream), "kc_conv_dgrad_f32")
+                L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
+                    ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
+                    _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbeta), stream)), "kc_conv_dgrad_f32")
             wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
             if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
                 nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
                 ws = torch.empty(max(nbytes, 16), device=xb.device, dtype=torch.uint8)
                 dwb = torch.empty_like(wbg) if wbg is not None else None
                 dwsg = torch.empty_like(wsg)
-                L.check(lib.kc_conv_wgrad_f32(ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg),
-                                              _ptr(ws), stream), "kc_conv_wgrad_f32")
+                L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
+                    ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
+                    "kc_conv_wgrad_f32")
                 if wi_base is not None:
                     dws[wi_base] = dwb
                 dws[wi_basis] = dwsg
@@ -239,9 +283,9 @@ class _NormActFn(torch.autograd.Function):
                 else:
                     mean[g].copy_(given_mean[g * cg:(g + 1) * cg])
                     rstd[g].copy_(given_rstd[g * cg:(g + 1) * cg])
-            L.check(lib.kc_norm_act_fwd(ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
-                                        _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream),
-                    "kc_norm_act_fwd")
+            L.check(_timed("kc_instnorm_fwd_kernel", 0.0, 8.0 * n * cg * hw, lambda: lib.kc_norm_act_fwd(
+                ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
+                _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream)), "kc_norm_act_fwd")
         ctx.spec = spec
         ctx.save_for_backward(z, mean, rstd, *params)
         ctx.mark_non_differentiable(mean, rstd)
@@ -275,9 +319,9 @@ class _NormActFn(torch.autograd.Function):
             dbet = torch.empty_like(bet[g]) if spec.affine else None
             dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
             sl = slice(g * cg, (g + 1) * cg)
-            L.check(lib.kc_norm_act_bwd(ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]),
-                                        _ptr(bet[g]), _ptr(alp[g]), _ptr(dz[:, sl]), _ptr(dgam), _ptr(dbet), _ptr(dalp),
-                                        _ptr(partials), stream), "kc_norm_act_bwd")
+            L.check(_timed("kc_norm_bwd_kernel", 0.0, 12.0 * n * cg * hw, lambda: lib.kc_norm_act_bwd(
+                ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]), _ptr(bet[g]),
+                _ptr(alp[g]), _ptr(dz[:, sl]), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials), stream)), "kc_norm_act_bwd")
             if spec.affine:
                 grads[2 * g], grads[2 * g + 1] = dgam, dbet
             if dalp is not None:

@@ -84,6 +84,8 @@ int kc_version(void);
 const char* kc_last_error(void);
 /* Number of SMs / compute capability of the current device, for the binding's sanity check (returns KC_OK). */
 int kc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of CUDA kernels this library has launched in the calling process so far (monotonic; for bench accounting). */
+long long kc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * FP32 path (CUDA-core FFMA, fp32 accumulate): any kernel size / stride / dilation / padding, nb <= 16.
