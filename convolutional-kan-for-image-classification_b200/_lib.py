@@ -42,6 +42,7 @@ _SIGNATURES = {
     "kc_tc_supported": (ctypes.c_int, [_P(KcDesc)]),
     "kc_tc_bytes": (c_sz, [_P(KcDesc), ctypes.c_int]),
     "kc_tc_pack_weights": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 5),
+    "kc_tc_dz_flat": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 3),
     "kc_conv_fwd_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 6),
     "kc_conv_dgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 10),
     "kc_conv_wgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 8),

@@ -21,6 +21,8 @@
 #include "kc_common.cuh"
 #include "kc_umma.cuh"
 
+size_t kc_tc_wgrad_ws_bytes(const kc_desc* d);   // kc_tc_wgrad.cu
+
 namespace {
 
 using namespace kc;
@@ -59,7 +61,14 @@ struct TcFwdArgs {
   const unsigned char* wp;
   const float* beta;
   float* z;
+  // dgrad mode only
+  const unsigned char* dzf;     // bf16 [L][cq] flat, zero at padding / invalid output positions
+  int cq;                       // channels per flat row (cout rounded up to 16)
+  float* dx_base;
+  float* dx_basis;
 };
+
+constexpr int kModeFwd = 0, kModeDgrad = 1;
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -127,6 +136,24 @@ __device__ __noinline__ uint2 basis4(const KcBasisCtx& B, float x) {
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
 
+// d/dx of the uniform cubic B-spline weights dotted with 8 incoming gradients g[j] (closed form, Appendix A.2)
+__device__ __forceinline__ float cubic8_dot_grad(float x, float t0, float inv_h, int nintervals, const float* gsp) {
+  const float u = (x - t0) * inv_h;
+  if (!(u >= 0.0f) || !(u < (float)nintervals)) return 0.0f;
+  const float fi = floorf(u);
+  const float f = u - fi, omf = 1.0f - f;
+  const int i0 = (int)fi;
+  const float d0 = -0.5f * omf * omf, d1 = fmaf(1.5f * f, f, -2.0f * f), d2 = fmaf(fmaf(-1.5f, f, 1.0f), f, 0.5f), d3 = 0.5f * f * f;
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = j - (i0 - 3);
+    const float w = (r == 0) ? d0 : (r == 1) ? d1 : (r == 2) ? d2 : (r == 3) ? d3 : 0.0f;
+    acc = fmaf(gsp[j], w, acc);
+  }
+  return acc * inv_h;
+}
+
 __device__ __forceinline__ int chunk_cols(const TcGeom& g, int q) {
   return (q < g.nsc || q - g.nsc != g.nbc - 1) ? kPL : g.last_base_cols;
 }
@@ -149,7 +176,8 @@ __device__ __forceinline__ void issue_step(uint32_t tmem_base, uint32_t ntile, u
 // ---------------------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_constant__ TcFwdArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_constant__ TcFwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
@@ -172,7 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
   const int nt = blockIdx.y;
   const int T = d.kh * d.kw, HW = d.h * d.w;
   const bool has_base = d.act != KC_ACT_NONE;
-  const int nchunks = g.nsc + (has_base ? g.nbc : 0);
+  const int nchunks = (MODE == kModeDgrad) ? g.nbc : g.nsc + (has_base ? g.nbc : 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], kProdThreads); mbar_init(&a_empty[i], 1); }
@@ -202,10 +230,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
         int r = min(b / g.SS, d.kh - 1);
         long long q = qbase + (long long)r * g.P + (b - r * g.SS);
         if (q >= 0 && q < g.L) {
-          int n = (int)(q / g.IMG);
-          int rem = (int)(q - (long long)n * g.IMG);
-          int y = rem / g.P, x = rem - y * g.P;
-          if (y < d.h && x < d.w) off = (int)((long long)n * d.x_batch_stride + y * d.w + x);
+          if (MODE == kModeDgrad) {
+            off = (int)q;                 // the flat dz buffer is indexed by the flat position itself
+          } else {
+            int n = (int)(q / g.IMG);
+            int rem = (int)(q - (long long)n * g.IMG);
+            int y = rem / g.P, x = rem - y * g.P;
+            if (y < d.h && x < d.w) off = (int)((long long)n * d.x_batch_stride + y * d.w + x);
+          }
         }
       }
       offs[k] = off;
@@ -230,7 +262,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
     for (int q = 0; q < nchunks; ++q) {
       unsigned char* ab = abuf0 + buf * abuf_bytes;
       trp.stamp();                                   // chunk start
-      if (q < g.nsc && nb == 8) {
+      if (MODE == kModeDgrad) {
+        // copy chunk: k-core = 8 consecutive output channels of one flat position, read as one 16-byte vector
+        const int ncols = chunk_cols(g, q);
+        uint4 v[kRB][2];
+#pragma unroll
+        for (int k = 0; k < kRB; ++k)
+#pragma unroll
+          for (int cl = 0; cl < 2; ++cl) {
+            const int grp = q * kPL + half * 2 + cl;
+            v[k][cl] = (offs[k] >= 0 && grp * 8 < a.cq)
+                           ? __ldg(reinterpret_cast<const uint4*>(a.dzf + ((long long)offs[k] * a.cq + grp * 8) * 2))
+                           : make_uint4(0u, 0u, 0u, 0u);
+          }
+        mbar_wait(&a_empty[buf], aphase ^ 1);
+        trp.stamp();
+#pragma unroll
+        for (int k = 0; k < kRB; ++k) {
+          const int b = r0 + k * kRowThreads;
+#pragma unroll
+          for (int cl = 0; cl < 2; ++cl) {
+            const int pl = half * 2 + cl;
+            if (offs[k] != -2 && pl < ncols) reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v[k][cl];
+          }
+        }
+      } else if (q < g.nsc && nb == 8) {
         float xv[kRB][2];
 #pragma unroll
         for (int k = 0; k < kRB; ++k) { xv[k][0] = xnext[k][0]; xv[k][1] = xnext[k][1]; }
@@ -343,6 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
           const bool two = nk2 == 2;
           if (elect_one_sync()) {
             if (nsub == 4) issue_step<4>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+            else if (nsub == 3) issue_step<3>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
             else if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
             else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
             tc_commit(&b_empty[stage]);
@@ -379,7 +436,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
     }
     __syncwarp();
   }
-  if (warp < 4) {
+  if (MODE == kModeFwd && warp < 4) {
     // ================================ epilogue: TMEM -> registers -> z (fp32 NCHW) =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -411,6 +468,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_fwd_tc_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) {
           int co = n0 + c0 + j;
           if (valid && j < lim && co < d.cout) a.z[zoff + (long long)co * HoWo] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  if (MODE == kModeDgrad && warp < 4) {
+    // ================================ dgrad epilogue: dPhi (TMEM) x analytic basis derivative -> dx =======
+    // Columns of this N tile are (channel cl, j) with j < nb the basis gradients and j == nb the base-branch gradient;
+    // dPhi never leaves the SM (the reference's autograd materialises it, ~50 elementwise backward launches).
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int nb = d.nb, wb = nb + (has_base ? 1 : 0);
+    const bool alias = a.dx_base == a.dx_basis;
+    for (int i = 0; i < g.nsub; ++i) {
+      const long long q = m0 + i * kTileM + warp * 32 + lane;
+      bool valid = false;
+      long long off = 0;
+      if (q < g.L) {
+        int n = (int)(q / g.IMG);
+        int rem = (int)(q - (long long)n * g.IMG);
+        int y = rem / g.P, x = rem - y * g.P;
+        if (y < d.h && x < d.w) { valid = true; off = (long long)n * d.x_batch_stride + y * d.w + x; }
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * g.ntile);
+      for (int cl = 0; cl < 16; ++cl) {
+        const int c = nt * 16 + cl;
+        if (c >= d.cin) break;
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)(cl * wb), r);
+        tmem_ld_wait();
+        if (valid) {
+          const long long o = off + (long long)c * HW;
+          const float xs = __ldg(a.x_basis + o);
+          float gs = 0.0f;
+          if (g.fast_cubic) {
+            float gg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gg[j] = __uint_as_float(r[j]);
+            gs = cubic8_dot_grad(xs, g.t0, g.inv_h, B->nparams - 1, gg);
+          } else {
+            float phi[KC_MAX_BASIS], dphi[KC_MAX_BASIS];
+            kc_eval_basis(*B, xs, phi, dphi, 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nb) gs = fmaf(__uint_as_float(r[j]), dphi[j], gs);
+          }
+          float gb = 0.0f;
+          if (has_base) {
+            float ga = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j == nb) ga = __uint_as_float(r[j]);
+            gb = ga * kc_act_grad(d.act, __ldg(a.x_base + o));
+          }
+          if (alias) {
+            a.dx_basis[o] = gs + gb;
+          } else {
+            a.dx_basis[o] = gs;
+            if (has_base && a.dx_base != nullptr) a.dx_base[o] = gb;
+          }
         }
       }
     }
@@ -476,6 +592,75 @@ __global__ void __launch_bounds__(256) kc_pack_fwd_kernel(const __grid_constant_
   }
 }
 
+// dgrad weights: [ntile = 16 input channels][chunk of 32 couts][flipped tap][k-core = 8 couts][n = (cl, j)][8]
+__global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constant__ TcPackArgs a) {
+  const kc_desc& d = a.d;
+  const TcGeom& g = a.g;
+  const int T = d.kh * d.kw, nb = d.nb;
+  const bool has_base = d.act != KC_ACT_NONE;
+  const int wb = nb + (has_base ? 1 : 0);
+  const long long vec_per_ntile = g.wimg_bytes_per_ntile / 16;
+  const long long total = vec_per_ntile * g.n_ntiles;
+  const long long full_chunk = (long long)T * kPL * g.ntile;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const int nt = (int)(v / vec_per_ntile);
+    long long vl = v - (long long)nt * vec_per_ntile;
+    int bq = (int)min((long long)(g.nbc - 1), vl / full_chunk);
+    long long rem = vl - (long long)bq * full_chunk;
+    int ncols = (bq == g.nbc - 1) ? g.last_base_cols : kPL;
+    int t = (int)(rem / (ncols * g.ntile));
+    int rem2 = (int)(rem - (long long)t * ncols * g.ntile);
+    int kc = rem2 / g.ntile, nl = rem2 - kc * g.ntile;
+    const int c = nt * 16 + nl / wb, j = nl % wb, tap = T - 1 - t;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int co = (bq * kPL + kc) * 8 + e;
+      float w = 0.0f;
+      if (co < d.cout && c < d.cin) {
+        if (j < nb) w = a.w_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + tap];
+        else w = a.w_base[((long long)co * d.cin + c) * T + tap];
+      }
+      f[e] = w;
+    }
+    a.out[v] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+}
+
+// dz (fp32 NCHW) -> flat bf16 [L][cq]: position q = n*IMG + y*P + x, zero where (y, x) is not an output pixel.
+// 64 positions x 64 channels per block, transposed through shared memory (coalesced on both sides).
+__global__ void __launch_bounds__(256) kc_dz_flat_kernel(const __grid_constant__ kc_desc d, int P, int IMG, long long L, int cq,
+                                                         const float* __restrict__ dz, unsigned char* __restrict__ out) {
+  __shared__ float tile[64][65];
+  const long long q0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int HoWo = d.ho * d.wo;
+  for (int it = threadIdx.x; it < 64 * 64; it += 256) {
+    const int p = it & 63, c = it >> 6;
+    const long long q = q0 + p;
+    float v = 0.0f;
+    if (q < L && c0 + c < d.cout) {
+      int n = (int)(q / IMG);
+      int rem = (int)(q - (long long)n * IMG);
+      int y = rem / P, x = rem - y * P;
+      if (y < d.ho && x < d.wo) v = dz[(long long)n * d.z_batch_stride + (long long)(c0 + c) * HoWo + y * d.wo + x];
+    }
+    tile[c][p] = v;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < 64 * 8; it += 256) {
+    const int grp = it & 7, p = it >> 3;
+    const long long q = q0 + p;
+    if (q < L && c0 + grp * 8 < cq) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = tile[grp * 8 + e][p];
+      *reinterpret_cast<uint4*>(out + (q * cq + c0 + grp * 8) * 2) =
+          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host-side geometry
 // ---------------------------------------------------------------------------------------------------------
@@ -495,33 +680,14 @@ bool knots_uniform_cubic(const kc_desc* d, float* t0, float* inv_h) {
 
 size_t tc_fixed_smem() { return (size_t)kNumBars * 8 + 16 + sizeof(KcBasisCtx) + 128; }
 
-int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
-  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs stride 1 and dilation 1");
-  if (d->nb != 8 && d->nb != 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs basis width 4 or 8 (got %d)", d->nb);
-  if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs padding < kernel size");
-  if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs kernel size <= 8");
-  if ((long long)d->n * d->x_batch_stride >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs < 2^31 input elements");
-  memset(g, 0, sizeof(*g));
-  const bool has_base = d->act != KC_ACT_NONE;
-  const int T = d->kh * d->kw;
-  g->cps = (d->nb == 8) ? 4 : 8;
-  g->Cp = round_up(d->cin, 8);
-  g->nsc = g->Cp / g->cps;
-  g->ngroups = g->Cp / 8;
-  g->nbc = has_base ? (g->ngroups + kPL - 1) / kPL : 0;
-  g->last_base_cols = has_base ? round_up(g->ngroups - (g->nbc - 1) * kPL, 2) : 0;
-  g->ph = d->pad_h; g->pw = d->pad_w;
-  g->P = d->w + d->pad_w;
-  g->IMG = (d->h + d->pad_h) * g->P;
-  g->L = (long long)d->n * g->IMG;
-  int want_tiles = (d->cout + 255) / 256;
-  g->ntile = round_up((d->cout + want_tiles - 1) / want_tiles, 16);
-  g->n_ntiles = (d->cout + g->ntile - 1) / g->ntile;
+// Common tail of the forward / dgrad geometry: choose nsub, ring depths and shared-memory carve-up.
+// kcores = total number of 16-byte k-cores per tap in the weight image of one N tile.
+int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
   const size_t bstage = (size_t)kPL * g->ntile * 16;
   // nsub: as many 128-row sub-tiles per CTA as TMEM (512 columns), the producer row mapping (1024 rows), shared memory
   // and the wish for >= 2 waves of CTAs allow.
   bool found = false;
-  for (int nsub = 4; nsub >= 1 && !found; nsub >>= 1) {
+  for (int nsub = 4; nsub >= 1 && !found; --nsub) {
     if (nsub * g->ntile > 512) continue;
     const int mcta = nsub * kTileM;
     const int seglen = round_up(mcta + d->kw - 1, 8);
@@ -544,10 +710,62 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
   if (!found) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path: tile does not fit shared memory");
   g->tmem_cols = 32;
   while (g->tmem_cols < g->nsub * g->ntile) g->tmem_cols *= 2;
-  int base_cols = has_base ? (g->nbc - 1) * kPL + g->last_base_cols : 0;
-  g->wimg_bytes_per_ntile = (long long)T * g->ntile * 16 * (g->nsc * kPL + base_cols);
+  g->wimg_bytes_per_ntile = (long long)T * g->ntile * 16 * kcores;
   g->fast_cubic = knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
   return KC_OK;
+}
+
+int tc_common_checks(const kc_desc* d) {
+  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs stride 1 and dilation 1");
+  if (d->nb != 8 && d->nb != 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs basis width 4 or 8 (got %d)", d->nb);
+  if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs padding < kernel size");
+  if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs kernel size <= 8");
+  if ((long long)d->n * d->x_batch_stride >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs < 2^31 input elements");
+  return KC_OK;
+}
+
+// dgrad GEMM: rows = input positions, K = (tap, cout), N = (channel, basis j | base) in tiles of 16 channels.
+int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
+  int rc = tc_common_checks(d);
+  if (rc != KC_OK) return rc;
+  if (d->basis == KC_BASIS_GRAM) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core dgrad: GRAM beta gradient is computed by the FP32 kernel");
+  memset(g, 0, sizeof(*g));
+  const bool has_base = d->act != KC_ACT_NONE;
+  const int T = d->kh * d->kw, wb = d->nb + (has_base ? 1 : 0);
+  const int cq = round_up(d->cout, 16), planes = cq / 8;
+  g->Cp = cq; g->cps = 0; g->nsc = 0; g->ngroups = planes;
+  g->nbc = (planes + kPL - 1) / kPL;
+  g->last_base_cols = planes - (g->nbc - 1) * kPL;
+  g->ph = d->kh - 1 - d->pad_h; g->pw = d->kw - 1 - d->pad_w;      // transposed convolution: flipped taps
+  g->P = d->w + d->pad_w;
+  g->IMG = (d->h + d->pad_h) * g->P;
+  g->L = (long long)d->n * g->IMG;
+  if (g->L >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core dgrad needs < 2^31 flat positions");
+  g->ntile = 16 * wb;
+  g->n_ntiles = (d->cin + 15) / 16;
+  return tc_fit(d, g, T, planes);
+}
+
+int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
+  int rc0 = tc_common_checks(d);
+  if (rc0 != KC_OK) return rc0;
+  memset(g, 0, sizeof(*g));
+  const bool has_base = d->act != KC_ACT_NONE;
+  const int T = d->kh * d->kw;
+  g->cps = (d->nb == 8) ? 4 : 8;
+  g->Cp = round_up(d->cin, 8);
+  g->nsc = g->Cp / g->cps;
+  g->ngroups = g->Cp / 8;
+  g->nbc = has_base ? (g->ngroups + kPL - 1) / kPL : 0;
+  g->last_base_cols = has_base ? round_up(g->ngroups - (g->nbc - 1) * kPL, 2) : 0;
+  g->ph = d->pad_h; g->pw = d->pad_w;
+  g->P = d->w + d->pad_w;
+  g->IMG = (d->h + d->pad_h) * g->P;
+  g->L = (long long)d->n * g->IMG;
+  int want_tiles = (d->cout + 255) / 256;
+  g->ntile = round_up((d->cout + want_tiles - 1) / want_tiles, 16);
+  g->n_ntiles = (d->cout + g->ntile - 1) / g->ntile;
+  return tc_fit(d, g, T, (has_base ? (g->nbc - 1) * kPL + g->last_base_cols : 0) + g->nsc * kPL);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -649,6 +867,11 @@ extern "C" size_t kc_tc_bytes(const kc_desc* d, int which) {
   TcGeom g;
   if (tc_forward_geometry(d, &g) != KC_OK) return 0;
   if (which == 0) return (size_t)g.wimg_bytes_per_ntile * g.n_ntiles;
+  TcGeom gd;
+  if (tc_dgrad_geometry(d, &gd) != KC_OK) return 0;
+  if (which == 1) return (size_t)gd.wimg_bytes_per_ntile * gd.n_ntiles;
+  if (which == 2) return (size_t)gd.L * gd.Cp * 2;
+  if (which == 3) return kc_tc_wgrad_ws_bytes(d);
   return 0;
 }
 
@@ -659,16 +882,41 @@ extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const f
   TcGeom g;
   rc = tc_forward_geometry(d, &g);
   if (rc != KC_OK) return rc;
-  if (!w_basis || !packed_fwd) KC_FAIL(KC_ERR_INVALID, "kc_tc_pack_weights: null pointer");
+  if (!w_basis || (!packed_fwd && !packed_dgrad)) KC_FAIL(KC_ERR_INVALID, "kc_tc_pack_weights: null pointer");
   if (d->act != KC_ACT_NONE && !w_base) KC_FAIL(KC_ERR_INVALID, "kc_tc_pack_weights: base branch needs w_base");
-  (void)packed_dgrad;
   TcPackArgs a;
   a.d = *d; a.g = g; a.w_base = w_base; a.w_basis = w_basis; a.out = (uint4*)packed_fwd;
   long long total = g.wimg_bytes_per_ntile / 16 * g.n_ntiles;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  kc_pack_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
-  KC_LAUNCH_CHECK("kc_pack_fwd_kernel");
+  if (packed_fwd != nullptr) {
+    kc_pack_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    KC_LAUNCH_CHECK("kc_pack_fwd_kernel");
+  }
+  if (packed_dgrad != nullptr) {
+    TcGeom gd;
+    rc = tc_dgrad_geometry(d, &gd);
+    if (rc != KC_OK) return rc;
+    a.g = gd; a.out = (uint4*)packed_dgrad;
+    total = gd.wimg_bytes_per_ntile / 16 * gd.n_ntiles;
+    blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    kc_pack_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    KC_LAUNCH_CHECK("kc_pack_dgrad_kernel");
+  }
+  return KC_OK;
+}
+
+extern "C" int kc_tc_dz_flat(const kc_desc* d, const float* dz, void* dz_flat, void* stream) {
+  int rc = kc_validate_desc(d);
+  if (rc != KC_OK) return rc;
+  TcGeom g;
+  rc = tc_dgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  if (!dz || !dz_flat) KC_FAIL(KC_ERR_INVALID, "kc_tc_dz_flat: null pointer");
+  dim3 grid((unsigned)((g.L + 63) / 64), (unsigned)((g.Cp + 63) / 64));
+  kc_dz_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, g.P, g.IMG, g.L, g.Cp, dz, (unsigned char*)dz_flat);
+  KC_LAUNCH_CHECK("kc_dz_flat_kernel");
   return KC_OK;
 }
 
@@ -684,26 +932,36 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
   if (d->basis == KC_BASIS_GRAM && !beta) KC_FAIL(KC_ERR_INVALID, "kc_conv_fwd_tc: GRAM basis needs beta_weights");
   if (g.mtiles > 0x7fffffffLL) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_fwd_tc: too many tiles");
   TcFwdArgs a;
+  memset(&a, 0, sizeof(a));
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.wp = (const unsigned char*)packed_fwd; a.beta = beta; a.z = z;
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
-  kc_fwd_tc_kernel<<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
-  KC_LAUNCH_CHECK("kc_fwd_tc_kernel");
+  kc_tc_kernel<kModeFwd><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  KC_LAUNCH_CHECK("kc_tc_kernel<fwd>");
   return KC_OK;
 }
 
 extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                                 const void* packed_dgrad, const float* beta, float* dx_base, float* dx_basis,
                                 float* dbeta, void* workspace, void* stream) {
-  (void)d; (void)dz; (void)x_base; (void)x_basis; (void)packed_dgrad; (void)beta; (void)dx_base; (void)dx_basis;
-  (void)dbeta; (void)workspace; (void)stream;
-  KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_dgrad_tc: not built yet");
-}
-
-extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
-                                const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream) {
-  (void)d; (void)dz; (void)x_base; (void)x_basis; (void)beta; (void)dw_base; (void)dw_basis; (void)workspace; (void)stream;
-  KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_wgrad_tc: not built yet");
+  (void)dz; (void)dbeta;
+  int rc = kc_validate_desc(d);
+  if (rc != KC_OK) return rc;
+  TcGeom g;
+  rc = tc_dgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  if (!x_basis || !packed_dgrad || !dx_basis || !workspace) KC_FAIL(KC_ERR_INVALID, "kc_conv_dgrad_tc: null pointer");
+  if (d->act != KC_ACT_NONE && !x_base) KC_FAIL(KC_ERR_INVALID, "kc_conv_dgrad_tc: base branch needs x_base");
+  if (g.mtiles > 0x7fffffffLL) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_dgrad_tc: too many tiles");
+  TcFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.wp = (const unsigned char*)packed_dgrad; a.beta = beta;
+  a.dzf = (const unsigned char*)workspace; a.cq = g.Cp; a.dx_base = dx_base; a.dx_basis = dx_basis;
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
+  kc_tc_kernel<kModeDgrad><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  KC_LAUNCH_CHECK("kc_tc_kernel<dgrad>");
+  return KC_OK;
 }
 
 // Debug only: raw tcgen05.mma rate from resident smem operands, with knobs that mimic the convolution main loop:

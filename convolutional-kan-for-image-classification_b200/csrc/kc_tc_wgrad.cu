@@ -1,0 +1,429 @@
+// kc_tc_wgrad.cu - BF16 tensor-core weight gradient of the KAN convolution (tcgen05 / TMEM), sm_100a.
+//
+//   dW[cout][tap][c, j] = sum over flat output positions m of  dz[m][cout] * Phi_j(x[m + off(tap)][c])      (j = nb: base act)
+//
+// GEMM view per CTA: D[M = 128 expanded input rows (16 channels x 8 basis, or 128 base channels)][N = cout tile] for the
+// kw taps of ONE filter row r, reduced over a range of 64-position blocks (split-K).  Both operands are "MN-major"
+// no-swizzle UMMA layouts whose K dimension (positions) runs along 16-byte rows:
+//   A = Phi  planes [channel (8 j) | 8-channel group][row = position + tap shift][8 x bf16]   - evaluated on the fly
+//   B = dz   planes [8 couts][row = position][8 x bf16]                                        - 16-byte copies of the
+//                                                                                               flat bf16 dz buffer
+// so the three taps of the filter row are again shifted VIEWS (start row + s) of the same Phi buffer and the expanded
+// tensor never exists in HBM.  Each tap has its own TMEM accumulator (kw * N <= 512 columns).  Partial sums go to a
+// workspace [split][unit][s][128][N] and kc_wgrad_tc_reduce_kernel adds the splits in fixed order (deterministic) while
+// scattering into the reference's parameter layouts.
+#include <string.h>
+
+#include "kc_common.cuh"
+#include "kc_umma.cuh"
+
+namespace {
+
+using namespace kc;
+
+constexpr int kThreadsW = 576;       // warps 0-15 producers / epilogue, 16 idle, 17 MMA issuer
+constexpr int kProdW = 512;
+constexpr int kMmaWarpW = 17;
+constexpr int kKS = 64;              // positions per pipeline stage (4 MMA k-steps)
+constexpr int kMaxStagesW = 6;
+constexpr size_t kSmemLimitW = 227 * 1024;
+
+struct WgGeom {
+  int P, IMG;
+  long long L;
+  int cq;                       // channels per row of the flat dz buffer
+  int cps;                      // input channels per spline chunk (16 for nb = 8, 32 for nb = 4)
+  int nsc, nbc, nchunks;        // spline / base chunks (M = 128 rows each)
+  int ntile, n_ct;              // cout tile (MMA N), number of cout tiles
+  int units;                    // n_ct * nchunks * kh
+  int arows, aplane_bytes;      // Phi rows per stage (kKS + kw - 1, padded), plane pitch
+  int bplanes, bplane_bytes;
+  int stages, stage_bytes, a_bytes;
+  int tmem_cols;
+  long long nblk;               // 64-position blocks in total
+  int nsplit;
+  long long blk_per_split;
+  size_t smem_bytes;
+  size_t ws_bytes;
+  int fast_cubic;
+  float t0, inv_h;
+};
+
+struct WgArgs {
+  kc_desc d;
+  WgGeom g;
+  const float* x_base;
+  const float* x_basis;
+  const unsigned char* dzf;
+  const float* beta;
+  float* ws;
+};
+
+__host__ __device__ inline int round_up_w(int a, int b) { return (a + b - 1) / b * b; }
+
+__device__ __forceinline__ unsigned long long shl64w(unsigned long long v, int s) {
+  unsigned long long r;
+  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
+  return r;
+}
+__device__ __forceinline__ unsigned long long shr64w(unsigned long long v, int s) {
+  unsigned long long r;
+  asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
+  return r;
+}
+// uniform cubic B-spline, closed form, branch-free (same as the forward kernel's producer)
+__device__ __forceinline__ uint4 cubic8w(float x, float t0, float inv_h, int nintervals, bool valid) {
+  const float u = (x - t0) * inv_h;
+  const bool ok = valid && (u >= 0.0f) && (u < (float)nintervals);
+  const float fi = floorf(u);
+  const float f = u - fi;
+  const int i0 = min(max((int)fi, 0), 15);
+  const float s6 = 1.0f / 6.0f;
+  const float w0 = fmaf(fmaf(fmaf(-s6, f, 0.5f), f, -0.5f), f, s6);
+  const float w1 = fmaf(fmaf(0.5f, f, -1.0f) * f, f, 4.0f * s6);
+  const float w2 = fmaf(fmaf(fmaf(-0.5f, f, 0.5f), f, 0.5f), f, s6);
+  const float w3 = f * f * f * s6;
+  unsigned long long v = (unsigned long long)pack_bf16(w0, w1) | ((unsigned long long)pack_bf16(w2, w3) << 32);
+  v = ok ? v : 0ull;
+  const int sh = 16 * (i0 - 3);
+  const unsigned long long lo = shl64w(v, sh) | shr64w(v, -sh);
+  const unsigned long long hi = shr64w(v, 64 - sh) | shl64w(v, sh - 64);
+  return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+}
+__device__ __noinline__ uint4 basis8w_generic(const KcBasisCtx& B, float x) {
+  float phi[KC_MAX_BASIS];
+  kc_eval_basis(B, x, phi, nullptr, 1);
+  return make_uint4(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]), pack_bf16(phi[4], phi[5]), pack_bf16(phi[6], phi[7]));
+}
+__device__ __noinline__ uint2 basis4w(const KcBasisCtx& B, float x) {
+  float phi[KC_MAX_BASIS];
+  kc_eval_basis(B, x, phi, nullptr, 1);
+  return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
+}
+
+__global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_constant__ WgArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const kc_desc& d = a.d;
+  const WgGeom& g = a.g;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * g.stage_bytes);
+  uint64_t* full = bars;                         // [kMaxStagesW]
+  uint64_t* empty = bars + kMaxStagesW;          // [kMaxStagesW]
+  uint64_t* acc_full = bars + 2 * kMaxStagesW;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesW + 1);
+  KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = d.h * d.w;
+  // unit = ((cout tile * nchunks + chunk) * kh + r)
+  const int unit = blockIdx.x, split = blockIdx.y;
+  const int r = unit % d.kh;
+  const int chunk = (unit / d.kh) % g.nchunks;
+  const int ct = unit / (d.kh * g.nchunks);
+  const bool is_base = chunk >= g.nsc;
+  const long long blk0 = (long long)split * g.blk_per_split;
+  const long long blk1 = min(g.nblk, blk0 + g.blk_per_split);
+  const int nblocks = (int)(blk1 - blk0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxStagesW; ++i) { mbar_init(&full[i], kProdW); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarpW) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
+  kc_load_basis_ctx(B, d, a.beta);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 16) {
+    // ============================ producers: Phi (A) evaluated on the fly, dz (B) copied ===========================
+    const int tid = threadIdx.x;
+    // static A items of this thread: it = tid + 512*k  ->  row = it % arows, plane = it / arows
+    const int nAitems = g.arows * 16;
+    int row_k[3], plane_k[3];
+    long long q_k[3];
+    const long long qoff = (long long)(r - d.pad_h) * g.P - d.pad_w;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int it = tid + kProdW * k;
+      row_k[k] = it % g.arows;
+      plane_k[k] = (it < nAitems) ? it / g.arows : -1;
+      q_k[k] = blk0 * kKS + qoff + row_k[k];
+    }
+    const int nb = d.nb, cin = d.cin;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      unsigned char* As = smem + (size_t)st * g.stage_bytes;
+      unsigned char* Bs = As + g.a_bytes;
+      const long long m0 = (blk0 + bi) * kKS;
+      // ---- global loads first (latency overlaps the wait for the stage) ----
+      float xv[3][8];
+      int nld = is_base ? 8 : (nb == 8 ? 1 : 2);
+      bool okk[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        okk[k] = false;
+        const long long q = q_k[k];
+        if (plane_k[k] >= 0 && q >= 0 && q < g.L) {
+          const int n = (int)(q / g.IMG);
+          const int rem = (int)(q - (long long)n * g.IMG);
+          const int y = rem / g.P, x = rem - y * g.P;
+          if (y < d.h && x < d.w) {
+            okk[k] = true;
+            const long long off = (long long)n * d.x_batch_stride + y * d.w + x;
+            const int c0 = is_base ? ((chunk - g.nsc) * 128 + plane_k[k] * 8) : (chunk * g.cps + plane_k[k] * (nb == 8 ? 1 : 2));
+            const float* src = (is_base ? a.x_base : a.x_basis) + off + (long long)c0 * HW;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[k][i] = (i < nld && c0 + i < cin) ? __ldg(src + (long long)i * HW) : 0.0f;
+          }
+        }
+        if (!okk[k]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xv[k][i] = 0.0f;
+        }
+        q_k[k] += kKS;
+      }
+      // dz vectors: it -> plane = it % bplanes (fastest: contiguous in global), row = it / bplanes
+      uint4 dzv[3];
+      const int nBitems = kKS * g.bplanes;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int it = tid + kProdW * k;
+        dzv[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (it < nBitems) {
+          const int pl = it % g.bplanes, row = it / g.bplanes;
+          const long long m = m0 + row;
+          const int co = ct * g.ntile + pl * 8;
+          if (m < g.L && co < g.cq) dzv[k] = __ldg(reinterpret_cast<const uint4*>(a.dzf + (m * g.cq + co) * 2));
+        }
+      }
+      mbar_wait(&empty[st], ph ^ 1);
+      // ---- evaluate / convert and store ----
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (plane_k[k] < 0) continue;
+        uint4 v;
+        if (is_base) {
+          const int c0 = (chunk - g.nsc) * 128 + plane_k[k] * 8;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = (okk[k] && c0 + i < cin) ? kc_act(d.act, xv[k][i]) : 0.0f;
+          v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        } else if (nb == 8) {
+          const int c = chunk * g.cps + plane_k[k];
+          const bool ok = okk[k] && c < cin;
+          if (g.fast_cubic) v = cubic8w(xv[k][0], g.t0, g.inv_h, B->nparams - 1, ok);
+          else v = ok ? basis8w_generic(*B, xv[k][0]) : make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          const int c = chunk * g.cps + plane_k[k] * 2;
+          uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+          if (okk[k]) {
+            if (c < cin) lo = basis4w(*B, xv[k][0]);
+            if (c + 1 < cin) hi = basis4w(*B, xv[k][1]);
+          }
+          v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        }
+        reinterpret_cast<uint4*>(As + plane_k[k] * g.aplane_bytes)[row_k[k]] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int it = tid + kProdW * k;
+        if (it < nBitems) {
+          const int pl = it % g.bplanes, row = it / g.bplanes;
+          reinterpret_cast<uint4*>(Bs + pl * g.bplane_bytes)[row] = dzv[k];
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full[st]);
+      if (++st == g.stages) { st = 0; ph ^= 1; }
+    }
+  }
+  if (warp == kMmaWarpW) {
+    // ============================ MMA issuer (whole warp uniform, one elected lane issues) ==========================
+    const uint32_t idesc = make_idesc_bf16(128, g.ntile, 1, 1);        // both operands MN-major
+    const uint32_t lo_c = (128u >> 4) << 16;                            // LBO = 128 B between 8-row K groups
+    const uint32_t a_hi = ((uint32_t)g.aplane_bytes >> 4) | (1u << 14); // SBO = plane pitch (8 M rows), version 1
+    const uint32_t b_hi = ((uint32_t)g.bplane_bytes >> 4) | (1u << 14);
+    const uint32_t smem_u = smem_u32(smem) >> 4, stage_u = (uint32_t)g.stage_bytes >> 4, a_u = (uint32_t)g.a_bytes >> 4;
+    const int kw = d.kw, ntile = g.ntile;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t au = smem_u + (uint32_t)st * stage_u, bu = au + a_u;
+      const uint32_t first = bi != 0 ? 1u : 0u;
+      if (elect_one_sync()) {
+        for (int s = 0; s < kw; ++s) {
+          const uint32_t td = tmem_base + (uint32_t)(s * ntile);
+#pragma unroll
+          for (int ks = 0; ks < kKS / 16; ++ks) {
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(lo_c | (au + (uint32_t)(s + 16 * ks)));
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(lo_c | (bu + (uint32_t)(16 * ks)));
+            tc_mma_bf16(td, ad, bd, idesc, ks == 0 ? first : 1u);
+          }
+        }
+        tc_commit(&empty[st]);
+      }
+      __syncwarp();
+      if (++st == g.stages) { st = 0; ph ^= 1; }
+    }
+    if (elect_one_sync()) tc_commit(acc_full);
+    __syncwarp();
+  }
+  if (warp < 16) {
+    // ============================ epilogue: TMEM -> fp32 partial sums in the split workspace ========================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3, cgrp = warp >> 2;
+    const int m = quarter * 32 + lane;
+    const int ncol16 = d.kw * g.ntile / 16;
+    float* wsu = a.ws + ((long long)split * g.units + unit) * ((long long)d.kw * 128 * g.ntile);
+    for (int c16 = cgrp; c16 < ncol16; c16 += 4) {
+      uint32_t rr[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c16 * 16), rr);
+      tmem_ld_wait();
+      const int col = c16 * 16, s = col / g.ntile, n = col - s * g.ntile;
+      float4* dst = reinterpret_cast<float4*>(wsu + ((long long)s * 128 + m) * g.ntile + n);
+      const bool live = nblocks > 0;
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        dst[v4] = live ? make_float4(__uint_as_float(rr[4 * v4]), __uint_as_float(rr[4 * v4 + 1]), __uint_as_float(rr[4 * v4 + 2]),
+                                     __uint_as_float(rr[4 * v4 + 3]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarpW) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+// Sum the splits (fixed order) and scatter into the reference layouts dw_basis [cout][cin*nb][kh][kw] (inner index
+// c*nb+j, or j*cin+c for GRAM) and dw_base [cout][cin][kh][kw].
+__global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_kernel(const __grid_constant__ kc_desc d, const __grid_constant__ WgGeom g,
+                                                                 const float* __restrict__ ws, float* __restrict__ dw_base,
+                                                                 float* __restrict__ dw_basis) {
+  const bool has_base = d.act != KC_ACT_NONE;
+  const int nb = d.nb, wb = nb + (has_base ? 1 : 0), T = d.kh * d.kw;
+  const long long total = (long long)d.cout * d.cin * wb * T;
+  const long long unit_sz = (long long)d.kw * 128 * g.ntile;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i enumerates [co][c][j (wb)][tap]
+    const int tap = (int)(i % T);
+    long long rest = i / T;
+    const int j = (int)(rest % wb); rest /= wb;
+    const int c = (int)(rest % d.cin);
+    const int co = (int)(rest / d.cin);
+    const int r = tap / d.kw, s = tap - r * d.kw;
+    const int ct = co / g.ntile, n = co - ct * g.ntile;
+    int chunk, m;
+    if (j < nb) { chunk = c / g.cps; m = (c - chunk * g.cps) * nb + j; }
+    else { chunk = g.nsc + c / 128; m = c % 128; }
+    const long long unit = ((long long)ct * g.nchunks + chunk) * d.kh + r;
+    const float* p = ws + unit * unit_sz + ((long long)s * 128 + m) * g.ntile + n;
+    float acc = 0.0f;
+    for (int k = 0; k < g.nsplit; ++k) acc += p[(long long)k * g.units * unit_sz];
+    if (j < nb) dw_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + tap] = acc;
+    else dw_base[((long long)co * d.cin + c) * T + tap] = acc;
+  }
+}
+
+bool knots_uniform_cubic_w(const kc_desc* d, float* t0, float* inv_h) {
+  if (d->basis != KC_BASIS_BSPLINE || d->order != 3 || d->nb != 8 || d->nparams != 12) return false;
+  double h = ((double)d->params[11] - (double)d->params[0]) / 11.0;
+  if (!(h > 0)) return false;
+  for (int i = 0; i < 12; ++i) {
+    double e = (double)d->params[0] + h * i - (double)d->params[i];
+    if (e < 0) e = -e;
+    if (e > 1e-5 * h) return false;
+  }
+  *t0 = d->params[0];
+  *inv_h = (float)(1.0 / h);
+  return true;
+}
+
+int wgrad_geometry(const kc_desc* d, WgGeom* g) {
+  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs stride 1 and dilation 1");
+  if (d->nb != 8 && d->nb != 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs basis width 4 or 8 (got %d)", d->nb);
+  if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs padding < kernel size");
+  if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs kernel size <= 8");
+  if ((long long)d->n * d->x_batch_stride >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs < 2^31 input elements");
+  memset(g, 0, sizeof(*g));
+  const bool has_base = d->act != KC_ACT_NONE;
+  g->P = d->w + d->pad_w;
+  g->IMG = (d->h + d->pad_h) * g->P;
+  g->L = (long long)d->n * g->IMG;
+  if (g->L >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs < 2^31 flat positions");
+  g->cq = round_up_w(d->cout, 16);
+  g->cps = 128 / d->nb;
+  g->nsc = (d->cin + g->cps - 1) / g->cps;
+  g->nbc = has_base ? (d->cin + 127) / 128 : 0;
+  g->nchunks = g->nsc + g->nbc;
+  int nmax = (512 / d->kw) / 16 * 16;
+  if (nmax > 256) nmax = 256;
+  int want = (g->cq + nmax - 1) / nmax;
+  g->ntile = round_up_w((g->cq + want - 1) / want, 16);
+  g->n_ct = (g->cq + g->ntile - 1) / g->ntile;
+  g->units = g->n_ct * g->nchunks * d->kh;
+  g->arows = round_up_w(kKS + d->kw - 1, 8);
+  g->aplane_bytes = g->arows * 16 + 16;
+  g->a_bytes = 16 * g->aplane_bytes;
+  g->bplanes = g->ntile / 8;
+  g->bplane_bytes = kKS * 16 + 16;
+  g->stage_bytes = round_up_w(g->a_bytes + g->bplanes * g->bplane_bytes, 128);
+  if (g->arows * 16 > 3 * kProdW || kKS * g->bplanes > 3 * kProdW) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage too large for the producer mapping");
+  size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 128;
+  g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
+  if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
+  if (g->stages < 2) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
+  g->smem_bytes = fixed + (size_t)g->stages * g->stage_bytes;
+  g->tmem_cols = 32;
+  while (g->tmem_cols < d->kw * g->ntile) g->tmem_cols *= 2;
+  g->nblk = (g->L + kKS - 1) / kKS;
+  long long want_split = (3LL * 148 + g->units - 1) / g->units;
+  long long max_split = g->nblk / 16 > 0 ? g->nblk / 16 : 1;       // at least 16 blocks (1024 positions) per CTA
+  long long ns = want_split < 1 ? 1 : want_split;
+  if (ns > max_split) ns = max_split;
+  g->blk_per_split = (g->nblk + ns - 1) / ns;
+  g->nsplit = (int)((g->nblk + g->blk_per_split - 1) / g->blk_per_split);
+  g->ws_bytes = (size_t)g->nsplit * g->units * d->kw * 128 * g->ntile * sizeof(float);
+  g->fast_cubic = knots_uniform_cubic_w(d, &g->t0, &g->inv_h) ? 1 : 0;
+  return KC_OK;
+}
+
+}  // namespace
+
+size_t kc_tc_wgrad_ws_bytes(const kc_desc* d) {
+  WgGeom g;
+  if (wgrad_geometry(d, &g) != KC_OK) return 0;
+  return g.ws_bytes;
+}
+
+extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base, const float* x_basis,
+                                const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream) {
+  int rc = kc_validate_desc(d);
+  if (rc != KC_OK) return rc;
+  WgGeom g;
+  rc = wgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  if (!dz_flat || !x_basis || !dw_basis || !workspace) KC_FAIL(KC_ERR_INVALID, "kc_conv_wgrad_tc: null pointer");
+  if (d->act != KC_ACT_NONE && (!x_base || !dw_base)) KC_FAIL(KC_ERR_INVALID, "kc_conv_wgrad_tc: base branch needs x_base and dw_base");
+  if (d->basis == KC_BASIS_GRAM && !beta) KC_FAIL(KC_ERR_INVALID, "kc_conv_wgrad_tc: GRAM basis needs beta_weights");
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.dzf = (const unsigned char*)dz_flat; a.beta = beta;
+  a.ws = (float*)workspace;
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
+  kc_wgrad_tc_kernel<<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  KC_LAUNCH_CHECK("kc_wgrad_tc_kernel");
+  const int wb = d->nb + (d->act != KC_ACT_NONE ? 1 : 0);
+  long long total = (long long)d->cout * d->cin * wb * d->kh * d->kw;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  kc_wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
+  KC_LAUNCH_CHECK("kc_wgrad_tc_reduce_kernel");
+  return KC_OK;
+}

@@ -12,6 +12,7 @@ intermediates of the reference never exist.  CPU tensors are rejected: there is 
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -19,6 +20,7 @@ import torch
 
 from . import _lib as L
 
+_TC_BACKWARD = os.environ.get("KANCONV_TC_BACKWARD", "1") != "0"   # debug switch: FP32 CUDA-core backward after a TC forward
 _PRECISION = "auto"      # "auto": tensor cores when the shape is supported, else CUDA-core FP32 | "bf16" | "fp32"
 
 
@@ -182,7 +184,7 @@ class _KanConvFn(torch.autograd.Function):
                 packed = torch.empty(nbytes, device=xb.device, dtype=torch.uint8)
                 L.check(_timed("kc_pack_fwd_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
                     ctypes.byref(d), _ptr(wbg), _ptr(wsg), _ptr(packed), None, stream)), "kc_tc_pack_weights")
-                L.check(_timed("kc_fwd_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
+                L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
                     ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), stream)), "kc_conv_fwd_tc")
             else:
                 L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
@@ -226,19 +228,40 @@ class _KanConvFn(torch.autograd.Function):
             xbg, xsg, dzg = xb[:, sl], xs[:, sl], dz[:, g * og:(g + 1) * og]
             wbg = None if w_base[g] is None else w_base[g].contiguous()
             wsg = w_basis[g].contiguous()
+            tc_bwd = ctx.used_tc[g] and _TC_BACKWARD and lib.kc_tc_bytes(ctypes.byref(d), 1) > 0
+            dzf = None
+            if tc_bwd:
+                dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=xb.device, dtype=torch.uint8)
+                L.check(_timed("kc_dz_flat_kernel", 0.0, 6.0 * dzg.numel(), lambda: lib.kc_tc_dz_flat(
+                    ctypes.byref(d), _ptr(dzg), _ptr(dzf), stream)), "kc_tc_dz_flat")
             if run_dgrad:
-                L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
-                    ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
-                    _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbeta), stream)), "kc_conv_dgrad_f32")
+                if tc_bwd:
+                    nbytes = lib.kc_tc_bytes(ctypes.byref(d), 1)
+                    packed_d = torch.empty(nbytes, device=xb.device, dtype=torch.uint8)
+                    L.check(_timed("kc_pack_dgrad_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
+                        ctypes.byref(d), _ptr(wbg), _ptr(wsg), None, _ptr(packed_d), stream)), "kc_tc_pack_weights")
+                    L.check(_timed("kc_tc_kernel<dgrad>", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_tc(
+                        ctypes.byref(d), None, _ptr(xbg), _ptr(xsg), _ptr(packed_d), _ptr(beta), _ptr(dx_base[:, sl]),
+                        _ptr(dx_basis[:, sl]), None, _ptr(dzf), stream)), "kc_conv_dgrad_tc")
+                else:
+                    L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
+                        ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
+                        _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbeta), stream)), "kc_conv_dgrad_f32")
             wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
             if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
-                nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
-                ws = torch.empty(max(nbytes, 16), device=xb.device, dtype=torch.uint8)
                 dwb = torch.empty_like(wbg) if wbg is not None else None
                 dwsg = torch.empty_like(wsg)
-                L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
-                    ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
-                    "kc_conv_wgrad_f32")
+                if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
+                    ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 3), device=xb.device, dtype=torch.uint8)
+                    L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
+                        ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
+                        "kc_conv_wgrad_tc")
+                else:
+                    nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
+                    ws = torch.empty(max(nbytes, 16), device=xb.device, dtype=torch.uint8)
+                    L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
+                        ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
+                        "kc_conv_wgrad_f32")
                 if wi_base is not None:
                     dws[wi_base] = dwb
                 dws[wi_basis] = dwsg

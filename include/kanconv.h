@@ -130,10 +130,14 @@ int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, cons
  * Parity target: <= 2e-2 relative / 1e-3 absolute to the reference fp32 modules.
  * ------------------------------------------------------------------------------------------------------- */
 int kc_tc_supported(const kc_desc* d);
-/* Bytes of the packed bf16 weight images for the forward (which=0), dgrad (1) kernels, and of the wgrad split
- * workspace (2). */
+/* Bytes of the packed bf16 weight images of the forward (which=0) and dgrad (which=1) kernels, of the flat bf16
+ * dz buffer that kc_tc_dz_flat fills (which=2), and of the wgrad split-K workspace (which=3). */
 size_t kc_tc_bytes(const kc_desc* d, int which);
-/* fp32 reference-layout weights -> bf16 UMMA-canonical K-block images (once per optimizer step). */
+/* dz (fp32 NCHW) -> bf16 "flat" layout [n*(h+pad_h)*(w+pad_w)][round_up(cout,16)], zeros at padding positions: the
+ * operand format of the tensor-core dgrad / wgrad kernels (pass it as their `workspace` / `dz_flat`). */
+int kc_tc_dz_flat(const kc_desc* d, const float* dz, void* dz_flat, void* stream);
+/* fp32 reference-layout weights -> bf16 UMMA-canonical K-block images (once per optimizer step).  Either output
+ * pointer may be NULL to skip that image. */
 int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const float* w_basis, void* packed_fwd,
                        void* packed_dgrad, void* stream);
 int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float* x_basis, const void* packed_fwd,
@@ -141,7 +145,8 @@ int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float* x_basis, 
 int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                      const void* packed_dgrad, const float* beta, float* dx_base, float* dx_basis, float* dbeta,
                      void* workspace, void* stream);
-int kc_conv_wgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
+/* `dz_flat` = buffer filled by kc_tc_dz_flat; `workspace` = kc_tc_bytes(d, 3) bytes of split-K partial sums. */
+int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base, const float* x_basis,
                      const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream);
 
 /* Self-test of the tcgen05 shared-memory descriptor conventions this library relies on: runs a 128xNx64 bf16 GEMM

@@ -120,3 +120,87 @@ def test_l1_wrapper_hook_fires():
     x = torch.randn(2, 4, 6, 6, device="cuda", requires_grad=True)
     layer(x).sum().backward()
     assert all(p.grad is not None for p in layer.parameters())
+
+
+def _conv_only_oracle(kind, ora, x, g):
+    """Pre-normalisation output z and its gradients from the oracle's functional pieces (fp64)."""
+    import torch.nn.functional as F
+    xx = x.double().requires_grad_(True)
+    if kind == "kan":
+        wb, ws = ora.base_conv[0].weight, ora.spline_conv[0].weight
+        z = F.conv2d(F.silu(xx), wb, padding=1) + F.conv2d(O._expand(O.bspline_basis(xx, ora.knots, 3)), ws, padding=1)
+        params = {"base": wb, "basis": ws}
+    elif kind == "cheby":
+        ws = ora.poly_conv[0].weight
+        z = F.conv2d(O._expand(O.cheby_basis(xx, 3)), ws, padding=1)
+        params = {"basis": ws}
+    else:
+        wb, ws = ora.base_conv[0].weight, ora.spline_conv[0].weight
+        z = F.conv2d(F.silu(xx), wb, padding=1) + F.conv2d(O._expand(O.rbf_basis(xx, ora.rbf.grid, ora.rbf.denominator)), ws, padding=1)
+        params = {"base": wb, "basis": ws}
+    for p_ in params.values():
+        p_.grad = None
+    z.backward(g.double())
+    return z.detach(), xx.grad, {k: v.grad for k, v in params.items()}
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,n", [("kan", 64, 128, 32, 2), ("kan", 16, 320, 20, 3), ("kan", 24, 40, 9, 5),
+                                               ("kan", 40, 24, 13, 3), ("kan", 8, 16, 40, 2), ("cheby", 32, 64, 16, 2),
+                                               ("fast", 16, 32, 14, 2)])
+def test_bf16_tensor_core_conv_op_fwd_dgrad_wgrad(kind, cin, cout, hw, n):
+    """The convolution op alone (no norm / PReLU): z, dX and dW of the tcgen05 kernels vs the fp64 oracle, BF16 tolerance."""
+    from kanconv_b200 import functional as KF
+    okw = dict(input_dim=cin, output_dim=cout, kernel_size=3, padding=1)
+    mkw = dict(okw)
+    if kind == "kan":
+        okw["base_activation"] = "silu"
+        mkw["base_activation"] = nn.SiLU
+    ora, mod = _oracle_and_module(kind, okw, mkw)
+    torch.manual_seed(3)
+    x = torch.randn(n, cin, hw, hw + 3)
+    g = torch.randn(n, cout, hw, hw + 3)
+    zo, dxo, go = _conv_only_oracle(kind, ora, x, g)
+    xg = x.cuda().requires_grad_(True)
+    if kind == "kan":
+        wb, ws, spec = [mod.base_conv[0].weight], [mod.spline_conv[0].weight], mod._spec
+    elif kind == "cheby":
+        wb, ws, spec = [], [mod.poly_conv[0].weight], mod._spec
+    else:
+        wb, ws = [mod.base_conv[0].weight], [mod.spline_conv[0].weight]
+        spec = KF.ConvSpec(basis=L.BASIS_RBF, act=mod._act, nb=mod.grid_size, order=0, params=mod.rbf.host_params(), **mod._geom)
+    z = KF.kan_conv(spec, xg, None, None, wb, ws, "bf16")
+    z.backward(g.cuda())
+    errs = {"z": rel_err(z, zo), "dx": rel_err(xg.grad, dxo), "dw_basis": rel_err(ws[0].grad, go["basis"])}
+    if wb:
+        errs["dw_base"] = rel_err(wb[0].grad, go["base"])
+    print(kind, cin, cout, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < BF16_TOL, errs
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,n", [("kan", 64, 128, 32, 2), ("kan", 16, 320, 20, 3), ("kan", 24, 40, 9, 5),
+                                               ("kan", 40, 24, 13, 3), ("cheby", 32, 64, 16, 2), ("fast", 16, 32, 14, 2)])
+def test_bf16_tensor_core_backward_vs_oracle(kind, cin, cout, hw, n):
+    """Whole layer (conv -> InstanceNorm -> PReLU) in BF16 mode.  y meets the BF16 tolerance.  Gradients are compared with
+    a looser bound: the bf16 rounding of z flips the sign of the ~1 % of normalised activations with |zhat| < 3e-3, and each
+    flip changes dzhat by (1 - alpha) * dy - an inherent property of differentiating through the PReLU kink at a
+    slightly different point (the FP32 backward kernels give the same deviation after a BF16 forward), not kernel error;
+    the kernels themselves are held to BF16_TOL in test_bf16_tensor_core_conv_op_fwd_dgrad_wgrad."""
+    okw = dict(input_dim=cin, output_dim=cout, kernel_size=3, padding=1)
+    mkw = dict(okw)
+    if kind == "kan":
+        okw["base_activation"] = "silu"
+        mkw["base_activation"] = nn.SiLU
+    ora, mod = _oracle_and_module(kind, okw, mkw)
+    mod.precision = "bf16"
+    torch.manual_seed(3)
+    x = torch.randn(n, cin, hw, hw + 3)
+    ho = ora(x.double()).shape
+    g = torch.randn(*ho)
+    yo, dxo, go = run_fwd_bwd(ora, x.double(), g.double())
+    y, dx, gr = run_fwd_bwd(mod, x.cuda(), g.cuda())
+    errs = {"y": rel_err(y, yo), "dx": rel_err(dx, dxo)}
+    for k in go:
+        errs[k] = rel_err(gr[k], go[k])
+    print(kind, cin, cout, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["y"] < BF16_TOL, errs
+    assert max(errs.values()) < 0.15, errs

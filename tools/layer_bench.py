@@ -62,6 +62,18 @@ def main():
                "norm_ms": round(t_norm, 3), "norm_gbs": round(2 * z.numel() * 4 / t_norm / 1e6, 1)}
         if a.bwd:
             g = torch.randn_like(z)
+            def one():
+                for p in m.parameters():
+                    p.grad = None
+                y = m(x)
+                y.backward(g)
+            one(); one()
+            torch.cuda.synchronize()
+            KF.profile_begin()
+            one()
+            prof = KF.profile_end()
+            rec["kernels"] = {k: [round(v["ms"], 3), round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else round(v["bytes"] / v["ms"] / 1e6, 1)]
+                              for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
             def step():
                 for p in m.parameters():
                     p.grad = None
