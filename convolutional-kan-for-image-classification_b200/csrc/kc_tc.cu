@@ -472,43 +472,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       }
     }
   }
-  if (MODE == kModeDgrad && warp < 4) {
+  if (MODE == kModeDgrad && warp < 16) {
     // ================================ dgrad epilogue: dPhi (TMEM) x analytic basis derivative -> dx =======
     // Columns of this N tile are (channel cl, j) with j < nb the basis gradients and j == nb the base-branch gradient;
     // dPhi never leaves the SM (the reference's autograd materialises it, ~50 elementwise backward launches).
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    // All 16 producer warps take part: warp w reads TMEM lanes 32*(w%4).. (its hardware quarter) and handles the four
+    // channels 4*(w/4) .. +3; the x values of all sub-tiles are fetched BEFORE waiting for the accumulator.
     const int nb = d.nb, wb = nb + (has_base ? 1 : 0);
-    const bool alias = a.dx_base == a.dx_basis;
-    for (int i = 0; i < g.nsub; ++i) {
-      const long long q = m0 + i * kTileM + warp * 32 + lane;
-      bool valid = false;
-      long long off = 0;
-      if (q < g.L) {
+    const bool alias = a.dx_base == a.dx_basis, same_x = a.x_base == a.x_basis;
+    const int quarter = warp & 3, cgrp = warp >> 2;
+    long long offv[4];
+    float xs[4][4], xb[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      offv[i] = -1;
+      const long long q = m0 + i * kTileM + quarter * 32 + lane;
+      if (i < g.nsub && q < g.L) {
         int n = (int)(q / g.IMG);
         int rem = (int)(q - (long long)n * g.IMG);
         int y = rem / g.P, x = rem - y * g.P;
-        if (y < d.h && x < d.w) { valid = true; off = (long long)n * d.x_batch_stride + y * d.w + x; }
+        if (y < d.h && x < d.w) offv[i] = (long long)n * d.x_batch_stride + y * d.w + x;
       }
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * g.ntile);
-      for (int cl = 0; cl < 16; ++cl) {
-        const int c = nt * 16 + cl;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = nt * 16 + cgrp * 4 + c4;
+        const bool ok = offv[i] >= 0 && c < d.cin;
+        xs[i][c4] = ok ? __ldg(a.x_basis + offv[i] + (long long)c * HW) : 0.0f;
+        xb[i][c4] = (ok && has_base && !same_x) ? __ldg(a.x_base + offv[i] + (long long)c * HW) : xs[i][c4];
+      }
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= g.nsub) break;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * g.ntile);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int cl = cgrp * 4 + c4, c = nt * 16 + cl;
         if (c >= d.cin) break;
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)(cl * wb), r);
         tmem_ld_wait();
-        if (valid) {
-          const long long o = off + (long long)c * HW;
-          const float xs = __ldg(a.x_basis + o);
+        if (offv[i] >= 0) {
+          const long long o = offv[i] + (long long)c * HW;
           float gs = 0.0f;
           if (g.fast_cubic) {
             float gg[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) gg[j] = __uint_as_float(r[j]);
-            gs = cubic8_dot_grad(xs, g.t0, g.inv_h, B->nparams - 1, gg);
+            gs = cubic8_dot_grad(xs[i][c4], g.t0, g.inv_h, B->nparams - 1, gg);
           } else {
             float phi[KC_MAX_BASIS], dphi[KC_MAX_BASIS];
-            kc_eval_basis(*B, xs, phi, dphi, 1);
+            kc_eval_basis(*B, xs[i][c4], phi, dphi, 1);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (j < nb) gs = fmaf(__uint_as_float(r[j]), dphi[j], gs);
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (j == nb) ga = __uint_as_float(r[j]);
-            gb = ga * kc_act_grad(d.act, __ldg(a.x_base + o));
+            gb = ga * kc_act_grad(d.act, xb[i][c4]);
           }
           if (alias) {
             a.dx_basis[o] = gs + gb;
@@ -969,7 +985,7 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
 // warps streaming 16-byte st.shared into an unrelated smem region while the MMAs run.
 __global__ void __launch_bounds__(576, 1) kc_mma_rate_kernel(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters,
                                                               int a_rowshift, int nsub, int commit_every, int writers,
-                                                              float* out) {
+                                                              int mn_major, float* out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ __align__(8) uint64_t bar, dummy[8];
   __shared__ uint32_t tmem_ptr;
@@ -984,15 +1000,15 @@ __global__ void __launch_bounds__(576, 1) kc_mma_rate_kernel(int N, int a_lbo, i
   tc_fence_after();
   const uint32_t tb = tmem_ptr;
   if (tid == 17 * 32) {
-    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
     const uint32_t abase = smem_u32(sm) + a_rowshift * 16, bbase = smem_u32(sm) + 96 * 1024;
     long long t0 = clock64();
     int cnt = 0;
     for (int it = 0; it < iters; ++it) {
       for (int s = 0; s < nsub; ++s) {
         for (int i = 0; i < 2; ++i) {
-          uint64_t ad = make_smem_desc(abase + s * 2048 + i * 2 * a_lbo, a_lbo, a_sbo);
-          uint64_t bd = make_smem_desc(bbase + i * 2 * b_lbo, b_lbo, b_sbo);
+          uint64_t ad = make_smem_desc(abase + (mn_major ? s * 16 + i * 256 : s * 2048 + i * 2 * a_lbo), a_lbo, a_sbo);
+          uint64_t bd = make_smem_desc(bbase + (mn_major ? i * 256 : i * 2 * b_lbo), b_lbo, b_sbo);
           tc_mma_bf16(tb + s * N, ad, bd, idesc, 1u);
           if (commit_every > 0 && (++cnt % commit_every) == 0) tc_commit(&dummy[(cnt / commit_every) & 7]);
         }
@@ -1018,15 +1034,71 @@ __global__ void __launch_bounds__(576, 1) kc_mma_rate_kernel(int N, int a_lbo, i
 }
 
 extern "C" int kc_debug_mma_rate(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters, int a_rowshift, int nsub,
-                                 int commit_every, int writers, float* cycles) {
+                                 int commit_every, int writers, int mn_major, float* cycles) {
   float* dev = nullptr;
   KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  kc_mma_rate_kernel<<<1, 576, 160 * 1024>>>(N, a_lbo, a_sbo, b_lbo, b_sbo, iters, a_rowshift, nsub, commit_every, writers, dev);
+  kc_mma_rate_kernel<<<1, 576, 160 * 1024>>>(N, a_lbo, a_sbo, b_lbo, b_sbo, iters, a_rowshift, nsub, commit_every, writers, mn_major, dev);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(dev);
   if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate: %s", cudaGetErrorString(e));
+  return KC_OK;
+}
+
+// Debug only: tcgen05.mma execution rate with the warp-uniform elect issue path (4 MMAs per iteration, descriptors are
+// loop-invariant apart from the k-step), for the K-major (conv fwd/dgrad) and MN-major (wgrad) no-swizzle layouts.
+__global__ void __launch_bounds__(32, 1) kc_mma_rate2_kernel(int N, int mn_major, int iters, float* out) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  for (int i = threadIdx.x; i < (96 * 1024) / 4; i += 32) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  tmem_alloc(&tmem_ptr, 256);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t tb = tmem_ptr;
+  const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
+  const uint32_t au = smem_u32(sm) >> 4, bu = (smem_u32(sm) + 48 * 1024) >> 4;
+  // K-major: planes [k-core][row]: LBO = plane pitch, SBO = 128 B; step = 2 planes.  MN-major: planes [mn-group][k row]:
+  // SBO = plane pitch, LBO = 128 B; step = 16 rows.
+  const uint32_t a_pitch = mn_major ? 1168u : 6544u, b_pitch = mn_major ? 1040u : (uint32_t)N * 16u;
+  const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
+  const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
+  const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + ks * a_step));
+        const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + ks * b_step));
+        tc_mma_bf16(tb, ad, bd, idesc, 1u);
+      }
+    }
+    __syncwarp();
+  }
+  if (elect_one_sync()) tc_commit(&bar);
+  __syncwarp();
+  mbar_wait(&bar, 0);
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = (float)(t1 - t0) / (float)(iters * 4);
+  tc_fence_before();
+  __syncwarp();
+  tmem_dealloc(tb, 256);
+}
+
+extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, float* cycles) {
+  float* dev = nullptr;
+  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  kc_mma_rate2_kernel<<<1, 32, 96 * 1024>>>(N, mn_major, iters, dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate2: %s", cudaGetErrorString(e));
   return KC_OK;
 }
 

@@ -21,9 +21,9 @@ namespace {
 
 using namespace kc;
 
-constexpr int kThreadsW = 576;       // warps 0-15 producers / epilogue, 16 idle, 17 MMA issuer
+constexpr int kThreadsW = 544;       // warps 0-15 producers / epilogue, 16 MMA issuer (highest warp id)
 constexpr int kProdW = 512;
-constexpr int kMmaWarpW = 17;
+constexpr int kMmaWarpW = 16;
 constexpr int kKS = 64;              // positions per pipeline stage (4 MMA k-steps)
 constexpr int kMaxStagesW = 6;
 constexpr size_t kSmemLimitW = 227 * 1024;
@@ -60,6 +60,17 @@ struct WgArgs {
 };
 
 __host__ __device__ inline int round_up_w(int a, int b) { return (a + b - 1) / b * b; }
+
+// optional timeline trace (debug), enabled by kc_debug_trace_wgrad(buffer of 4 x 1024 int64)
+__device__ long long* g_trace_w = nullptr;
+struct TracerW {
+  long long* p; int n;
+  __device__ TracerW(int role, bool on) {
+    long long* t = g_trace_w;
+    p = (on && t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? t + role * 1024 : nullptr; n = 0;
+  }
+  __device__ __forceinline__ void stamp() { if (p != nullptr && n < 1024) p[n++] = clock64(); }
+};
 
 __device__ __forceinline__ unsigned long long shl64w(unsigned long long v, int s) {
   unsigned long long r;
@@ -101,6 +112,131 @@ __device__ __noinline__ uint2 basis4w(const KcBasisCtx& B, float x) {
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
 
+// Producer role of the wgrad kernel (512 threads).  Each thread owns up to three static (row, plane) items of the Phi
+// stage and up to three (row, plane) vectors of the dz stage.  The flat position of every Phi row is decoded to an input
+// offset by the first `arows` threads into a double-buffered shared table (advanced incrementally by kKS positions per
+// block - no integer division in the loop); the global loads of block i+1 are issued right after block i's values have
+// been converted to packed bf16 and before the thread waits for the stage (software prefetch, small register state).
+template <bool BASE>
+__device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, int* rowtab, uint64_t* full, uint64_t* empty,
+                                           const KcBasisCtx* B, int r, int chunk, int ct, long long blk0, int nblocks) {
+  const kc_desc& d = a.d;
+  const WgGeom& g = a.g;
+  constexpr int NX = BASE ? 8 : 2;                 // x values per A item (8 channels | 1-2 channels)
+  const int tid = threadIdx.x;
+  const int HW = d.h * d.w, nb = d.nb, cin = d.cin;
+  const int rows_img = d.h + d.pad_h, arows = g.arows;
+  const int nAitems = arows * 16, nBitems = kKS * g.bplanes;
+  const float* xsrc = BASE ? a.x_base : a.x_basis;
+  // row decode state (threads < arows)
+  int in_ = 0, iy_ = 0, ix_ = 0;
+  if (tid < arows) {
+    const long long q = blk0 * kKS + (long long)(r - d.pad_h) * g.P - d.pad_w + tid + g.IMG;   // + one image: non-negative
+    in_ = (int)(q / g.IMG) - 1;
+    const int rem = (int)(q % g.IMG);
+    iy_ = rem / g.P;
+    ix_ = rem - iy_ * g.P;
+  }
+  auto table_step = [&](int slot) {                // write this block's offsets, then advance by kKS positions
+    if (tid < arows) {
+      const bool ok = in_ >= 0 && in_ < d.n && iy_ < d.h && ix_ < d.w;
+      rowtab[slot * 80 + tid] = ok ? (int)((long long)in_ * d.x_batch_stride + iy_ * d.w + ix_) : -1;
+      ix_ += kKS;
+      while (ix_ >= g.P) { ix_ -= g.P; ++iy_; }
+      while (iy_ >= rows_img) { iy_ -= rows_img; ++in_; }
+    }
+  };
+  int arow[3], apl[3], brow[3], bpl[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int it = tid + kProdW * k;
+    arow[k] = it % arows;
+    apl[k] = (it < nAitems) ? it / arows : -1;
+    bpl[k] = (it < nBitems) ? it % g.bplanes : -1;
+    brow[k] = it / g.bplanes;
+  }
+  float xn[3][NX];
+  uint4 dzn[3];
+  bool okn[3];
+  auto fetch = [&](int bi) {
+    const int* tab = rowtab + (bi & 1) * 80;
+    const long long m0 = (blk0 + bi) * kKS;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int off = (apl[k] >= 0) ? tab[arow[k]] : -1;
+      okn[k] = off >= 0;
+      const int c0 = BASE ? ((chunk - g.nsc) * 128 + apl[k] * 8) : (chunk * g.cps + apl[k] * (nb == 8 ? 1 : 2));
+      const float* src = xsrc + (long long)c0 * HW + (off >= 0 ? off : 0);
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+        xn[k][i] = (off >= 0 && c0 + i < cin && (BASE || nb != 8 || i == 0)) ? __ldg(src + (long long)i * HW) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dzn[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (bpl[k] >= 0) {
+        const long long m = m0 + brow[k];
+        const int co = ct * g.ntile + bpl[k] * 8;
+        if (m < g.L && co < g.cq) dzn[k] = __ldg(reinterpret_cast<const uint4*>(a.dzf + (m * g.cq + co) * 2));
+      }
+    }
+  };
+  auto prod_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kProdW) : "memory"); };
+
+  table_step(0);
+  table_step(1);
+  prod_sync();
+  if (nblocks > 0) fetch(0);
+  int st = 0;
+  uint32_t ph = 0;
+  TracerW trp(0, tid == 0);
+  for (int bi = 0; bi < nblocks; ++bi) {
+    trp.stamp();
+    unsigned char* As = smem + (size_t)st * g.stage_bytes;
+    unsigned char* Bs = As + g.a_bytes;
+    // ---- convert block bi (registers) to packed bf16 ----
+    uint4 v[3], dzv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dzv[k] = dzn[k];
+      const int c0 = BASE ? ((chunk - g.nsc) * 128 + apl[k] * 8) : (chunk * g.cps + apl[k] * (nb == 8 ? 1 : 2));
+      if (BASE) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = (okn[k] && c0 + i < cin) ? kc_act(d.act, xn[k][i < NX ? i : 0]) : 0.0f;
+        v[k] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+      } else if (nb == 8) {
+        const bool ok = okn[k] && c0 < cin;
+        if (g.fast_cubic) v[k] = cubic8w(xn[k][0], g.t0, g.inv_h, B->nparams - 1, ok);
+        else v[k] = ok ? basis8w_generic(*B, xn[k][0]) : make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+        if (okn[k]) {
+          if (c0 < cin) lo = basis4w(*B, xn[k][0]);
+          if (c0 + 1 < cin) hi = basis4w(*B, xn[k][1]);
+        }
+        v[k] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      }
+    }
+    // ---- prefetch block bi+1; the table slot of block bi is recycled for block bi+2 ----
+    if (bi + 1 < nblocks) fetch(bi + 1);
+    table_step(bi & 1);
+    trp.stamp();
+    mbar_wait(&empty[st], ph ^ 1);
+    trp.stamp();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (apl[k] >= 0) reinterpret_cast<uint4*>(As + apl[k] * g.aplane_bytes)[arow[k]] = v[k];
+      if (bpl[k] >= 0) reinterpret_cast<uint4*>(Bs + bpl[k] * g.bplane_bytes)[brow[k]] = dzv[k];
+    }
+    trp.stamp();
+    fence_proxy_async_smem();
+    mbar_arrive(&full[st]);
+    prod_sync();                                   // table slot (bi & 1) is complete before block bi+2 is fetched
+    if (++st == g.stages) { st = 0; ph ^= 1; }
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
@@ -111,9 +247,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   uint64_t* acc_full = bars + 2 * kMaxStagesW;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesW + 1);
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
+  int* rowtab = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(B) + ((sizeof(KcBasisCtx) + 15) / 16) * 16);   // [2][80]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HW = d.h * d.w;
   // unit = ((cout tile * nchunks + chunk) * kh + r)
   const int unit = blockIdx.x, split = blockIdx.y;
   const int r = unit % d.kh;
@@ -138,107 +274,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
 
   if (warp < 16) {
     // ============================ producers: Phi (A) evaluated on the fly, dz (B) copied ===========================
-    const int tid = threadIdx.x;
-    // static A items of this thread: it = tid + 512*k  ->  row = it % arows, plane = it / arows
-    const int nAitems = g.arows * 16;
-    int row_k[3], plane_k[3];
-    long long q_k[3];
-    const long long qoff = (long long)(r - d.pad_h) * g.P - d.pad_w;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int it = tid + kProdW * k;
-      row_k[k] = it % g.arows;
-      plane_k[k] = (it < nAitems) ? it / g.arows : -1;
-      q_k[k] = blk0 * kKS + qoff + row_k[k];
-    }
-    const int nb = d.nb, cin = d.cin;
-    int st = 0;
-    uint32_t ph = 0;
-    for (int bi = 0; bi < nblocks; ++bi) {
-      unsigned char* As = smem + (size_t)st * g.stage_bytes;
-      unsigned char* Bs = As + g.a_bytes;
-      const long long m0 = (blk0 + bi) * kKS;
-      // ---- global loads first (latency overlaps the wait for the stage) ----
-      float xv[3][8];
-      int nld = is_base ? 8 : (nb == 8 ? 1 : 2);
-      bool okk[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        okk[k] = false;
-        const long long q = q_k[k];
-        if (plane_k[k] >= 0 && q >= 0 && q < g.L) {
-          const int n = (int)(q / g.IMG);
-          const int rem = (int)(q - (long long)n * g.IMG);
-          const int y = rem / g.P, x = rem - y * g.P;
-          if (y < d.h && x < d.w) {
-            okk[k] = true;
-            const long long off = (long long)n * d.x_batch_stride + y * d.w + x;
-            const int c0 = is_base ? ((chunk - g.nsc) * 128 + plane_k[k] * 8) : (chunk * g.cps + plane_k[k] * (nb == 8 ? 1 : 2));
-            const float* src = (is_base ? a.x_base : a.x_basis) + off + (long long)c0 * HW;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) xv[k][i] = (i < nld && c0 + i < cin) ? __ldg(src + (long long)i * HW) : 0.0f;
-          }
-        }
-        if (!okk[k]) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xv[k][i] = 0.0f;
-        }
-        q_k[k] += kKS;
-      }
-      // dz vectors: it -> plane = it % bplanes (fastest: contiguous in global), row = it / bplanes
-      uint4 dzv[3];
-      const int nBitems = kKS * g.bplanes;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int it = tid + kProdW * k;
-        dzv[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (it < nBitems) {
-          const int pl = it % g.bplanes, row = it / g.bplanes;
-          const long long m = m0 + row;
-          const int co = ct * g.ntile + pl * 8;
-          if (m < g.L && co < g.cq) dzv[k] = __ldg(reinterpret_cast<const uint4*>(a.dzf + (m * g.cq + co) * 2));
-        }
-      }
-      mbar_wait(&empty[st], ph ^ 1);
-      // ---- evaluate / convert and store ----
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (plane_k[k] < 0) continue;
-        uint4 v;
-        if (is_base) {
-          const int c0 = (chunk - g.nsc) * 128 + plane_k[k] * 8;
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = (okk[k] && c0 + i < cin) ? kc_act(d.act, xv[k][i]) : 0.0f;
-          v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        } else if (nb == 8) {
-          const int c = chunk * g.cps + plane_k[k];
-          const bool ok = okk[k] && c < cin;
-          if (g.fast_cubic) v = cubic8w(xv[k][0], g.t0, g.inv_h, B->nparams - 1, ok);
-          else v = ok ? basis8w_generic(*B, xv[k][0]) : make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          const int c = chunk * g.cps + plane_k[k] * 2;
-          uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-          if (okk[k]) {
-            if (c < cin) lo = basis4w(*B, xv[k][0]);
-            if (c + 1 < cin) hi = basis4w(*B, xv[k][1]);
-          }
-          v = make_uint4(lo.x, lo.y, hi.x, hi.y);
-        }
-        reinterpret_cast<uint4*>(As + plane_k[k] * g.aplane_bytes)[row_k[k]] = v;
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int it = tid + kProdW * k;
-        if (it < nBitems) {
-          const int pl = it % g.bplanes, row = it / g.bplanes;
-          reinterpret_cast<uint4*>(Bs + pl * g.bplane_bytes)[row] = dzv[k];
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&full[st]);
-      if (++st == g.stages) { st = 0; ph ^= 1; }
-    }
+    if (is_base) wg_produce<true>(a, smem, rowtab, full, empty, B, r, chunk, ct, blk0, nblocks);
+    else wg_produce<false>(a, smem, rowtab, full, empty, B, r, chunk, ct, blk0, nblocks);
   }
   if (warp == kMmaWarpW) {
     // ============================ MMA issuer (whole warp uniform, one elected lane issues) ==========================
@@ -250,9 +287,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     const int kw = d.kw, ntile = g.ntile;
     int st = 0;
     uint32_t ph = 0;
+    TracerW trm(1, lane == 0);
     for (int bi = 0; bi < nblocks; ++bi) {
+      trm.stamp();
       mbar_wait(&full[st], ph);
       tc_fence_after();
+      trm.stamp();
       const uint32_t au = smem_u + (uint32_t)st * stage_u, bu = au + a_u;
       const uint32_t first = bi != 0 ? 1u : 0u;
       if (elect_one_sync()) {
@@ -374,7 +414,8 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->bplane_bytes = kKS * 16 + 16;
   g->stage_bytes = round_up_w(g->a_bytes + g->bplanes * g->bplane_bytes, 128);
   if (g->arows * 16 > 3 * kProdW || kKS * g->bplanes > 3 * kProdW) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage too large for the producer mapping");
-  size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 128;
+  if (g->arows > 80) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: kernel width too large");
+  size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 16 + 2 * 80 * sizeof(int) + 128;
   g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
   if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
   if (g->stages < 2) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
@@ -394,6 +435,12 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
 }
 
 }  // namespace
+
+extern "C" int kc_debug_trace_wgrad(void* device_buffer) {
+  long long* p = (long long*)device_buffer;
+  KC_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_w, &p, sizeof(p)));
+  return KC_OK;
+}
 
 size_t kc_tc_wgrad_ws_bytes(const kc_desc* d) {
   WgGeom g;
