@@ -62,7 +62,7 @@ struct TcFwdArgs {
   const float* beta;
   float* z;
   // dgrad mode only
-  const unsigned char* dzf;     // bf16 [L][cq] flat, zero at padding / invalid output positions
+  const unsigned char* dzf;     // bf16 plane-major [cq/8][L][8], zero at padding / invalid output positions
   int cq;                       // channels per flat row (cout rounded up to 16)
   float* dx_base;
   float* dx_basis;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
           for (int cl = 0; cl < 2; ++cl) {
             const int grp = q * kPL + half * 2 + cl;
             v[k][cl] = (offs[k] >= 0 && grp * 8 < a.cq)
-                           ? __ldg(reinterpret_cast<const uint4*>(a.dzf + ((long long)offs[k] * a.cq + grp * 8) * 2))
+                           ? __ldg(reinterpret_cast<const uint4*>(a.dzf + ((long long)grp * g.L + offs[k]) * 16))
                            : make_uint4(0u, 0u, 0u, 0u);
           }
         mbar_wait(&a_empty[buf], aphase ^ 1);
@@ -643,38 +643,29 @@ __global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constan
   }
 }
 
-// dz (fp32 NCHW) -> flat bf16 [L][cq]: position q = n*IMG + y*P + x, zero where (y, x) is not an output pixel.
-// 64 positions x 64 channels per block, transposed through shared memory (coalesced on both sides).
+// dz (fp32 NCHW) -> flat bf16, plane-major [cq/8][L][8]: plane p holds output channels 8p..8p+7 of flat position
+// q = n*IMG + y*P + x as one 16-byte vector; zero where (y, x) is not an output pixel.  One thread per (q, plane): its
+// eight channel reads are each coalesced across the warp (consecutive q), the 16-byte stores are contiguous.
 __global__ void __launch_bounds__(256) kc_dz_flat_kernel(const __grid_constant__ kc_desc d, int P, int IMG, long long L, int cq,
                                                          const float* __restrict__ dz, unsigned char* __restrict__ out) {
-  __shared__ float tile[64][65];
-  const long long q0 = (long long)blockIdx.x * 64;
-  const int c0 = blockIdx.y * 64;
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int pl = blockIdx.y;
+  if (q >= L) return;
   const int HoWo = d.ho * d.wo;
-  for (int it = threadIdx.x; it < 64 * 64; it += 256) {
-    const int p = it & 63, c = it >> 6;
-    const long long q = q0 + p;
-    float v = 0.0f;
-    if (q < L && c0 + c < d.cout) {
-      int n = (int)(q / IMG);
-      int rem = (int)(q - (long long)n * IMG);
-      int y = rem / P, x = rem - y * P;
-      if (y < d.ho && x < d.wo) v = dz[(long long)n * d.z_batch_stride + (long long)(c0 + c) * HoWo + y * d.wo + x];
-    }
-    tile[c][p] = v;
-  }
-  __syncthreads();
-  for (int it = threadIdx.x; it < 64 * 8; it += 256) {
-    const int grp = it & 7, p = it >> 3;
-    const long long q = q0 + p;
-    if (q < L && c0 + grp * 8 < cq) {
-      float f[8];
+  float f[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = tile[grp * 8 + e][p];
-      *reinterpret_cast<uint4*>(out + (q * cq + c0 + grp * 8) * 2) =
-          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-    }
+  for (int e = 0; e < 8; ++e) f[e] = 0.0f;
+  const int n = (int)(q / IMG);
+  const int rem = (int)(q - (long long)n * IMG);
+  const int y = rem / P, x = rem - y * P;
+  if (y < d.ho && x < d.wo) {
+    const float* src = dz + (long long)n * d.z_batch_stride + y * d.wo + x;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (pl * 8 + e < d.cout) f[e] = __ldg(src + (long long)(pl * 8 + e) * HoWo);
   }
+  *reinterpret_cast<uint4*>(out + ((long long)pl * L + q) * 16) =
+      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -930,7 +921,7 @@ extern "C" int kc_tc_dz_flat(const kc_desc* d, const float* dz, void* dz_flat, v
   rc = tc_dgrad_geometry(d, &g);
   if (rc != KC_OK) return rc;
   if (!dz || !dz_flat) KC_FAIL(KC_ERR_INVALID, "kc_tc_dz_flat: null pointer");
-  dim3 grid((unsigned)((g.L + 63) / 64), (unsigned)((g.Cp + 63) / 64));
+  dim3 grid((unsigned)((g.L + 255) / 256), (unsigned)(g.Cp / 8));
   kc_dz_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, g.P, g.IMG, g.L, g.Cp, dz, (unsigned char*)dz_flat);
   KC_LAUNCH_CHECK("kc_dz_flat_kernel");
   return KC_OK;

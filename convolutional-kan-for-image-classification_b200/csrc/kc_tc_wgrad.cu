@@ -44,7 +44,7 @@ struct WgGeom {
   int nsplit;
   long long blk_per_split;
   size_t smem_bytes;
-  size_t ws_bytes;
+  size_t ws_bytes, phi_bytes;
   int fast_cubic;
   float t0, inv_h;
 };
@@ -54,7 +54,8 @@ struct WgArgs {
   WgGeom g;
   const float* x_base;
   const float* x_basis;
-  const unsigned char* dzf;
+  const unsigned char* dzf;     // bf16 plane-major [cq/8][L][8]
+  const unsigned char* phi;     // bf16 plane-major [nchunks*16][L][8]  (kc_phi_flat_kernel)
   const float* beta;
   float* ws;
 };
@@ -112,80 +113,86 @@ __device__ __noinline__ uint2 basis4w(const KcBasisCtx& B, float x) {
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
 
-// Producer role of the wgrad kernel (512 threads).  Each thread owns up to three static (row, plane) items of the Phi
-// stage and up to three (row, plane) vectors of the dz stage.  The flat position of every Phi row is decoded to an input
-// offset by the first `arows` threads into a double-buffered shared table (advanced incrementally by kKS positions per
-// block - no integer division in the loop); the global loads of block i+1 are issued right after block i's values have
-// been converted to packed bf16 and before the thread waits for the stage (software prefetch, small register state).
-template <bool BASE>
-__device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, int* rowtab, uint64_t* full, uint64_t* empty,
-                                           const KcBasisCtx* B, int r, int chunk, int ct, long long blk0, int nblocks) {
+// Pre-pass: evaluate the A operand ONCE per (position, channel) into a transient bf16 plane-major buffer
+//   phi[chunk][plane 0..15][L][8]     spline chunk: plane = channel (nb = 8) or channel pair (nb = 4), 8 basis values
+//                                     base chunk  : plane = 8 consecutive channels, their base activations
+// (zero at padding positions).  Reads of x are coalesced along the flat position, writes are contiguous 16-byte vectors.
+// The wgrad kernel would otherwise re-evaluate every basis value kh * n_ct (6-12) times; see DESIGN.md.
+__global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant__ WgArgs a, unsigned char* __restrict__ out) {
+  __shared__ KcBasisCtx Bs;
   const kc_desc& d = a.d;
   const WgGeom& g = a.g;
-  constexpr int NX = BASE ? 8 : 2;                 // x values per A item (8 channels | 1-2 channels)
-  const int tid = threadIdx.x;
-  const int HW = d.h * d.w, nb = d.nb, cin = d.cin;
-  const int rows_img = d.h + d.pad_h, arows = g.arows;
-  const int nAitems = arows * 16, nBitems = kKS * g.bplanes;
-  const float* xsrc = BASE ? a.x_base : a.x_basis;
-  // row decode state (threads < arows)
-  int in_ = 0, iy_ = 0, ix_ = 0;
-  if (tid < arows) {
-    const long long q = blk0 * kKS + (long long)(r - d.pad_h) * g.P - d.pad_w + tid + g.IMG;   // + one image: non-negative
-    in_ = (int)(q / g.IMG) - 1;
-    const int rem = (int)(q % g.IMG);
-    iy_ = rem / g.P;
-    ix_ = rem - iy_ * g.P;
-  }
-  auto table_step = [&](int slot) {                // write this block's offsets, then advance by kKS positions
-    if (tid < arows) {
-      const bool ok = in_ >= 0 && in_ < d.n && iy_ < d.h && ix_ < d.w;
-      rowtab[slot * 80 + tid] = ok ? (int)((long long)in_ * d.x_batch_stride + iy_ * d.w + ix_) : -1;
-      ix_ += kKS;
-      while (ix_ >= g.P) { ix_ -= g.P; ++iy_; }
-      while (iy_ >= rows_img) { iy_ -= rows_img; ++in_; }
+  kc_load_basis_ctx(&Bs, d, a.beta);
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int gp = blockIdx.y, chunk = gp >> 4, pl = gp & 15;
+  if (q >= g.L) return;
+  const int HW = d.h * d.w, nb = d.nb;
+  const int n = (int)(q / g.IMG);
+  const int rem = (int)(q - (long long)n * g.IMG);
+  const int y = rem / g.P, x = rem - y * g.P;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (y < d.h && x < d.w) {
+    const long long off = (long long)n * d.x_batch_stride + y * d.w + x;
+    if (chunk >= g.nsc) {
+      const int c0 = (chunk - g.nsc) * 128 + pl * 8;
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = (c0 + i < d.cin) ? kc_act(d.act, __ldg(a.x_base + off + (long long)(c0 + i) * HW)) : 0.0f;
+      v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    } else if (nb == 8) {
+      const int c = chunk * g.cps + pl;
+      if (c < d.cin) {
+        const float xv = __ldg(a.x_basis + off + (long long)c * HW);
+        v = g.fast_cubic ? cubic8w(xv, g.t0, g.inv_h, Bs.nparams - 1, true) : basis8w_generic(Bs, xv);
+      }
+    } else {
+      const int c = chunk * g.cps + pl * 2;
+      uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+      if (c < d.cin) lo = basis4w(Bs, __ldg(a.x_basis + off + (long long)c * HW));
+      if (c + 1 < d.cin) hi = basis4w(Bs, __ldg(a.x_basis + off + (long long)(c + 1) * HW));
+      v = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
-  };
+  }
+  *reinterpret_cast<uint4*>(out + ((long long)gp * g.L + q) * 16) = v;
+}
+
+// Producer role of the wgrad kernel (512 threads): pure 16-byte copies of the Phi planes (A, with the filter-row shift)
+// and the dz planes (B) into the stage; rows are the fastest index so global reads are contiguous.  Block i+1 is
+// prefetched into registers while block i is stored.
+__device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int r, int chunk,
+                                           int ct, long long blk0, int nblocks) {
+  const kc_desc& d = a.d;
+  const WgGeom& g = a.g;
+  const int tid = threadIdx.x;
+  const int nAitems = g.arows * 16, nBitems = kKS * g.bplanes;
+  const long long qoff = blk0 * kKS + (long long)(r - d.pad_h) * g.P - d.pad_w;
   int arow[3], apl[3], brow[3], bpl[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int it = tid + kProdW * k;
-    arow[k] = it % arows;
-    apl[k] = (it < nAitems) ? it / arows : -1;
-    bpl[k] = (it < nBitems) ? it % g.bplanes : -1;
-    brow[k] = it / g.bplanes;
+    arow[k] = it % g.arows;
+    apl[k] = (it < nAitems) ? it / g.arows : -1;
+    brow[k] = it % kKS;
+    bpl[k] = (it < nBitems) ? it / kKS : -1;
   }
-  float xn[3][NX];
-  uint4 dzn[3];
-  bool okn[3];
+  const unsigned char* aplane[3];
+  const unsigned char* bplane[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    aplane[k] = a.phi + ((long long)(chunk * 16 + (apl[k] >= 0 ? apl[k] : 0)) * g.L) * 16;
+    bplane[k] = a.dzf + ((long long)(ct * g.bplanes + (bpl[k] >= 0 ? bpl[k] : 0)) * g.L) * 16;
+  }
+  uint4 an[3], bn[3];
   auto fetch = [&](int bi) {
-    const int* tab = rowtab + (bi & 1) * 80;
-    const long long m0 = (blk0 + bi) * kKS;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const int off = (apl[k] >= 0) ? tab[arow[k]] : -1;
-      okn[k] = off >= 0;
-      const int c0 = BASE ? ((chunk - g.nsc) * 128 + apl[k] * 8) : (chunk * g.cps + apl[k] * (nb == 8 ? 1 : 2));
-      const float* src = xsrc + (long long)c0 * HW + (off >= 0 ? off : 0);
-#pragma unroll
-      for (int i = 0; i < NX; ++i)
-        xn[k][i] = (off >= 0 && c0 + i < cin && (BASE || nb != 8 || i == 0)) ? __ldg(src + (long long)i * HW) : 0.0f;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      dzn[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (bpl[k] >= 0) {
-        const long long m = m0 + brow[k];
-        const int co = ct * g.ntile + bpl[k] * 8;
-        if (m < g.L && co < g.cq) dzn[k] = __ldg(reinterpret_cast<const uint4*>(a.dzf + (m * g.cq + co) * 2));
-      }
+      const long long q = qoff + (long long)bi * kKS + arow[k];
+      an[k] = (apl[k] >= 0 && q >= 0 && q < g.L) ? __ldg(reinterpret_cast<const uint4*>(aplane[k] + q * 16)) : make_uint4(0u, 0u, 0u, 0u);
+      const long long m = (blk0 + bi) * kKS + brow[k];
+      bn[k] = (bpl[k] >= 0 && m < g.L && (ct * g.bplanes + bpl[k]) * 8 < g.cq)
+                  ? __ldg(reinterpret_cast<const uint4*>(bplane[k] + m * 16)) : make_uint4(0u, 0u, 0u, 0u);
     }
   };
-  auto prod_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kProdW) : "memory"); };
-
-  table_step(0);
-  table_step(1);
-  prod_sync();
   if (nblocks > 0) fetch(0);
   int st = 0;
   uint32_t ph = 0;
@@ -194,45 +201,21 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     trp.stamp();
     unsigned char* As = smem + (size_t)st * g.stage_bytes;
     unsigned char* Bs = As + g.a_bytes;
-    // ---- convert block bi (registers) to packed bf16 ----
-    uint4 v[3], dzv[3];
+    uint4 av[3], bv[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      dzv[k] = dzn[k];
-      const int c0 = BASE ? ((chunk - g.nsc) * 128 + apl[k] * 8) : (chunk * g.cps + apl[k] * (nb == 8 ? 1 : 2));
-      if (BASE) {
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = (okn[k] && c0 + i < cin) ? kc_act(d.act, xn[k][i < NX ? i : 0]) : 0.0f;
-        v[k] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-      } else if (nb == 8) {
-        const bool ok = okn[k] && c0 < cin;
-        if (g.fast_cubic) v[k] = cubic8w(xn[k][0], g.t0, g.inv_h, B->nparams - 1, ok);
-        else v[k] = ok ? basis8w_generic(*B, xn[k][0]) : make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-        if (okn[k]) {
-          if (c0 < cin) lo = basis4w(*B, xn[k][0]);
-          if (c0 + 1 < cin) hi = basis4w(*B, xn[k][1]);
-        }
-        v[k] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-      }
-    }
-    // ---- prefetch block bi+1; the table slot of block bi is recycled for block bi+2 ----
+    for (int k = 0; k < 3; ++k) { av[k] = an[k]; bv[k] = bn[k]; }
     if (bi + 1 < nblocks) fetch(bi + 1);
-    table_step(bi & 1);
     trp.stamp();
     mbar_wait(&empty[st], ph ^ 1);
     trp.stamp();
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (apl[k] >= 0) reinterpret_cast<uint4*>(As + apl[k] * g.aplane_bytes)[arow[k]] = v[k];
-      if (bpl[k] >= 0) reinterpret_cast<uint4*>(Bs + bpl[k] * g.bplane_bytes)[brow[k]] = dzv[k];
+      if (apl[k] >= 0) reinterpret_cast<uint4*>(As + apl[k] * g.aplane_bytes)[arow[k]] = av[k];
+      if (bpl[k] >= 0) reinterpret_cast<uint4*>(Bs + bpl[k] * g.bplane_bytes)[brow[k]] = bv[k];
     }
     trp.stamp();
     fence_proxy_async_smem();
     mbar_arrive(&full[st]);
-    prod_sync();                                   // table slot (bi & 1) is complete before block bi+2 is fetched
     if (++st == g.stages) { st = 0; ph ^= 1; }
   }
 }
@@ -247,7 +230,6 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   uint64_t* acc_full = bars + 2 * kMaxStagesW;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesW + 1);
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
-  int* rowtab = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(B) + ((sizeof(KcBasisCtx) + 15) / 16) * 16);   // [2][80]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // unit = ((cout tile * nchunks + chunk) * kh + r)
@@ -255,7 +237,6 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   const int r = unit % d.kh;
   const int chunk = (unit / d.kh) % g.nchunks;
   const int ct = unit / (d.kh * g.nchunks);
-  const bool is_base = chunk >= g.nsc;
   const long long blk0 = (long long)split * g.blk_per_split;
   const long long blk1 = min(g.nblk, blk0 + g.blk_per_split);
   const int nblocks = (int)(blk1 - blk0);
@@ -274,8 +255,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
 
   if (warp < 16) {
     // ============================ producers: Phi (A) evaluated on the fly, dz (B) copied ===========================
-    if (is_base) wg_produce<true>(a, smem, rowtab, full, empty, B, r, chunk, ct, blk0, nblocks);
-    else wg_produce<false>(a, smem, rowtab, full, empty, B, r, chunk, ct, blk0, nblocks);
+    wg_produce(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
   }
   if (warp == kMmaWarpW) {
     // ============================ MMA issuer (whole warp uniform, one elected lane issues) ==========================
@@ -429,7 +409,8 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   if (ns > max_split) ns = max_split;
   g->blk_per_split = (g->nblk + ns - 1) / ns;
   g->nsplit = (int)((g->nblk + g->blk_per_split - 1) / g->blk_per_split);
-  g->ws_bytes = (size_t)g->nsplit * g->units * d->kw * 128 * g->ntile * sizeof(float);
+  g->ws_bytes = (((size_t)g->nsplit * g->units * d->kw * 128 * g->ntile * sizeof(float)) + 255) / 256 * 256;
+  g->phi_bytes = (size_t)g->nchunks * 16 * (size_t)g->L * 16;
   g->fast_cubic = knots_uniform_cubic_w(d, &g->t0, &g->inv_h) ? 1 : 0;
   return KC_OK;
 }
@@ -445,7 +426,7 @@ extern "C" int kc_debug_trace_wgrad(void* device_buffer) {
 size_t kc_tc_wgrad_ws_bytes(const kc_desc* d) {
   WgGeom g;
   if (wgrad_geometry(d, &g) != KC_OK) return 0;
-  return g.ws_bytes;
+  return g.ws_bytes + g.phi_bytes;
 }
 
 extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base, const float* x_basis,
@@ -462,6 +443,13 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   memset(&a, 0, sizeof(a));
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.dzf = (const unsigned char*)dz_flat; a.beta = beta;
   a.ws = (float*)workspace;
+  unsigned char* phi = (unsigned char*)workspace + g.ws_bytes;
+  a.phi = phi;
+  {
+    dim3 pgrid((unsigned)((g.L + 255) / 256), (unsigned)(g.nchunks * 16));
+    kc_phi_flat_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a, phi);
+    KC_LAUNCH_CHECK("kc_phi_flat_kernel");
+  }
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
   kc_wgrad_tc_kernel<<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
