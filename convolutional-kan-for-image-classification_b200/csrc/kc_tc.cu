@@ -46,6 +46,7 @@ struct TcGeom {
   int nsub, mcta;              // M sub-tiles per CTA, rows per CTA
   int SS, nrows, plane_bytes;
   int ntile, n_ntiles, tmem_cols, bstages, na;
+  int tps;                     // filter taps per B ring stage (1, or kw = a whole filter row)
   long long mtiles;
   long long wimg_bytes_per_ntile;
   size_t smem_bytes;
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
   const TcGeom& g = a.g;
   // ---- carve shared memory ---------------------------------------------------------------------------
   const int abuf_bytes = kPL * g.plane_bytes;
-  const int bstage_bytes = kPL * g.ntile * 16;
+  const int btap_bytes = kPL * g.ntile * 16;
+  const int bstage_bytes = g.tps * btap_bytes;
   unsigned char* abuf0 = smem;
   unsigned char* bst0 = abuf0 + g.na * abuf_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bst0 + g.bstages * bstage_bytes);
@@ -257,36 +259,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     };
     Tracer trp(tp == 0 ? 0 : 3, tp == 0 || tp == 300);
     if (nb == 8 && g.nsc > 0) fetch8(0, xnext);
-    int buf = 0;
-    uint32_t aphase = 0;
-    for (int q = 0; q < nchunks; ++q) {
-      unsigned char* ab = abuf0 + buf * abuf_bytes;
-      trp.stamp();                                   // chunk start
-      if (MODE == kModeDgrad) {
-        // copy chunk: k-core = 8 consecutive output channels of one flat position, read as one 16-byte vector
-        const int ncols = chunk_cols(g, q);
-        uint4 v[kRB][2];
+    if (MODE == kModeDgrad) {
+      // copy chunks: k-core = 8 consecutive output channels of one flat position = one 16-byte vector of the plane-major
+      // dz buffer.  cp.async straight into the A ring, na-1 chunks in flight per thread (no registers, no exposed latency).
+      const int depth = g.na - 1;
+      for (int it = 0; it < nchunks + depth; ++it) {
+        if (it < nchunks) {
+          const int bufc = it % g.na;
+          const uint32_t phc = (uint32_t)(it / g.na) & 1u;
+          const int ncols = chunk_cols(g, it);
+          mbar_wait(&a_empty[bufc], phc ^ 1);
+          unsigned char* ab = abuf0 + bufc * abuf_bytes;
 #pragma unroll
-        for (int k = 0; k < kRB; ++k)
+          for (int k = 0; k < kRB; ++k) {
+            if (offs[k] == -2) continue;
+            const int b = r0 + k * kRowThreads;
 #pragma unroll
-          for (int cl = 0; cl < 2; ++cl) {
-            const int grp = q * kPL + half * 2 + cl;
-            v[k][cl] = (offs[k] >= 0 && grp * 8 < a.cq)
-                           ? __ldg(reinterpret_cast<const uint4*>(a.dzf + ((long long)grp * g.L + offs[k]) * 16))
-                           : make_uint4(0u, 0u, 0u, 0u);
-          }
-        mbar_wait(&a_empty[buf], aphase ^ 1);
-        trp.stamp();
-#pragma unroll
-        for (int k = 0; k < kRB; ++k) {
-          const int b = r0 + k * kRowThreads;
-#pragma unroll
-          for (int cl = 0; cl < 2; ++cl) {
-            const int pl = half * 2 + cl;
-            if (offs[k] != -2 && pl < ncols) reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v[k][cl];
+            for (int cl = 0; cl < 2; ++cl) {
+              const int pl = half * 2 + cl, grp = it * kPL + pl;
+              if (pl >= ncols) continue;
+              const bool ok = offs[k] >= 0 && grp * 8 < a.cq;
+              cp_async16(ab + pl * plane_bytes + b * 16, ok ? a.dzf + ((long long)grp * g.L + offs[k]) * 16 : a.dzf, ok ? 16u : 0u);
+            }
           }
         }
-      } else if (q < g.nsc && nb == 8) {
+        cp_async_commit();
+        if (it >= depth) {
+          if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          fence_proxy_async_smem();
+          mbar_arrive(&a_full[(it - depth) % g.na]);
+        }
+      }
+    }
+    int buf = 0;
+    uint32_t aphase = 0;
+    for (int q = 0; MODE != kModeDgrad && q < nchunks; ++q) {
+      unsigned char* ab = abuf0 + buf * abuf_bytes;
+      trp.stamp();                                   // chunk start
+      if (q < g.nsc && nb == 8) {
         float xv[kRB][2];
 #pragma unroll
         for (int k = 0; k < kRB; ++k) { xv[k][0] = xnext[k][0]; xv[k][1] = xnext[k][1]; }
@@ -378,37 +388,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * g.ntile);
       const uint32_t abuf_u = smem_u32(abuf0) >> 4, bst_u = smem_u32(bst0) >> 4;
       const uint32_t abuf_sz = (uint32_t)abuf_bytes >> 4, bst_sz = (uint32_t)bstage_bytes >> 4;
-      const int nsub = g.nsub, ntile = g.ntile, kw = d.kw, SS = g.SS;
+      const int nsub = g.nsub, ntile = g.ntile, kw = d.kw, SS = g.SS, tps = g.tps;
       int stage = 0, buf = 0;
       uint32_t bphase = 0, aphase = 0;
       Tracer trm(1, lane == 0);
       for (int q = 0; q < nchunks; ++q) {
         const int nk2 = chunk_cols(g, q) >> 1;
+        const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);      // 16-byte units per tap image
         trm.stamp();                                 // before a_full wait
         mbar_wait(&a_full[buf], aphase);
         tc_fence_after();
         trm.stamp();                                 // a_full acquired
         uint32_t arow = abuf_u + (uint32_t)buf * abuf_sz;      // (address >> 4) of tap (0,0), sub-tile 0, k2 = 0
         int s = 0;
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t < T; t += tps) {
           mbar_wait(&b_full[stage], bphase);
           tc_fence_after();
           trm.stamp();                               // b_full acquired
-          const uint32_t b_lo = b_lo_c + bst_u + (uint32_t)stage * bst_sz;
-          const uint32_t first = (q | t) != 0 ? 1u : 0u;
+          uint32_t b_lo = b_lo_c + bst_u + (uint32_t)stage * bst_sz;
           const bool two = nk2 == 2;
-          if (elect_one_sync()) {
-            if (nsub == 4) issue_step<4>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
-            else if (nsub == 3) issue_step<3>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
-            else if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
-            else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+          const bool leader = elect_one_sync();
+          for (int tt = 0; tt < tps; ++tt) {
+            const uint32_t first = (q | (t + tt)) != 0 ? 1u : 0u;
+            if (leader) {
+              if (nsub == 4) issue_step<4>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+              else if (nsub == 3) issue_step<3>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+              else if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+              else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+            }
+            b_lo += btap_u;
+            // next tap: one position right, or first position of the next filter row (SS rows down)
+            if (++s == kw) { s = 0; arow += (uint32_t)(SS - (kw - 1)); } else { arow += 1u; }
+          }
+          if (leader) {
             tc_commit(&b_empty[stage]);
-            if (t == T - 1) tc_commit(&a_empty[buf]);
+            if (t + tps >= T) tc_commit(&a_empty[buf]);
           }
           __syncwarp();
           if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
-          // next tap: one position right, or first position of the next filter row (SS rows down)
-          if (++s == kw) { s = 0; arow += (uint32_t)(SS - (kw - 1)); } else { arow += 1u; }
         }
         if (++buf == g.na) { buf = 0; aphase ^= 1; }
       }
@@ -423,8 +440,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
       Tracer trl(2, true);
       for (int q = 0; q < nchunks; ++q) {
-        const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u;
-        for (int t = 0; t < T; ++t) {
+        const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
+        for (int t = 0; t < T; t += g.tps) {
           mbar_wait(&b_empty[stage], bphase ^ 1);
           trl.stamp();                               // b_empty acquired
           mbar_arrive_expect_tx(&b_full[stage], bytes);
@@ -690,9 +707,11 @@ size_t tc_fixed_smem() { return (size_t)kNumBars * 8 + 16 + sizeof(KcBasisCtx) +
 // Common tail of the forward / dgrad geometry: choose nsub, ring depths and shared-memory carve-up.
 // kcores = total number of 16-byte k-cores per tap in the weight image of one N tile.
 int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
-  const size_t bstage = (size_t)kPL * g->ntile * 16;
+  const size_t btap = (size_t)kPL * g->ntile * 16;
   // nsub: as many 128-row sub-tiles per CTA as TMEM (512 columns), the producer row mapping (1024 rows), shared memory
-  // and the wish for >= 2 waves of CTAs allow.
+  // and the wish for >= 2 waves of CTAs allow.  tps: a ring stage carries a whole filter row (kw taps) when at least 4
+  // such stages fit - the per-stage cost of the issuing warp (barrier wait, fence, commits ~ several hundred cycles) is
+  // then paid once per kw taps - else a single tap.
   bool found = false;
   for (int nsub = 4; nsub >= 1 && !found; --nsub) {
     if (nsub * g->ntile > 512) continue;
@@ -706,10 +725,13 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
     const int plane_bytes = nrows * 16 + 16;       // +16 B: consecutive planes start 4 banks apart
     for (int na = kMaxA; na >= 2 && !found; --na) {
       size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
-      if (fixed + 6 * bstage > kSmemLimit) continue;
+      int tps = d->kw;
+      if (fixed + 4 * btap * tps > kSmemLimit) tps = 1;
+      const size_t bstage = btap * tps;
+      if (fixed + (tps == 1 ? 6 : 4) * bstage > kSmemLimit) continue;
       int bst = (int)((kSmemLimit - fixed) / bstage);
       if (bst > kMaxBStages) bst = kMaxBStages;
-      g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes;
+      g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps;
       g->na = na; g->bstages = bst; g->mtiles = mtiles; g->smem_bytes = fixed + bst * bstage;
       found = true;
     }

@@ -156,9 +156,12 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
   *reinterpret_cast<uint4*>(out + ((long long)gp * g.L + q) * 16) = v;
 }
 
-// Producer role of the wgrad kernel (512 threads): pure 16-byte copies of the Phi planes (A, with the filter-row shift)
-// and the dz planes (B) into the stage; rows are the fastest index so global reads are contiguous.  Block i+1 is
-// prefetched into registers while block i is stored.
+// Producer role of the wgrad kernel (512 threads): pure 16-byte cp.async copies of the Phi planes (A, with the filter-row
+// shift) and the dz planes (B) straight into the stage; rows are the fastest index so global reads are contiguous.
+// kPrefetchW stages are kept in flight per thread (commit_group / wait_group), then the landed stage is fenced for the
+// tensor-core proxy and published on its `full` barrier.
+constexpr int kPrefetchW = 3;
+
 __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int r, int chunk,
                                            int ct, long long blk0, int nblocks) {
   const kc_desc& d = a.d;
@@ -166,57 +169,67 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
   const int tid = threadIdx.x;
   const int nAitems = g.arows * 16, nBitems = kKS * g.bplanes;
   const long long qoff = blk0 * kKS + (long long)(r - d.pad_h) * g.P - d.pad_w;
-  int arow[3], apl[3], brow[3], bpl[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int it = tid + kProdW * k;
-    arow[k] = it % g.arows;
-    apl[k] = (it < nAitems) ? it / g.arows : -1;
-    brow[k] = it % kKS;
-    bpl[k] = (it < nBitems) ? it / kKS : -1;
-  }
+  int arow[3], brow[3];
+  uint32_t adst[3], bdst[3];                      // byte offsets inside a stage, 0xffffffff = no item
   const unsigned char* aplane[3];
   const unsigned char* bplane[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    aplane[k] = a.phi + ((long long)(chunk * 16 + (apl[k] >= 0 ? apl[k] : 0)) * g.L) * 16;
-    bplane[k] = a.dzf + ((long long)(ct * g.bplanes + (bpl[k] >= 0 ? bpl[k] : 0)) * g.L) * 16;
+    const int it = tid + kProdW * k;
+    arow[k] = it % g.arows;
+    const int apl = it / g.arows;
+    adst[k] = (it < nAitems) ? (uint32_t)(apl * g.aplane_bytes + arow[k] * 16) : 0xffffffffu;
+    aplane[k] = a.phi + ((long long)(chunk * 16 + (it < nAitems ? apl : 0)) * g.L) * 16;
+    brow[k] = it % kKS;
+    const int bpl = it / kKS;
+    const bool bok = it < nBitems && (ct * g.bplanes + bpl) * 8 < g.cq;
+    bdst[k] = (it < nBitems) ? (uint32_t)(g.a_bytes + bpl * g.bplane_bytes + brow[k] * 16) : 0xffffffffu;
+    bplane[k] = bok ? a.dzf + ((long long)(ct * g.bplanes + bpl) * g.L) * 16 : nullptr;
   }
-  uint4 an[3], bn[3];
-  auto fetch = [&](int bi) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const long long q = qoff + (long long)bi * kKS + arow[k];
-      an[k] = (apl[k] >= 0 && q >= 0 && q < g.L) ? __ldg(reinterpret_cast<const uint4*>(aplane[k] + q * 16)) : make_uint4(0u, 0u, 0u, 0u);
-      const long long m = (blk0 + bi) * kKS + brow[k];
-      bn[k] = (bpl[k] >= 0 && m < g.L && (ct * g.bplanes + bpl[k]) * 8 < g.cq)
-                  ? __ldg(reinterpret_cast<const uint4*>(bplane[k] + m * 16)) : make_uint4(0u, 0u, 0u, 0u);
-    }
-  };
-  if (nblocks > 0) fetch(0);
-  int st = 0;
-  uint32_t ph = 0;
   TracerW trp(0, tid == 0);
-  for (int bi = 0; bi < nblocks; ++bi) {
-    trp.stamp();
-    unsigned char* As = smem + (size_t)st * g.stage_bytes;
-    unsigned char* Bs = As + g.a_bytes;
-    uint4 av[3], bv[3];
+  for (int it = 0; it < nblocks + kPrefetchW; ++it) {
+    if (it < nblocks) {
+      const int st = it % g.stages;
+      const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
+      trp.stamp();
+      mbar_wait(&empty[st], ph ^ 1);
+      trp.stamp();
+      unsigned char* stage = smem + (size_t)st * g.stage_bytes;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { av[k] = an[k]; bv[k] = bn[k]; }
-    if (bi + 1 < nblocks) fetch(bi + 1);
-    trp.stamp();
-    mbar_wait(&empty[st], ph ^ 1);
-    trp.stamp();
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (apl[k] >= 0) reinterpret_cast<uint4*>(As + apl[k] * g.aplane_bytes)[arow[k]] = av[k];
-      if (bpl[k] >= 0) reinterpret_cast<uint4*>(Bs + bpl[k] * g.bplane_bytes)[brow[k]] = bv[k];
+      for (int k = 0; k < 3; ++k) {
+        if (adst[k] != 0xffffffffu) {
+          const long long q = qoff + (long long)it * kKS + arow[k];
+          const bool ok = q >= 0 && q < g.L;
+          cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
+        }
+        if (bdst[k] != 0xffffffffu) {
+          const long long m = (blk0 + it) * kKS + brow[k];
+          const bool ok = bplane[k] != nullptr && m < g.L;
+          cp_async16(stage + bdst[k], ok ? bplane[k] + m * 16 : a.dzf, ok ? 16u : 0u);
+        }
+      }
     }
-    trp.stamp();
-    fence_proxy_async_smem();
-    mbar_arrive(&full[st]);
-    if (++st == g.stages) { st = 0; ph ^= 1; }
+    cp_async_commit();
+    if (it >= kPrefetchW) {
+      cp_async_wait<kPrefetchW>();                 // every group older than the newest kPrefetchW has landed
+      fence_proxy_async_smem();
+      mbar_arrive(&full[(it - kPrefetchW) % g.stages]);
+    }
+  }
+}
+
+// Straight-line issue of the KW x 4 MMAs of one stage (tap s reads the Phi planes from row s; k-step ks advances both
+// operands by 16 rows).  Descriptor low words differ by small constants only.
+template <int KW>
+__device__ __forceinline__ void wg_issue(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int s = 0; s < KW; ++s) {
+    const uint32_t td = tmem_base + (uint32_t)s * ntile;
+#pragma unroll
+    for (int ks = 0; ks < kKS / 16; ++ks)
+      tc_mma_bf16(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
+                  ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
   }
 }
 
@@ -276,13 +289,16 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
       const uint32_t au = smem_u + (uint32_t)st * stage_u, bu = au + a_u;
       const uint32_t first = bi != 0 ? 1u : 0u;
       if (elect_one_sync()) {
-        for (int s = 0; s < kw; ++s) {
-          const uint32_t td = tmem_base + (uint32_t)(s * ntile);
+        const uint32_t a_lo = lo_c | au, b_lo = lo_c | bu;
+        if (kw == 3) wg_issue<3>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else if (kw == 1) wg_issue<1>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else {
+          for (int s = 0; s < kw; ++s) {
+            const uint32_t td = tmem_base + (uint32_t)(s * ntile);
 #pragma unroll
-          for (int ks = 0; ks < kKS / 16; ++ks) {
-            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(lo_c | (au + (uint32_t)(s + 16 * ks)));
-            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(lo_c | (bu + (uint32_t)(16 * ks)));
-            tc_mma_bf16(td, ad, bd, idesc, ks == 0 ? first : 1u);
+            for (int ks = 0; ks < kKS / 16; ++ks)
+              tc_mma_bf16(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
+                          ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
           }
         }
         tc_commit(&empty[st]);
@@ -321,32 +337,38 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
 }
 
 // Sum the splits (fixed order) and scatter into the reference layouts dw_basis [cout][cin*nb][kh][kw] (inner index
-// c*nb+j, or j*cin+c for GRAM) and dw_base [cout][cin][kh][kw].
+// c*nb+j, or j*cin+c for GRAM) and dw_base [cout][cin][kh][kw].  Threads walk the workspace layout, so the nsplit reads
+// per element are coalesced; only the single write per weight is scattered.
 __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_kernel(const __grid_constant__ kc_desc d, const __grid_constant__ WgGeom g,
                                                                  const float* __restrict__ ws, float* __restrict__ dw_base,
                                                                  float* __restrict__ dw_basis) {
-  const bool has_base = d.act != KC_ACT_NONE;
-  const int nb = d.nb, wb = nb + (has_base ? 1 : 0), T = d.kh * d.kw;
-  const long long total = (long long)d.cout * d.cin * wb * T;
+  const int nb = d.nb, T = d.kh * d.kw;
   const long long unit_sz = (long long)d.kw * 128 * g.ntile;
+  const long long total = (long long)g.units * unit_sz;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // i enumerates [co][c][j (wb)][tap]
-    const int tap = (int)(i % T);
-    long long rest = i / T;
-    const int j = (int)(rest % wb); rest /= wb;
-    const int c = (int)(rest % d.cin);
-    const int co = (int)(rest / d.cin);
-    const int r = tap / d.kw, s = tap - r * d.kw;
-    const int ct = co / g.ntile, n = co - ct * g.ntile;
-    int chunk, m;
-    if (j < nb) { chunk = c / g.cps; m = (c - chunk * g.cps) * nb + j; }
-    else { chunk = g.nsc + c / 128; m = c % 128; }
-    const long long unit = ((long long)ct * g.nchunks + chunk) * d.kh + r;
-    const float* p = ws + unit * unit_sz + ((long long)s * 128 + m) * g.ntile + n;
+    const int n = (int)(i % g.ntile);
+    long long rest = i / g.ntile;
+    const int m = (int)(rest % 128); rest /= 128;
+    const int s = (int)(rest % d.kw);
+    const int unit = (int)(rest / d.kw);
+    const int r = unit % d.kh;
+    const int chunk = (unit / d.kh) % g.nchunks;
+    const int ct = unit / (d.kh * g.nchunks);
+    const int co = ct * g.ntile + n;
+    if (co >= d.cout) continue;
+    float* dst;
+    if (chunk < g.nsc) {
+      const int c = chunk * g.cps + m / nb, j = m % nb;
+      if (c >= d.cin) continue;
+      dst = dw_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + r * d.kw + s;
+    } else {
+      const int c = (chunk - g.nsc) * 128 + m;
+      if (c >= d.cin) continue;
+      dst = dw_base + ((long long)co * d.cin + c) * T + r * d.kw + s;
+    }
     float acc = 0.0f;
-    for (int k = 0; k < g.nsplit; ++k) acc += p[(long long)k * g.units * unit_sz];
-    if (j < nb) dw_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + tap] = acc;
-    else dw_base[((long long)co * d.cin + c) * T + tap] = acc;
+    for (int k = 0; k < g.nsplit; ++k) acc += ws[(long long)k * total + i];
+    *dst = acc;
   }
 }
 
@@ -398,7 +420,7 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 16 + 2 * 80 * sizeof(int) + 128;
   g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
   if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
-  if (g->stages < 2) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
+  if (g->stages < kPrefetchW + 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
   g->smem_bytes = fixed + (size_t)g->stages * g->stage_bytes;
   g->tmem_cols = 32;
   while (g->tmem_cols < d->kw * g->ntile) g->tmem_cols *= 2;
@@ -454,8 +476,7 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
   kc_wgrad_tc_kernel<<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
   KC_LAUNCH_CHECK("kc_wgrad_tc_kernel");
-  const int wb = d->nb + (d->act != KC_ACT_NONE ? 1 : 0);
-  long long total = (long long)d->cout * d->cin * wb * d->kh * d->kw;
+  long long total = (long long)g.units * d->kw * 128 * g.ntile;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   kc_wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);

@@ -5,7 +5,8 @@ import sys
 
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+extra = sys.argv[3:]  # e.g. -k regex:wgrad
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
