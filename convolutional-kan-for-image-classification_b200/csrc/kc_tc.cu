@@ -124,6 +124,8 @@ __device__ __forceinline__ uint4 cubic8(float x, float t0, float inv_h, int nint
 // allocation of the closed-form cubic fast path
 __device__ __noinline__ uint4 basis8_generic(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) phi[j] = 0.0f;      // widths 5..7 are zero-padded to 8 (their packed weights are zero too)
   kc_eval_basis(B, x, phi, nullptr, 1);
   return make_uint4(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]), pack_bf16(phi[4], phi[5]), pack_bf16(phi[6], phi[7]));
 }
@@ -133,6 +135,8 @@ __device__ __forceinline__ uint4 basis8(const KcBasisCtx& B, const TcGeom& g, fl
 }
 __device__ __noinline__ uint2 basis4(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) phi[j] = 0.0f;      // widths 1..3 are zero-padded to 4
   kc_eval_basis(B, x, phi, nullptr, 1);
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       }
       offs[k] = off;
     }
-    const int plane_bytes = g.plane_bytes, cin = d.cin, nb = d.nb;
+    const int plane_bytes = g.plane_bytes, cin = d.cin, nb = d.nb > 4 ? 8 : 4;   // padded basis width
     // x values of the NEXT spline chunk are fetched while the current one is evaluated (nb == 8 path):
     // this thread owns planes half*2 + {0,1} = channels q*4 + half*2 + {0,1}
     float xnext[kRB][2];
@@ -600,8 +604,8 @@ __global__ void __launch_bounds__(256) kc_pack_fwd_kernel(const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           int c, j;
-          if (nb == 8) { c = q * 4 + kc; j = e; } else { c = q * 8 + kc * 2 + (e >> 2); j = e & 3; }
-          if (c < d.cin) f[e] = a.w_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + t];
+          if (nb > 4) { c = q * 4 + kc; j = e; } else { c = q * 8 + kc * 2 + (e >> 2); j = e & 3; }
+          if (c < d.cin && j < nb) f[e] = a.w_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + t];
         }
       }
     } else if (has_base) {
@@ -746,7 +750,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
 
 int tc_common_checks(const kc_desc* d) {
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs stride 1 and dilation 1");
-  if (d->nb != 8 && d->nb != 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs basis width 4 or 8 (got %d)", d->nb);
+  if (d->nb < 1 || d->nb > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs basis width <= 8 (got %d)", d->nb);
   if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs padding < kernel size");
   if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs kernel size <= 8");
   if ((long long)d->n * d->x_batch_stride >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs < 2^31 input elements");
@@ -781,7 +785,7 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
   memset(g, 0, sizeof(*g));
   const bool has_base = d->act != KC_ACT_NONE;
   const int T = d->kh * d->kw;
-  g->cps = (d->nb == 8) ? 4 : 8;
+  g->cps = (d->nb > 4) ? 4 : 8;            // basis width is zero-padded to 8 or 4
   g->Cp = round_up(d->cin, 8);
   g->nsc = g->Cp / g->cps;
   g->ngroups = g->Cp / 8;

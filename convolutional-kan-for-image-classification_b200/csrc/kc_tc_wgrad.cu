@@ -104,11 +104,15 @@ __device__ __forceinline__ uint4 cubic8w(float x, float t0, float inv_h, int nin
 }
 __device__ __noinline__ uint4 basis8w_generic(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) phi[j] = 0.0f;
   kc_eval_basis(B, x, phi, nullptr, 1);
   return make_uint4(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]), pack_bf16(phi[4], phi[5]), pack_bf16(phi[6], phi[7]));
 }
 __device__ __noinline__ uint2 basis4w(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) phi[j] = 0.0f;
   kc_eval_basis(B, x, phi, nullptr, 1);
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
   const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
   const int gp = blockIdx.y, chunk = gp >> 4, pl = gp & 15;
   if (q >= g.L) return;
-  const int HW = d.h * d.w, nb = d.nb;
+  const int HW = d.h * d.w, nb = d.nb > 4 ? 8 : 4;      // padded basis width
   const int n = (int)(q / g.IMG);
   const int rem = (int)(q - (long long)n * g.IMG);
   const int y = rem / g.P, x = rem - y * g.P;
@@ -358,8 +362,9 @@ __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_kernel(const __grid_co
     if (co >= d.cout) continue;
     float* dst;
     if (chunk < g.nsc) {
-      const int c = chunk * g.cps + m / nb, j = m % nb;
-      if (c >= d.cin) continue;
+      const int nbp = nb > 4 ? 8 : 4;
+      const int c = chunk * g.cps + m / nbp, j = m % nbp;
+      if (c >= d.cin || j >= nb) continue;
       dst = dw_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + r * d.kw + s;
     } else {
       const int c = (chunk - g.nsc) * 128 + m;
@@ -388,7 +393,7 @@ bool knots_uniform_cubic_w(const kc_desc* d, float* t0, float* inv_h) {
 
 int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs stride 1 and dilation 1");
-  if (d->nb != 8 && d->nb != 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs basis width 4 or 8 (got %d)", d->nb);
+  if (d->nb < 1 || d->nb > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs basis width <= 8 (got %d)", d->nb);
   if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs padding < kernel size");
   if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs kernel size <= 8");
   if ((long long)d->n * d->x_batch_stride >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs < 2^31 input elements");
@@ -399,7 +404,7 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->L = (long long)d->n * g->IMG;
   if (g->L >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs < 2^31 flat positions");
   g->cq = round_up_w(d->cout, 16);
-  g->cps = 128 / d->nb;
+  g->cps = 128 / (d->nb > 4 ? 8 : 4);
   g->nsc = (d->cin + g->cps - 1) / g->cps;
   g->nbc = has_base ? (d->cin + 127) / 128 : 0;
   g->nchunks = g->nsc + g->nbc;
