@@ -302,3 +302,92 @@ def test_fastkan_mobilenetv2_bf16_layers_match_fp32_layers():
         worst = max(worst, e)
         assert e < BF16_TOL, (name, e)
     print("worst per-layer bf16 vs fp32 deviation:", f"{worst:.2e}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Size-independent properties at BASELINE's full sizes (the oracle is too slow there): configs 2 and 3/5 layer shapes.
+# ---------------------------------------------------------------------------------------------------------------------
+FULL = [("cheby", 64, 128, 32, 256), ("kan", 64, 128, 32, 256), ("kan", 64, 64, 224, 8)]
+
+
+def _full_layer(kind, cin, cout):
+    torch.manual_seed(0)
+    if kind == "cheby":
+        return K.ChebyKANConv2DLayer(cin, cout, 3, degree=3, padding=1).cuda()
+    return K.KANConv2DLayer(cin, cout, 3, spline_order=3, grid_size=5, padding=1, base_activation=nn.SiLU).cuda()
+
+
+def _conv_args(kind, m):
+    if kind == "cheby":
+        return m._spec, [], [m.poly_conv[0].weight]
+    return m._spec, [m.base_conv[0].weight], [m.spline_conv[0].weight]
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,n", FULL)
+def test_full_size_conv_is_linear_in_weights_and_dz(kind, cin, cout, hw, n):
+    """z(x; aW1 + W2) = a z(x; W1) + z(x; W2) and dX(dz1 + dz2) = dX(dz1) + dX(dz2) for the tensor-core kernels at full
+    BASELINE sizes (config 2: 256 x 64 x 32 x 32, 64 -> 128; config 5 layer 2 at batch 8)."""
+    from kanconv_b200 import functional as KF
+    m = _full_layer(kind, cin, cout)
+    spec, wb, ws = _conv_args(kind, m)
+    torch.manual_seed(1)
+    x = torch.randn(n, cin, hw, hw, device="cuda")
+    w2b = [torch.randn_like(w) * w.std() for w in wb]
+    w2s = [torch.randn_like(w) * w.std() for w in ws]
+    with torch.no_grad():
+        z1 = KF.kan_conv(spec, x, None, None, wb, ws, "bf16")
+        z2 = KF.kan_conv(spec, x, None, None, w2b, w2s, "bf16")
+        z12 = KF.kan_conv(spec, x, None, None, [0.5 * a + b for a, b in zip(wb, w2b)], [0.5 * a + b for a, b in zip(ws, w2s)], "bf16")
+    assert rel_err(z12, 0.5 * z1 + z2) < BF16_TOL
+    xg = x.clone().requires_grad_(True)
+    z = KF.kan_conv(spec, xg, None, None, wb, ws, "bf16")
+    g1, g2 = torch.randn_like(z), torch.randn_like(z)
+    d1, = torch.autograd.grad(z, xg, g1, retain_graph=True)
+    d2, = torch.autograd.grad(z, xg, g2, retain_graph=True)
+    d12, = torch.autograd.grad(z, xg, g1 + g2)
+    assert rel_err(d12, d1 + d2) < BF16_TOL
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,n", FULL)
+def test_full_size_shards_and_reruns_are_bit_identical(kind, cin, cout, hw, n):
+    """Per-sample independence (what data-parallel sharding relies on): the layer applied to the two halves of the batch gives
+    bit-identical outputs to the full batch; a second run of forward + backward is bit-identical (deterministic wgrad)."""
+    m = _full_layer(kind, cin, cout)
+    m.precision = "bf16"
+    torch.manual_seed(2)
+    x = torch.randn(n, cin, hw, hw, device="cuda")
+    g = torch.randn(n, cout, hw, hw, device="cuda")
+
+    def run(xx, gg):
+        m.zero_grad()
+        xr = xx.clone().requires_grad_(True)
+        y = m(xr)
+        y.backward(gg)
+        return y.detach(), xr.grad.detach(), [p.grad.detach().clone() for p in m.parameters()]
+
+    y, dx, gw = run(x, g)
+    y_b, dx_b, gw_b = run(x, g)
+    assert torch.equal(y, y_b) and torch.equal(dx, dx_b) and all(torch.equal(a, b) for a, b in zip(gw, gw_b))
+    h = n // 2
+    ya, dxa, _ = run(x[:h], g[:h])
+    yb, dxb, _ = run(x[h:], g[h:])
+    assert torch.equal(torch.cat([ya, yb]), y)
+    assert torch.equal(torch.cat([dxa, dxb]), dx)
+
+
+def test_full_size_padding_lives_in_basis_space():
+    """x outside the knot span => every basis function is exactly zero, so the spline branch must vanish (also at the image
+    border, where the reference zero-pads the EXPANDED tensor) and z equals the base-branch convolution alone."""
+    from kanconv_b200 import functional as KF
+    import torch.nn.functional as F
+    m = _full_layer("kan", 64, 128)
+    spec, wb, ws = _conv_args("kan", m)
+    x = torch.full((4, 64, 32, 32), 5.0, device="cuda")            # > 2.2: outside [t_0, t_last)
+    with torch.no_grad():
+        z = KF.kan_conv(spec, x, None, None, wb, ws, "bf16")
+        ref = F.conv2d(F.silu(x).bfloat16().float(), wb[0].bfloat16().float(), padding=1)
+    assert rel_err(z, ref) < 1e-5
+    xz = torch.zeros(2, 64, 32, 32, device="cuda")                  # basis(0) != 0: interior and border must differ
+    with torch.no_grad():
+        z0 = KF.kan_conv(spec, xz, None, None, wb, ws, "bf16")
+    assert not torch.allclose(z0[:, :, 0, 0], z0[:, :, 16, 16])
