@@ -67,6 +67,7 @@ struct TcFwdArgs {
   int cq;                       // channels per flat row (cout rounded up to 16)
   float* dx_base;
   float* dx_basis;
+  float* dbeta;                 // GRAM only: d/d beta_weights accumulator (atomics), else nullptr
 };
 
 constexpr int kModeFwd = 0, kModeDgrad = 1;
@@ -524,6 +525,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    const bool gram = d.basis == KC_BASIS_GRAM && a.dbeta != nullptr;
+    float dbl[KC_MAX_BASIS];
+#pragma unroll
+    for (int j = 0; j < KC_MAX_BASIS; ++j) dbl[j] = 0.0f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (i >= g.nsub) break;
@@ -549,6 +554,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (j < nb) gs = fmaf(__uint_as_float(r[j]), dphi[j], gs);
+            if (gram) {       // d/d beta_weights through the Gram recurrence (gram_kan_layers.py:150-170)
+              float gg[KC_MAX_BASIS];
+#pragma unroll
+              for (int j = 0; j < KC_MAX_BASIS; ++j) gg[j] = __uint_as_float(r[j]);
+              kc_gram_dbeta(*B, xs[i][c4], gg, 1, dbl);
+            }
           }
           float gb = 0.0f;
           if (has_base) {
@@ -565,6 +576,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
             if (has_base && a.dx_base != nullptr) a.dx_base[o] = gb;
           }
         }
+      }
+    }
+    if (gram) {
+      for (int nn = 1; nn <= nb - 2; ++nn) {
+        float v = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KC_MAX_BASIS; ++j)
+          if (j == nn) v = dbl[j];
+        v = kc_warp_sum(v);
+        if (lane == 0 && v != 0.0f) atomicAdd(&a.dbeta[nn], v);
       }
     }
   }
@@ -761,7 +782,6 @@ int tc_common_checks(const kc_desc* d) {
 int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
   int rc = tc_common_checks(d);
   if (rc != KC_OK) return rc;
-  if (d->basis == KC_BASIS_GRAM) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core dgrad: GRAM beta gradient is computed by the FP32 kernel");
   memset(g, 0, sizeof(*g));
   const bool has_base = d->act != KC_ACT_NONE;
   const int T = d->kh * d->kw, wb = d->nb + (has_base ? 1 : 0);
@@ -977,7 +997,7 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
 extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                                 const void* packed_dgrad, const float* beta, float* dx_base, float* dx_basis,
                                 float* dbeta, void* workspace, void* stream) {
-  (void)dz; (void)dbeta;
+  (void)dz;
   int rc = kc_validate_desc(d);
   if (rc != KC_OK) return rc;
   TcGeom g;
@@ -990,6 +1010,7 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
   memset(&a, 0, sizeof(a));
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.wp = (const unsigned char*)packed_dgrad; a.beta = beta;
   a.dzf = (const unsigned char*)workspace; a.cq = g.Cp; a.dx_base = dx_base; a.dx_basis = dx_basis;
+  a.dbeta = (d->basis == KC_BASIS_GRAM) ? dbeta : nullptr;
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
   kc_tc_kernel<kModeDgrad><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);

@@ -242,7 +242,7 @@ class _KanConvFn(torch.autograd.Function):
                         ctypes.byref(d), _ptr(wbg), _ptr(wsg), None, _ptr(packed_d), stream)), "kc_tc_pack_weights")
                     L.check(_timed("kc_tc_kernel<dgrad>", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_tc(
                         ctypes.byref(d), None, _ptr(xbg), _ptr(xsg), _ptr(packed_d), _ptr(beta), _ptr(dx_base[:, sl]),
-                        _ptr(dx_basis[:, sl]), None, _ptr(dzf), stream)), "kc_conv_dgrad_tc")
+                        _ptr(dx_basis[:, sl]), _ptr(dbeta), _ptr(dzf), stream)), "kc_conv_dgrad_tc")
                 else:
                     L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
                         ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
