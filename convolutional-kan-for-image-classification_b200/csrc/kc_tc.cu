@@ -13,7 +13,9 @@
 // cycles, so every B stage feeds nsub*2 MMAs and the ring holds up to 16 stages; tcgen05.mma accumulates fp32 in TMEM;
 // 4 warps read TMEM with tcgen05.ld and write z (fp32 NCHW) coalesced.
 //
-// Warp roles (576 threads): 0-15 producers (0-3 also run the epilogue) | 16 weight loader | 17 MMA issuer + TMEM allocator.
+// Warp roles (608 threads): 0-15 producers (0-3 also run the epilogue) | 16 weight loader | 17-18 MMA issuers (17 also
+// allocates TMEM).  Two issuers, each owning half of the sub-tile accumulators: the tensor-core queue is shallow, so the
+// ~250 cycles of per-ring-step bookkeeping of one issuer would otherwise leave the pipe idle at small N.
 // The MMA issuer is the highest warp id on purpose: the scheduler arbitrates highest-warp-id-first, and the single issuing
 // thread must never wait behind the 16 ALU-heavy producer warps (measured: 245 -> ~50 cycles per tcgen05.mma).
 #include <string.h>
@@ -27,9 +29,9 @@ namespace {
 
 using namespace kc;
 
-constexpr int kTcThreads = 576;        // 18 warps
+constexpr int kTcThreads = 608;        // 19 warps
 constexpr int kProdThreads = 512;      // warps 0-15
-constexpr int kLoaderWarp = 16, kMmaWarp = 17;
+constexpr int kLoaderWarp = 16, kMmaWarp = 17;   // MMA issuers: warps 17 and 18 (sub-tiles split between them)
 constexpr int kRowThreads = 256;       // producer thread t owns rows (t & 255) + 256*k and plane half (t >> 8)
 constexpr int kRB = 4;                 // rows per producer thread  (nrows <= 1024)
 constexpr int kPL = 4;                 // k-cores ("planes") per chunk: K = 32 per ring step
@@ -169,9 +171,11 @@ __device__ __forceinline__ int chunk_cols(const TcGeom& g, int q) {
 // the issuing thread executes ~2 integer adds per tcgen05.mma and no branches.
 template <int NSUB>
 __device__ __forceinline__ void issue_step(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_k2,
-                                           uint32_t b_k2, uint32_t desc_hi, uint32_t idesc, uint32_t first, bool two) {
+                                           uint32_t b_k2, uint32_t desc_hi, uint32_t idesc, uint32_t first, bool two, int i0,
+                                           int istep) {
 #pragma unroll
-  for (int i = 0; i < NSUB; ++i) {
+  for (int ii = 0; ii < NSUB; ++ii) {
+    const int i = i0 + ii * istep;
     const uint32_t al = a_lo + (uint32_t)(i * kTileM);
     const uint32_t td = tmem_base + (uint32_t)i * ntile;
     tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | al, ((uint64_t)desc_hi << 32) | b_lo, idesc, first);
@@ -210,9 +214,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
   const int nchunks = (MODE == kModeDgrad) ? g.nbc : g.nsc + (has_base ? g.nbc : 0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], kProdThreads); mbar_init(&a_empty[i], 1); }
-    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(acc_full, 1);
+    const uint32_t nmw = g.nsub >= 2 ? 2u : 1u;      // issuing warps
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], kProdThreads); mbar_init(&a_empty[i], nmw); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], nmw); }
+    mbar_init(acc_full, nmw);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
@@ -381,8 +386,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       if (++buf == g.na) { buf = 0; aphase ^= 1; }
     }
   }
-  if (warp == kMmaWarp) {
-    // ================================ MMA issuer ======================================================
+  if (warp >= kMmaWarp && warp - kMmaWarp < (g.nsub >= 2 ? 2 : 1)) {
+    // ================================ MMA issuers =====================================================
     // The whole warp walks the pipeline with warp-uniform state; one elected lane issues tcgen05.mma / commit.
     // Per MMA only the 14-bit start-address fields of the two descriptors change (a few uniform integer adds).
     {
@@ -393,10 +398,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * g.ntile);
       const uint32_t abuf_u = smem_u32(abuf0) >> 4, bst_u = smem_u32(bst0) >> 4;
       const uint32_t abuf_sz = (uint32_t)abuf_bytes >> 4, bst_sz = (uint32_t)bstage_bytes >> 4;
-      const int nsub = g.nsub, ntile = g.ntile, kw = d.kw, SS = g.SS, tps = g.tps;
+      const int ntile = g.ntile, kw = d.kw, SS = g.SS, tps = g.tps;
+      const int mw = warp - kMmaWarp, nmw = g.nsub >= 2 ? 2 : 1;
+      const int nsub = (g.nsub - mw + nmw - 1) / nmw;       // sub-tiles mw, mw + nmw, ... of this issuer
       int stage = 0, buf = 0;
       uint32_t bphase = 0, aphase = 0;
-      Tracer trm(1, lane == 0);
+      Tracer trm(1, lane == 0 && mw == 0);
       for (int q = 0; q < nchunks; ++q) {
         const int nk2 = chunk_cols(g, q) >> 1;
         const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);      // 16-byte units per tap image
@@ -416,10 +423,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
           for (int tt = 0; tt < tps; ++tt) {
             const uint32_t first = (q | (t + tt)) != 0 ? 1u : 0u;
             if (leader) {
-              if (nsub == 4) issue_step<4>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
-              else if (nsub == 3) issue_step<3>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
-              else if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
-              else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two);
+              if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
+              else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
             }
             b_lo += btap_u;
             // next tap: one position right, or first position of the next filter row (SS rows down)
@@ -748,10 +753,12 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
     const long long mtiles = (g->L + mcta - 1) / mcta;
     if (nsub > 1 && mtiles * g->n_ntiles < 2 * 148) continue;
     const int plane_bytes = nrows * 16 + 16;       // +16 B: consecutive planes start 4 banks apart
-    for (int na = kMaxA; na >= 2 && !found; --na) {
-      size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
-      int tps = d->kw;
-      if (fixed + 4 * btap * tps > kSmemLimit) tps = 1;
+    // preference: whole-filter-row stages with a 3-deep A ring, then with a 2-deep A ring, then single-tap stages
+    const int cand_na[4] = {3, 2, 3, 2}, cand_tps[4] = {d->kw, d->kw, 1, 1};
+    for (int ci = 0; ci < 4 && !found; ++ci) {
+      const int na = cand_na[ci], tps = cand_tps[ci];
+      if (ci >= 2 && d->kw == 1) break;
+      const size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
       const size_t bstage = btap * tps;
       if (fixed + (tps == 1 ? 6 : 4) * bstage > kSmemLimit) continue;
       int bst = (int)((kSmemLimit - fixed) / bstage);
@@ -1084,55 +1091,70 @@ extern "C" int kc_debug_mma_rate(int N, int a_lbo, int a_sbo, int b_lbo, int b_s
   return KC_OK;
 }
 
-// Debug only: tcgen05.mma execution rate with the warp-uniform elect issue path (4 MMAs per iteration, descriptors are
-// loop-invariant apart from the k-step), for the K-major (conv fwd/dgrad) and MN-major (wgrad) no-swizzle layouts.
-__global__ void __launch_bounds__(32, 1) kc_mma_rate2_kernel(int N, int mn_major, int iters, float* out) {
+// Debug only: tcgen05.mma execution rate with the warp-uniform elect issue path, mimicking one ring step of the conv
+// kernels: nsub accumulators x 2 k-steps per iteration, optional commit per iteration, optional writer warps hammering
+// shared memory with 16-byte stores, optional unaligned A view.
+__global__ void __launch_bounds__(576, 1) kc_mma_rate2_kernel(int N, int mn_major, int iters, int nsub, int commit_each, int writers,
+                                                               int a_shift_rows, float* out) {
   extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, dummy[8];
   __shared__ uint32_t tmem_ptr;
-  for (int i = threadIdx.x; i < (96 * 1024) / 4; i += 32) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-  tmem_alloc(&tmem_ptr, 256);
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1000000); done = 0; fence_barrier_init(); }
+  if (warp == 17) tmem_alloc(&tmem_ptr, 512);
   fence_proxy_async_smem();
   tc_fence_before();
-  __syncwarp();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tb = tmem_ptr;
-  const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
-  const uint32_t au = smem_u32(sm) >> 4, bu = (smem_u32(sm) + 48 * 1024) >> 4;
-  // K-major: planes [k-core][row]: LBO = plane pitch, SBO = 128 B; step = 2 planes.  MN-major: planes [mn-group][k row]:
-  // SBO = plane pitch, LBO = 128 B; step = 16 rows.
-  const uint32_t a_pitch = mn_major ? 1168u : 6544u, b_pitch = mn_major ? 1040u : (uint32_t)N * 16u;
-  const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
-  const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
-  const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
-  long long t0 = clock64();
-  for (int it = 0; it < iters; ++it) {
-    if (elect_one_sync()) {
+  if (warp == 17) {
+    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
+    const uint32_t au = (smem_u32(sm) >> 4) + (uint32_t)a_shift_rows, bu = (smem_u32(sm) + 100 * 1024) >> 4;
+    const uint32_t a_pitch = mn_major ? 1168u : 15456u, b_pitch = mn_major ? 1040u : (uint32_t)N * 16u;
+    const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
+    const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
+    const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one_sync()) {
+        for (int s = 0; s < nsub; ++s) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + ks * a_step));
-        const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + ks * b_step));
-        tc_mma_bf16(tb, ad, bd, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + s * 128 + ks * a_step));
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + ks * b_step));
+            tc_mma_bf16(tb + s * N, ad, bd, idesc, 1u);
+          }
+        }
+        if (commit_each) tc_commit(&dummy[it & 7]);
       }
+      __syncwarp();
     }
+    if (elect_one_sync()) tc_commit(&bar);
     __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 17 * 32) { out[0] = (float)(t1 - t0) / (float)(iters * nsub * 2); done = 1; }
+  } else if (warp < writers) {
+    uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + threadIdx.x;
+    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+    while (!done) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[(k * 512) & 1023] = v;
+      v.x += 1;
+    }
   }
-  if (elect_one_sync()) tc_commit(&bar);
-  __syncwarp();
-  mbar_wait(&bar, 0);
-  long long t1 = clock64();
-  if (threadIdx.x == 0) out[0] = (float)(t1 - t0) / (float)(iters * 4);
   tc_fence_before();
-  __syncwarp();
-  tmem_dealloc(tb, 256);
+  __syncthreads();
+  if (warp == 17) tmem_dealloc(tb, 512);
 }
 
-extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, float* cycles) {
+extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, int nsub, int commit_each, int writers, int a_shift_rows, float* cycles) {
   float* dev = nullptr;
   KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  kc_mma_rate2_kernel<<<1, 32, 96 * 1024>>>(N, mn_major, iters, dev);
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  kc_mma_rate2_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, nsub, commit_each, writers, a_shift_rows, dev);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(dev);

@@ -1,15 +1,16 @@
-"""Raw tcgen05.mma execution rate, K-major vs MN-major no-swizzle operands (debug micro-benchmark)."""
+"""tcgen05.mma execution rate under conv-kernel-like conditions (debug micro-benchmark)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import kanconv_b200 as K
 lib = K._lib.load()
 f = lib.kc_debug_mma_rate2
-f.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_float)]
+f.argtypes = [ctypes.c_int] * 7 + [ctypes.POINTER(ctypes.c_float)]
 torch.zeros(1, device="cuda")
-def run(N, mn, iters=256):
+def run(N, mn=0, nsub=1, commit=0, writers=0, shift=0, iters=256):
     c = ctypes.c_float()
-    assert f(N, mn, iters, ctypes.byref(c)) == 0, lib.kc_last_error()
+    assert f(N, mn, iters, nsub, commit, writers, shift, ctypes.byref(c)) == 0, lib.kc_last_error()
     return round(c.value, 1)
-for N in (64, 128, 144, 160, 256):
-    print(f"N={N}: K-major {run(N, 0)} cycles/MMA | MN-major {run(N, 1)} cycles/MMA   (floor 128*N/256 = {N // 2})")
+for N, ns in ((64, 4), (128, 4), (144, 3), (256, 2)):
+    print(f"N={N} (floor {N//2}): 1 acc {run(N)} | {ns} acc {run(N, 0, ns)} | +commit/step {run(N, 0, ns, 1)} | +shift 1 row {run(N, 0, ns, 1, 0, 1)}"
+          f" | +4 writer warps {run(N, 0, ns, 1, 4, 1)} | +16 writer warps {run(N, 0, ns, 1, 16, 1)} | MN-major {run(N, 1, min(ns, 3), 1)}")
