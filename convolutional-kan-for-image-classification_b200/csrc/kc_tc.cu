@@ -144,22 +144,57 @@ __device__ __noinline__ uint2 basis4(const KcBasisCtx& B, float x) {
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
 
-// d/dx of the uniform cubic B-spline weights dotted with 8 incoming gradients g[j] (closed form, Appendix A.2)
-__device__ __forceinline__ float cubic8_dot_grad(float x, float t0, float inv_h, int nintervals, const float* gsp) {
+// d/dx of the uniform cubic B-spline weights dotted with the 8 incoming gradients r[0..7] (closed form, Appendix A.2).
+// Same pack-and-shift trick as the forward producer: the 4 non-zero derivative weights are packed as bf16 into 64 bits,
+// moved to their slots j = i0-3..i0 with clamped shifts and unpacked with one shift/mask each (~40 instructions instead
+// of a select chain per j; the bf16 rounding of the weights is far inside the BF16 tolerance of this path).
+__device__ __forceinline__ float cubic8_dot_grad(float x, float t0, float inv_h, int nintervals, const uint32_t* r) {
   const float u = (x - t0) * inv_h;
-  if (!(u >= 0.0f) || !(u < (float)nintervals)) return 0.0f;
+  const bool ok = (u >= 0.0f) && (u < (float)nintervals);
   const float fi = floorf(u);
   const float f = u - fi, omf = 1.0f - f;
-  const int i0 = (int)fi;
+  const int i0 = min(max((int)fi, 0), 15);
   const float d0 = -0.5f * omf * omf, d1 = fmaf(1.5f * f, f, -2.0f * f), d2 = fmaf(fmaf(-1.5f, f, 1.0f), f, 0.5f), d3 = 0.5f * f * f;
+  unsigned long long v = (unsigned long long)pack_bf16(d0, d1) | ((unsigned long long)pack_bf16(d2, d3) << 32);
+  v = ok ? v : 0ull;
+  const int sh = 16 * (i0 - 3);
+  const unsigned long long lo = shl64(v, sh) | shr64(v, -sh);
+  const unsigned long long hi = shr64(v, 64 - sh) | shl64(v, sh - 64);
+  const uint32_t w[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
   float acc = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int r = j - (i0 - 3);
-    const float w = (r == 0) ? d0 : (r == 1) ? d1 : (r == 2) ? d2 : (r == 3) ? d3 : 0.0f;
-    acc = fmaf(gsp[j], w, acc);
+  for (int p = 0; p < 4; ++p) {
+    acc = fmaf(__uint_as_float(r[2 * p]), __uint_as_float(w[p] << 16), acc);
+    acc = fmaf(__uint_as_float(r[2 * p + 1]), __uint_as_float(w[p] & 0xffff0000u), acc);
   }
   return acc * inv_h;
+}
+
+// base-activation derivative with fast intrinsics (tensor-core path only; the FP32 path uses kc_act_grad)
+__device__ __forceinline__ float act_grad_fast(int kind, float x) {
+  if (kind == KC_ACT_SILU) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+    return s * fmaf(x, 1.0f - s, 1.0f);
+  }
+  if (kind == KC_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    return fmaf(x, 0.39894228040143268f * __expf(-0.5f * x * x), cdf);
+  }
+  return 1.0f;
+}
+
+// Generic (any basis family) contraction of the incoming gradients r[0..nb) with d(basis)/dx; optionally accumulates the
+// GRAM d/d(beta_weights) partials.  Out of line: rare path, keeps the dgrad epilogue loop compact.
+__device__ __noinline__ float dgrad_generic(const KcBasisCtx& B, float x, const uint32_t* r, float* dbl) {
+  float phi[KC_MAX_BASIS], dphi[KC_MAX_BASIS], gg[KC_MAX_BASIS];
+  kc_eval_basis(B, x, phi, dphi, 1);
+  float gs = 0.0f;
+  for (int j = 0; j < KC_MAX_BASIS; ++j) {
+    gg[j] = j < B.nb ? __uint_as_float(r[j]) : 0.0f;
+    if (j < B.nb) gs = fmaf(gg[j], dphi[j], gs);
+  }
+  if (dbl != nullptr) kc_gram_dbeta(B, x, gg, 1, dbl);
+  return gs;
 }
 
 __device__ __forceinline__ int chunk_cols(const TcGeom& g, int q) {
@@ -267,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
         for (int cl = 0; cl < 2; ++cl)
           xv[k][cl] = (offs[k] >= 0 && c0 + cl < cin) ? __ldg(xc + (long long)cl * HW + offs[k]) : 0.0f;
     };
-    Tracer trp(tp == 0 ? 0 : 3, tp == 0 || tp == 300);
+    Tracer trp(0, tp == 0);
     if (nb == 8 && g.nsc > 0) fetch8(0, xnext);
     if (MODE == kModeDgrad) {
       // copy chunks: k-core = 8 consecutive output channels of one flat position = one 16-byte vector of the plane-major
@@ -504,75 +539,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     // Columns of this N tile are (channel cl, j) with j < nb the basis gradients and j == nb the base-branch gradient;
     // dPhi never leaves the SM (the reference's autograd materialises it, ~50 elementwise backward launches).
     // All 16 producer warps take part: warp w reads TMEM lanes 32*(w%4).. (its hardware quarter) and handles the four
-    // channels 4*(w/4) .. +3; the x values of all sub-tiles are fetched BEFORE waiting for the accumulator.
+    // channels 4*(w/4) .. +3.  The loop over sub-tiles is a real loop with a compact body (the rare generic-basis and
+    // GRAM paths are out of line): a fully unrolled version was instruction-cache bound (40k cycles per CTA).
     const int nb = d.nb, wb = nb + (has_base ? 1 : 0);
     const bool alias = a.dx_base == a.dx_basis, same_x = a.x_base == a.x_basis;
-    const int quarter = warp & 3, cgrp = warp >> 2;
-    long long offv[4];
-    float xs[4][4], xb[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      offv[i] = -1;
-      const long long q = m0 + i * kTileM + quarter * 32 + lane;
-      if (i < g.nsub && q < g.L) {
-        int n = (int)(q / g.IMG);
-        int rem = (int)(q - (long long)n * g.IMG);
-        int y = rem / g.P, x = rem - y * g.P;
-        if (y < d.h && x < d.w) offv[i] = (long long)n * d.x_batch_stride + y * d.w + x;
-      }
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int c = nt * 16 + cgrp * 4 + c4;
-        const bool ok = offv[i] >= 0 && c < d.cin;
-        xs[i][c4] = ok ? __ldg(a.x_basis + offv[i] + (long long)c * HW) : 0.0f;
-        xb[i][c4] = (ok && has_base && !same_x) ? __ldg(a.x_base + offv[i] + (long long)c * HW) : xs[i][c4];
-      }
-    }
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
     const bool gram = d.basis == KC_BASIS_GRAM && a.dbeta != nullptr;
+    const int quarter = warp & 3, cgrp = warp >> 2;
+    const int c0 = nt * 16 + cgrp * 4;
+    Tracer tre(3, threadIdx.x == 0);
+    tre.stamp();                                     // epilogue entered (producer loop done)
     float dbl[KC_MAX_BASIS];
 #pragma unroll
     for (int j = 0; j < KC_MAX_BASIS; ++j) dbl[j] = 0.0f;
+    bool waited = false;
+#pragma unroll 1
+    for (int i = 0; i < g.nsub; ++i) {
+      const long long q = m0 + i * kTileM + quarter * 32 + lane;
+      long long off = -1;
+      if (q < g.L) {
+        int n = (int)(q / g.IMG);
+        int rem = (int)(q - (long long)n * g.IMG);
+        int y = rem / g.P, x = rem - y * g.P;
+        if (y < d.h && x < d.w) off = (long long)n * d.x_batch_stride + y * d.w + x;
+      }
+      float xs[4], xb[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i >= g.nsub) break;
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const bool ok = off >= 0 && c0 + c4 < d.cin;
+        xs[c4] = ok ? ldg_early(a.x_basis + off + (long long)(c0 + c4) * HW) : 0.0f;
+        xb[c4] = (ok && has_base && !same_x) ? ldg_early(a.x_base + off + (long long)(c0 + c4) * HW) : xs[c4];
+      }
+      if (!waited) {                                 // the x loads of the first sub-tile fly while the MMAs drain
+        tre.stamp();
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        tre.stamp();                                 // accumulator ready
+        waited = true;
+      }
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * g.ntile);
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
-        const int cl = cgrp * 4 + c4, c = nt * 16 + cl;
-        if (c >= d.cin) break;
+        const int c = c0 + c4;
+        if (c >= d.cin) break;                       // warp-uniform
         uint32_t r[16];
-        tmem_ld16(trow + (uint32_t)(cl * wb), r);
+        tmem_ld16(trow + (uint32_t)((cgrp * 4 + c4) * wb), r);
         tmem_ld_wait();
-        if (offv[i] >= 0) {
-          const long long o = offv[i] + (long long)c * HW;
-          float gs = 0.0f;
-          if (g.fast_cubic) {
-            float gg[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gg[j] = __uint_as_float(r[j]);
-            gs = cubic8_dot_grad(xs[i][c4], g.t0, g.inv_h, B->nparams - 1, gg);
-          } else {
-            float phi[KC_MAX_BASIS], dphi[KC_MAX_BASIS];
-            kc_eval_basis(*B, xs[i][c4], phi, dphi, 1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nb) gs = fmaf(__uint_as_float(r[j]), dphi[j], gs);
-            if (gram) {       // d/d beta_weights through the Gram recurrence (gram_kan_layers.py:150-170)
-              float gg[KC_MAX_BASIS];
-#pragma unroll
-              for (int j = 0; j < KC_MAX_BASIS; ++j) gg[j] = __uint_as_float(r[j]);
-              kc_gram_dbeta(*B, xs[i][c4], gg, 1, dbl);
-            }
-          }
+        if (off >= 0) {
+          const long long o = off + (long long)c * HW;
+          float gs;
+          if (g.fast_cubic) gs = cubic8_dot_grad(xs[c4], g.t0, g.inv_h, B->nparams - 1, r);
+          else gs = dgrad_generic(*B, xs[c4], r, gram ? dbl : nullptr);
           float gb = 0.0f;
           if (has_base) {
-            float ga = 0.0f;
+            float ga = __uint_as_float(r[8]);          // nb == 8 (the common case); other widths: pick column nb
+            if (nb != 8) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j == nb) ga = __uint_as_float(r[j]);
-            gb = ga * kc_act_grad(d.act, xb[i][c4]);
+              for (int j = 0; j < 8; ++j)
+                if (j == nb) ga = __uint_as_float(r[j]);
+            }
+            gb = ga * act_grad_fast(d.act, xb[c4]);
           }
           if (alias) {
             a.dx_basis[o] = gs + gb;
@@ -583,6 +608,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
         }
       }
     }
+    tre.stamp();                                     // dx written
     if (gram) {
       for (int nn = 1; nn <= nb - 2; ++nn) {
         float v = 0.0f;

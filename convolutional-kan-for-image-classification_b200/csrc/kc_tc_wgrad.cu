@@ -127,37 +127,55 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
   const kc_desc& d = a.d;
   const WgGeom& g = a.g;
   kc_load_basis_ctx(&Bs, d, a.beta);
+  // one thread = one flat position of one chunk: the position is decoded once, then the chunk's 16 planes are produced
   const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
-  const int gp = blockIdx.y, chunk = gp >> 4, pl = gp & 15;
+  const int chunk = blockIdx.y;
   if (q >= g.L) return;
   const int HW = d.h * d.w, nb = d.nb > 4 ? 8 : 4;      // padded basis width
   const int n = (int)(q / g.IMG);
   const int rem = (int)(q - (long long)n * g.IMG);
   const int y = rem / g.P, x = rem - y * g.P;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (y < d.h && x < d.w) {
-    const long long off = (long long)n * d.x_batch_stride + y * d.w + x;
-    if (chunk >= g.nsc) {
-      const int c0 = (chunk - g.nsc) * 128 + pl * 8;
+  const bool inside = y < d.h && x < d.w;
+  const long long off = inside ? (long long)n * d.x_batch_stride + y * d.w + x : 0;
+  unsigned char* dst = out + ((long long)chunk * 16 * g.L + q) * 16;
+  const long long pstride = g.L * 16;
+  if (chunk >= g.nsc) {
+    const int cb = (chunk - g.nsc) * 128;
+#pragma unroll 4
+    for (int pl = 0; pl < 16; ++pl) {
       float f[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = (c0 + i < d.cin) ? kc_act(d.act, __ldg(a.x_base + off + (long long)(c0 + i) * HW)) : 0.0f;
-      v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-    } else if (nb == 8) {
-      const int c = chunk * g.cps + pl;
-      if (c < d.cin) {
-        const float xv = __ldg(a.x_basis + off + (long long)c * HW);
-        v = g.fast_cubic ? cubic8w(xv, g.t0, g.inv_h, Bs.nparams - 1, true) : basis8w_generic(Bs, xv);
+      for (int i = 0; i < 8; ++i) {
+        const int c = cb + pl * 8 + i;
+        f[i] = (inside && c < d.cin) ? kc_act(d.act, __ldg(a.x_base + off + (long long)c * HW)) : 0.0f;
       }
-    } else {
+      *reinterpret_cast<uint4*>(dst + pl * pstride) =
+          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+  } else if (nb == 8) {
+    float xv[16];
+#pragma unroll
+    for (int pl = 0; pl < 16; ++pl) {
+      const int c = chunk * g.cps + pl;
+      xv[pl] = (inside && c < d.cin) ? __ldg(a.x_basis + off + (long long)c * HW) : 0.0f;
+    }
+#pragma unroll
+    for (int pl = 0; pl < 16; ++pl) {
+      const bool ok = inside && chunk * g.cps + pl < d.cin;
+      uint4 v;
+      if (g.fast_cubic) v = cubic8w(xv[pl], g.t0, g.inv_h, Bs.nparams - 1, ok);
+      else v = ok ? basis8w_generic(Bs, xv[pl]) : make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(dst + pl * pstride) = v;
+    }
+  } else {
+    for (int pl = 0; pl < 16; ++pl) {
       const int c = chunk * g.cps + pl * 2;
       uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-      if (c < d.cin) lo = basis4w(Bs, __ldg(a.x_basis + off + (long long)c * HW));
-      if (c + 1 < d.cin) hi = basis4w(Bs, __ldg(a.x_basis + off + (long long)(c + 1) * HW));
-      v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      if (inside && c < d.cin) lo = basis4w(Bs, __ldg(a.x_basis + off + (long long)c * HW));
+      if (inside && c + 1 < d.cin) hi = basis4w(Bs, __ldg(a.x_basis + off + (long long)(c + 1) * HW));
+      *reinterpret_cast<uint4*>(dst + pl * pstride) = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
   }
-  *reinterpret_cast<uint4*>(out + ((long long)gp * g.L + q) * 16) = v;
 }
 
 // Producer role of the wgrad kernel (512 threads): pure 16-byte cp.async copies of the Phi planes (A, with the filter-row
@@ -473,7 +491,7 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   unsigned char* phi = (unsigned char*)workspace + g.ws_bytes;
   a.phi = phi;
   {
-    dim3 pgrid((unsigned)((g.L + 255) / 256), (unsigned)(g.nchunks * 16));
+    dim3 pgrid((unsigned)((g.L + 255) / 256), (unsigned)g.nchunks);
     kc_phi_flat_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a, phi);
     KC_LAUNCH_CHECK("kc_phi_flat_kernel");
   }

@@ -133,6 +133,14 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
 }
 
+// Read-only global load that the compiler may not sink to its first use (volatile asm keeps the issue point): used where a
+// batch of independent loads must be in flight before a long wait.
+__device__ __forceinline__ float ldg_early(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE, sm_100 version field = 1 (cute::UMMA::SmemDescriptor bit layout).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
