@@ -3,7 +3,7 @@
 //   dW[cout][tap][c, j] = sum over flat output positions m of  dz[m][cout] * Phi_j(x[m + off(tap)][c])      (j = nb: base act)
 //
 // GEMM view per CTA: D[M = 128 expanded input rows (16 channels x 8 basis, or 128 base channels)][N = cout tile] for the
-// kw taps of ONE filter row r, reduced over a range of 64-position blocks (split-K).  Both operands are "MN-major"
+// kw taps of ONE filter row r, reduced over a range of 128-position blocks (split-K).  Both operands are "MN-major"
 // no-swizzle UMMA layouts whose K dimension (positions) runs along 16-byte rows:
 //   A = Phi  planes [channel (8 j) | 8-channel group][row = position + tap shift][8 x bf16]   - evaluated on the fly
 //   B = dz   planes [8 couts][row = position][8 x bf16]                                        - 16-byte copies of the
@@ -24,7 +24,6 @@ using namespace kc;
 constexpr int kThreadsW = 544;       // warps 0-15 producers / epilogue, 16 MMA issuer (highest warp id)
 constexpr int kProdW = 512;
 constexpr int kMmaWarpW = 16;
-constexpr int kKS = 64;              // positions per pipeline stage (4 MMA k-steps)
 constexpr int kMaxStagesW = 6;
 constexpr size_t kSmemLimitW = 227 * 1024;
 
@@ -39,6 +38,8 @@ struct WgGeom {
   int arows, aplane_bytes;      // Phi rows per stage (kKS + kw - 1, padded), plane pitch
   int bplanes, bplane_bytes;
   int stages, stage_bytes, a_bytes;
+  int ks;                       // positions per pipeline stage (64 or 128)
+  int prefetch;                 // cp.async stages in flight per producer thread
   int tmem_cols;
   long long nblk;               // 64-position blocks in total
   int nsplit;
@@ -182,34 +183,37 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
 // shift) and the dz planes (B) straight into the stage; rows are the fastest index so global reads are contiguous.
 // kPrefetchW stages are kept in flight per thread (commit_group / wait_group), then the landed stage is fenced for the
 // tensor-core proxy and published on its `full` barrier.
-constexpr int kPrefetchW = 3;
+constexpr int kPrefetchW = 3;          // max stages in flight per producer thread
 
+template <int KS>
 __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int r, int chunk,
                                            int ct, long long blk0, int nblocks) {
+  constexpr int kItems = KS == 64 ? 3 : 5;       // 16-byte vectors per producer thread and operand per stage
   const kc_desc& d = a.d;
   const WgGeom& g = a.g;
   const int tid = threadIdx.x;
-  const int nAitems = g.arows * 16, nBitems = kKS * g.bplanes;
-  const long long qoff = blk0 * kKS + (long long)(r - d.pad_h) * g.P - d.pad_w;
-  int arow[3], brow[3];
-  uint32_t adst[3], bdst[3];                      // byte offsets inside a stage, 0xffffffff = no item
-  const unsigned char* aplane[3];
-  const unsigned char* bplane[3];
+  const int nAitems = g.arows * 16, nBitems = KS * g.bplanes;
+  const long long qoff = blk0 * KS + (long long)(r - d.pad_h) * g.P - d.pad_w;
+  int arow[kItems], brow[kItems];
+  uint32_t adst[kItems], bdst[kItems];                      // byte offsets inside a stage, 0xffffffff = no item
+  const unsigned char* aplane[kItems];
+  const unsigned char* bplane[kItems];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const int it = tid + kProdW * k;
     arow[k] = it % g.arows;
     const int apl = it / g.arows;
     adst[k] = (it < nAitems) ? (uint32_t)(apl * g.aplane_bytes + arow[k] * 16) : 0xffffffffu;
     aplane[k] = a.phi + ((long long)(chunk * 16 + (it < nAitems ? apl : 0)) * g.L) * 16;
-    brow[k] = it % kKS;
-    const int bpl = it / kKS;
+    brow[k] = it % KS;
+    const int bpl = it / KS;
     const bool bok = it < nBitems && (ct * g.bplanes + bpl) * 8 < g.cq;
     bdst[k] = (it < nBitems) ? (uint32_t)(g.a_bytes + bpl * g.bplane_bytes + brow[k] * 16) : 0xffffffffu;
     bplane[k] = bok ? a.dzf + ((long long)(ct * g.bplanes + bpl) * g.L) * 16 : nullptr;
   }
   TracerW trp(0, tid == 0);
-  for (int it = 0; it < nblocks + kPrefetchW; ++it) {
+  const int depth = g.prefetch;
+  for (int it = 0; it < nblocks + depth; ++it) {
     if (it < nblocks) {
       const int st = it % g.stages;
       const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
@@ -218,43 +222,44 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
       trp.stamp();
       unsigned char* stage = smem + (size_t)st * g.stage_bytes;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < kItems; ++k) {
         if (adst[k] != 0xffffffffu) {
-          const long long q = qoff + (long long)it * kKS + arow[k];
+          const long long q = qoff + (long long)it * KS + arow[k];
           const bool ok = q >= 0 && q < g.L;
           cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
         }
         if (bdst[k] != 0xffffffffu) {
-          const long long m = (blk0 + it) * kKS + brow[k];
+          const long long m = (blk0 + it) * KS + brow[k];
           const bool ok = bplane[k] != nullptr && m < g.L;
           cp_async16(stage + bdst[k], ok ? bplane[k] + m * 16 : a.dzf, ok ? 16u : 0u);
         }
       }
     }
     cp_async_commit();
-    if (it >= kPrefetchW) {
-      cp_async_wait<kPrefetchW>();                 // every group older than the newest kPrefetchW has landed
+    if (it >= depth) {                             // every group older than the newest `depth` has landed
+      if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
       fence_proxy_async_smem();
-      mbar_arrive(&full[(it - kPrefetchW) % g.stages]);
+      mbar_arrive(&full[(it - depth) % g.stages]);
     }
   }
 }
 
-// Straight-line issue of the KW x 4 MMAs of one stage (tap s reads the Phi planes from row s; k-step ks advances both
+// Straight-line issue of the KW x (kKS/16) MMAs of one stage (tap s reads the Phi planes from row s; k-step ks advances both
 // operands by 16 rows).  Descriptor low words differ by small constants only.
-template <int KW>
+template <int KW, int KS>
 __device__ __forceinline__ void wg_issue(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
                                          uint32_t b_hi, uint32_t idesc, uint32_t first) {
 #pragma unroll
   for (int s = 0; s < KW; ++s) {
     const uint32_t td = tmem_base + (uint32_t)s * ntile;
 #pragma unroll
-    for (int ks = 0; ks < kKS / 16; ++ks)
+    for (int ks = 0; ks < KS / 16; ++ks)
       tc_mma_bf16(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
                   ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
   }
 }
 
+template <int KS>
 __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
 
   if (warp < 16) {
     // ============================ producers: Phi (A) evaluated on the fly, dz (B) copied ===========================
-    wg_produce(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
+    wg_produce<KS>(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
   }
   if (warp == kMmaWarpW) {
     // ============================ MMA issuer (whole warp uniform, one elected lane issues) ==========================
@@ -312,13 +317,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
       const uint32_t first = bi != 0 ? 1u : 0u;
       if (elect_one_sync()) {
         const uint32_t a_lo = lo_c | au, b_lo = lo_c | bu;
-        if (kw == 3) wg_issue<3>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
-        else if (kw == 1) wg_issue<1>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        if (kw == 3) wg_issue<3, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else if (kw == 1) wg_issue<1, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
         else {
           for (int s = 0; s < kw; ++s) {
             const uint32_t td = tmem_base + (uint32_t)(s * ntile);
 #pragma unroll
-            for (int ks = 0; ks < kKS / 16; ++ks)
+            for (int ks = 0; ks < KS / 16; ++ks)
               tc_mma_bf16(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
                           ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
           }
@@ -432,24 +437,28 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->ntile = round_up_w((g->cq + want - 1) / want, 16);
   g->n_ct = (g->cq + g->ntile - 1) / g->ntile;
   g->units = g->n_ct * g->nchunks * d->kh;
-  g->arows = round_up_w(kKS + d->kw - 1, 8);
+  g->ks = g->ntile <= 64 ? 128 : 64;     // small cout tiles: more MMAs per barrier round
+  g->arows = round_up_w(g->ks + d->kw - 1, 8);
   g->aplane_bytes = g->arows * 16 + 16;
   g->a_bytes = 16 * g->aplane_bytes;
   g->bplanes = g->ntile / 8;
-  g->bplane_bytes = kKS * 16 + 16;
+  g->bplane_bytes = g->ks * 16 + 16;
   g->stage_bytes = round_up_w(g->a_bytes + g->bplanes * g->bplane_bytes, 128);
-  if (g->arows * 16 > 3 * kProdW || kKS * g->bplanes > 3 * kProdW) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage too large for the producer mapping");
-  if (g->arows > 80) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: kernel width too large");
-  size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 16 + 2 * 80 * sizeof(int) + 128;
+  const int items = g->ks == 64 ? 3 : 5;
+  if (g->arows * 16 > items * kProdW || g->ks * g->bplanes > items * kProdW) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage too large for the producer mapping");
+  size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 128;
   g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
   if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
-  if (g->stages < kPrefetchW + 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
+  if (g->stages < 2) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
+  g->prefetch = g->stages - 2 < kPrefetchW ? g->stages - 2 : kPrefetchW;      // keep two slack stages for the MMA side
+  if (g->prefetch < 1) g->prefetch = 1;
   g->smem_bytes = fixed + (size_t)g->stages * g->stage_bytes;
   g->tmem_cols = 32;
   while (g->tmem_cols < d->kw * g->ntile) g->tmem_cols *= 2;
-  g->nblk = (g->L + kKS - 1) / kKS;
+  g->nblk = (g->L + g->ks - 1) / g->ks;
   long long want_split = (3LL * 148 + g->units - 1) / g->units;
-  long long max_split = g->nblk / 16 > 0 ? g->nblk / 16 : 1;       // at least 16 blocks (1024 positions) per CTA
+  const long long minblk = 1024 / g->ks;                            // at least 1024 positions per CTA
+  long long max_split = g->nblk / minblk > 0 ? g->nblk / minblk : 1;
   long long ns = want_split < 1 ? 1 : want_split;
   if (ns > max_split) ns = max_split;
   g->blk_per_split = (g->nblk + ns - 1) / ns;
@@ -495,9 +504,14 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
     kc_phi_flat_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a, phi);
     KC_LAUNCH_CHECK("kc_phi_flat_kernel");
   }
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
-  kc_wgrad_tc_kernel<<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  if (g.ks == 128) {
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kc_wgrad_tc_kernel<128><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  } else {
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kc_wgrad_tc_kernel<64><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  }
   KC_LAUNCH_CHECK("kc_wgrad_tc_kernel");
   long long total = (long long)g.units * d->kw * 128 * g.ntile;
   int blocks = (int)((total + 255) / 256);
