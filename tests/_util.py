@@ -15,8 +15,13 @@ ORACLE_CTORS = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram
                 "fast": O.OracleFastKANConv2D}
 
 
+MODEL_FIXTURES = {"mbv2_fastkan_forward"}      # whole-model fixtures (make_model_golden.py): a different record layout
+
+
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    """Layer fixtures written by tests/golden/make_golden.py."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return [n for n in names if n not in MODEL_FIXTURES]
 
 
 class Golden:
