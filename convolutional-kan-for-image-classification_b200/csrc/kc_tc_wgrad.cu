@@ -213,33 +213,47 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
   }
   TracerW trp(0, tid == 0);
   const int depth = g.prefetch;
+  int st = 0, st_done = 0;                        // ring slot being filled / being published (no divisions in the loop)
+  uint32_t ph = 1;
   for (int it = 0; it < nblocks + depth; ++it) {
     if (it < nblocks) {
-      const int st = it % g.stages;
-      const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
       trp.stamp();
-      mbar_wait(&empty[st], ph ^ 1);
+      mbar_wait(&empty[st], ph);
       trp.stamp();
       unsigned char* stage = smem + (size_t)st * g.stage_bytes;
+      const long long q0 = qoff + (long long)it * KS, m0 = (blk0 + it) * KS;
+      if (q0 >= 0 && q0 + g.arows <= g.L && m0 + KS <= g.L) {     // interior block: no per-row range checks
 #pragma unroll
-      for (int k = 0; k < kItems; ++k) {
-        if (adst[k] != 0xffffffffu) {
-          const long long q = qoff + (long long)it * KS + arow[k];
-          const bool ok = q >= 0 && q < g.L;
-          cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
+        for (int k = 0; k < kItems; ++k) {
+          if (adst[k] != 0xffffffffu) cp_async16(stage + adst[k], aplane[k] + (q0 + arow[k]) * 16, 16u);
+          if (bdst[k] != 0xffffffffu) {
+            const bool ok = bplane[k] != nullptr;
+            cp_async16(stage + bdst[k], ok ? bplane[k] + (m0 + brow[k]) * 16 : a.dzf, ok ? 16u : 0u);
+          }
         }
-        if (bdst[k] != 0xffffffffu) {
-          const long long m = (blk0 + it) * KS + brow[k];
-          const bool ok = bplane[k] != nullptr && m < g.L;
-          cp_async16(stage + bdst[k], ok ? bplane[k] + m * 16 : a.dzf, ok ? 16u : 0u);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+          if (adst[k] != 0xffffffffu) {
+            const long long q = q0 + arow[k];
+            const bool ok = q >= 0 && q < g.L;
+            cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
+          }
+          if (bdst[k] != 0xffffffffu) {
+            const long long m = m0 + brow[k];
+            const bool ok = bplane[k] != nullptr && m < g.L;
+            cp_async16(stage + bdst[k], ok ? bplane[k] + m * 16 : a.dzf, ok ? 16u : 0u);
+          }
         }
       }
+      if (++st == g.stages) { st = 0; ph ^= 1; }
     }
     cp_async_commit();
     if (it >= depth) {                             // every group older than the newest `depth` has landed
       if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
       fence_proxy_async_smem();
-      mbar_arrive(&full[(it - depth) % g.stages]);
+      mbar_arrive(&full[st_done]);
+      if (++st_done == g.stages) st_done = 0;
     }
   }
 }
