@@ -43,9 +43,9 @@ _SIGNATURES = {
     "kc_tc_bytes": (c_sz, [_P(KcDesc), ctypes.c_int]),
     "kc_tc_pack_weights": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 5),
     "kc_tc_dz_flat": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 3),
-    "kc_conv_fwd_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 6),
+    "kc_conv_fwd_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 7),
     "kc_conv_dgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 10),
-    "kc_conv_wgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 8),
+    "kc_conv_wgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 9),
     "kc_tc_selftest": (ctypes.c_int, [ctypes.c_int, _P(ctypes.c_float), c_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -23,7 +23,8 @@
 #include "kc_common.cuh"
 #include "kc_umma.cuh"
 
-size_t kc_tc_wgrad_ws_bytes(const kc_desc* d);   // kc_tc_wgrad.cu
+size_t kc_tc_wgrad_ws_bytes(const kc_desc* d, int which);                                              // kc_tc_wgrad.cu
+int kc_tc_wgrad_phi_layout(const kc_desc* d, long long* L, int* spline_planes, int* base_planes);    // kc_tc_wgrad.cu
 
 namespace {
 
@@ -64,6 +65,8 @@ struct TcFwdArgs {
   const unsigned char* wp;
   const float* beta;
   float* z;
+  unsigned char* phi_out;       // optional: basis rows saved for the weight gradient, plane-major [plane][L][8] bf16
+  int phi_base_plane0;          // index of the first base-activation plane in phi_out
   // dgrad mode only
   const unsigned char* dzf;     // bf16 plane-major [cq/8][L][8], zero at padding / invalid output positions
   int cq;                       // channels per flat row (cout rounded up to 16)
@@ -289,6 +292,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       }
       offs[k] = off;
     }
+    // Rows of the centre strip are this tile's own flat positions m0 .. m0+mcta-1: when phi_out is given, their basis rows
+    // are also written to global memory in the plane-major layout of the weight-gradient kernel (first cout tile only).
+    unsigned ownmask = 0u;
+    unsigned char* phi_row = nullptr;
+    const long long phi_ps = g.L * 16;                                // bytes between planes
+    if (MODE == kModeFwd && a.phi_out != nullptr && nt == 0) {
+      const int bc0 = r0 - (g.ph * g.SS + g.pw);
+#pragma unroll
+      for (int k = 0; k < kRB; ++k) {
+        const int bc = bc0 + k * kRowThreads;
+        if (offs[k] != -2 && bc >= 0 && bc < g.mcta && m0 + bc < g.L) ownmask |= 1u << k;
+      }
+      phi_row = a.phi_out + (m0 + bc0) * 16;
+    }
     const int plane_bytes = g.plane_bytes, cin = d.cin, nb = d.nb > 4 ? 8 : 4;   // padded basis width
     // x values of the NEXT spline chunk are fetched while the current one is evaluated (nb == 8 path):
     // this thread owns planes half*2 + {0,1} = channels q*4 + half*2 + {0,1}
@@ -356,6 +373,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
             const int pl = half * 2 + cl;
             uint4 v = basis8(*B, g, xv[k][cl], offs[k] >= 0 && q * 4 + pl < cin);
             if (offs[k] != -2) reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v;
+            if (MODE == kModeFwd && (ownmask >> k) & 1u)
+              *reinterpret_cast<uint4*>(phi_row + (long long)(q * kPL + pl) * phi_ps + k * (kRowThreads * 16)) = v;
           }
         }
       } else if (q < g.nsc) {   // nb == 4: two channels share one 16-byte k-core, 8 channels per chunk
@@ -381,7 +400,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
               if (c < cin) lo = basis4(*B, xv[k][2 * pp]);
               if (c + 1 < cin) hi = basis4(*B, xv[k][2 * pp + 1]);
             }
-            reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            const uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v;
+            if (MODE == kModeFwd && (ownmask >> k) & 1u)
+              *reinterpret_cast<uint4*>(phi_row + (long long)(q * kPL + pl) * phi_ps + k * (kRowThreads * 16)) = v;
           }
         }
       } else {                  // base-activation chunk: k-core = 8 consecutive channels of one position
@@ -407,8 +429,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
               float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = (offs[kk + k] >= 0 && grp * 8 + i < cin) ? kc_act(d.act, xv[k][i]) : 0.0f;
-              reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] =
-                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              const uint4 v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v;
+              if (MODE == kModeFwd && (ownmask >> (kk + k)) & 1u)
+                *reinterpret_cast<uint4*>(phi_row + (long long)(a.phi_base_plane0 + grp) * phi_ps + (kk + k) * (kRowThreads * 16)) = v;
             }
           }
         }
@@ -957,7 +981,9 @@ extern "C" size_t kc_tc_bytes(const kc_desc* d, int which) {
   if (tc_dgrad_geometry(d, &gd) != KC_OK) return 0;
   if (which == 1) return (size_t)gd.wimg_bytes_per_ntile * gd.n_ntiles;
   if (which == 2) return (size_t)gd.L * gd.Cp * 2;
-  if (which == 3) return kc_tc_wgrad_ws_bytes(d);
+  if (which == 3) return kc_tc_wgrad_ws_bytes(d, 0);
+  if (which == 4) return kc_tc_wgrad_ws_bytes(d, 1);
+  if (which == 5) return kc_tc_wgrad_ws_bytes(d, 2);
   return 0;
 }
 
@@ -1007,7 +1033,7 @@ extern "C" int kc_tc_dz_flat(const kc_desc* d, const float* dz, void* dz_flat, v
 }
 
 extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float* x_basis, const void* packed_fwd,
-                              const float* beta, float* z, void* stream) {
+                              const float* beta, float* z, void* phi_out, void* stream) {
   int rc = kc_validate_desc(d);
   if (rc != KC_OK) return rc;
   TcGeom g;
@@ -1020,6 +1046,21 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
   TcFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.wp = (const unsigned char*)packed_fwd; a.beta = beta; a.z = z;
+  if (phi_out != nullptr) {
+    long long Lw = 0;
+    int splanes = 0, bplanes = 0;
+    rc = kc_tc_wgrad_phi_layout(d, &Lw, &splanes, &bplanes);
+    if (rc != KC_OK) return rc;
+    if (Lw != g.L) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_fwd_tc: forward / wgrad flat lengths differ");
+    a.phi_out = (unsigned char*)phi_out;
+    a.phi_base_plane0 = splanes;
+    // planes the weight-gradient kernel reads but this kernel does not produce (channel padding): zero them
+    const int wrote_s = g.nsc * kPL, wrote_b = d->act != KC_ACT_NONE ? g.ngroups : 0;
+    if (splanes > wrote_s)
+      KC_CUDA_CHECK(cudaMemsetAsync(a.phi_out + (size_t)wrote_s * g.L * 16, 0, (size_t)(splanes - wrote_s) * g.L * 16, (cudaStream_t)stream));
+    if (bplanes > wrote_b)
+      KC_CUDA_CHECK(cudaMemsetAsync(a.phi_out + (size_t)(splanes + wrote_b) * g.L * 16, 0, (size_t)(bplanes - wrote_b) * g.L * 16, (cudaStream_t)stream));
+  }
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
   kc_tc_kernel<kModeFwd><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);

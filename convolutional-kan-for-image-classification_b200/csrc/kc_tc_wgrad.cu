@@ -491,14 +491,25 @@ extern "C" int kc_debug_trace_wgrad(void* device_buffer) {
   return KC_OK;
 }
 
-size_t kc_tc_wgrad_ws_bytes(const kc_desc* d) {
+// which: 0 = split-K workspace + transient basis buffer, 1 = saved basis rows (phi), 2 = split-K workspace only
+size_t kc_tc_wgrad_ws_bytes(const kc_desc* d, int which) {
   WgGeom g;
   if (wgrad_geometry(d, &g) != KC_OK) return 0;
-  return g.ws_bytes + g.phi_bytes;
+  return which == 0 ? g.ws_bytes + g.phi_bytes : which == 1 ? g.phi_bytes : g.ws_bytes;
+}
+
+// Plane counts of the phi layout (for the forward kernel that fills it): flat length, spline planes, base planes.
+int kc_tc_wgrad_phi_layout(const kc_desc* d, long long* L, int* spline_planes, int* base_planes) {
+  WgGeom g;
+  int rc = wgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  *L = g.L; *spline_planes = g.nsc * 16; *base_planes = g.nbc * 16;
+  return KC_OK;
 }
 
 extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base, const float* x_basis,
-                                const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream) {
+                                const float* beta, const void* phi_saved, float* dw_base, float* dw_basis, void* workspace,
+                                void* stream) {
   int rc = kc_validate_desc(d);
   if (rc != KC_OK) return rc;
   WgGeom g;
@@ -511,9 +522,11 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   memset(&a, 0, sizeof(a));
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.dzf = (const unsigned char*)dz_flat; a.beta = beta;
   a.ws = (float*)workspace;
-  unsigned char* phi = (unsigned char*)workspace + g.ws_bytes;
-  a.phi = phi;
-  {
+  if (phi_saved != nullptr) {
+    a.phi = (const unsigned char*)phi_saved;          // rows written by kc_conv_fwd_tc
+  } else {
+    unsigned char* phi = (unsigned char*)workspace + g.ws_bytes;
+    a.phi = phi;
     dim3 pgrid((unsigned)((g.L + 255) / 256), (unsigned)g.nchunks);
     kc_phi_flat_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a, phi);
     KC_LAUNCH_CHECK("kc_phi_flat_kernel");

@@ -21,6 +21,9 @@ import torch
 from . import _lib as L
 
 _TC_BACKWARD = os.environ.get("KANCONV_TC_BACKWARD", "1") != "0"   # debug switch: FP32 CUDA-core backward after a TC forward
+# KANCONV_SAVE_PHI=0: do not keep the bf16 basis rows between forward and backward (saves 18 B per input element per
+# layer of activation memory; the weight gradient then re-evaluates them in a pre-pass)
+_SAVE_PHI = os.environ.get("KANCONV_SAVE_PHI", "1") != "0"
 _PRECISION = "auto"      # "auto": tensor cores when the shape is supported, else CUDA-core FP32 | "bf16" | "fp32"
 
 
@@ -172,6 +175,9 @@ class _KanConvFn(torch.autograd.Function):
         z = torch.empty((n, og * G, ho, wo), device=xb.device, dtype=torch.float32)
         stream = _stream()
         used_tc = []
+        # basis rows saved for the weight gradient (the reference keeps the expanded basis alive for autograd, too)
+        want_phi = _SAVE_PHI and _TC_BACKWARD and any(ctx.needs_input_grad[5:])
+        phis = []
         for g in range(G):
             d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
             xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
@@ -184,12 +190,17 @@ class _KanConvFn(torch.autograd.Function):
                 packed = torch.empty(nbytes, device=xb.device, dtype=torch.uint8)
                 L.check(_timed("kc_pack_fwd_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
                     ctypes.byref(d), _ptr(wbg), _ptr(wsg), _ptr(packed), None, stream)), "kc_tc_pack_weights")
+                phi = None
+                if want_phi and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
+                    phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=xb.device, dtype=torch.uint8)
+                phis.append(phi)
                 L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
-                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), stream)), "kc_conv_fwd_tc")
+                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), _ptr(phi), stream)), "kc_conv_fwd_tc")
             else:
+                phis.append(None)
                 L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
                     ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream)), "kc_conv_fwd_f32")
-        ctx.spec, ctx.alias, ctx.precision, ctx.used_tc = spec, alias, precision, used_tc
+        ctx.spec, ctx.alias, ctx.precision, ctx.used_tc, ctx.phis = spec, alias, precision, used_tc, phis
         ctx.save_for_backward(xb, xs if not alias else None, beta, *weights)
         return z
 
@@ -252,10 +263,12 @@ class _KanConvFn(torch.autograd.Function):
                 dwb = torch.empty_like(wbg) if wbg is not None else None
                 dwsg = torch.empty_like(wsg)
                 if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
-                    ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 3), device=xb.device, dtype=torch.uint8)
+                    phi = ctx.phis[g]
+                    ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=xb.device, dtype=torch.uint8)
                     L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
-                        ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
-                        "kc_conv_wgrad_tc")
+                        ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(phi), _ptr(dwb), _ptr(dwsg), _ptr(ws),
+                        stream)), "kc_conv_wgrad_tc")
+                    ctx.phis[g] = None
                 else:
                     nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
                     ws = torch.empty(max(nbytes, 16), device=xb.device, dtype=torch.uint8)

@@ -131,7 +131,9 @@ int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, cons
  * ------------------------------------------------------------------------------------------------------- */
 int kc_tc_supported(const kc_desc* d);
 /* Bytes of the packed bf16 weight images of the forward (which=0) and dgrad (which=1) kernels, of the flat bf16
- * dz buffer that kc_tc_dz_flat fills (which=2), and of the wgrad split-K workspace (which=3). */
+ * dz buffer that kc_tc_dz_flat fills (which=2), of the wgrad workspace when the forward did not save its basis rows
+ * (which=3: split-K partial sums + a transient basis buffer), of the saved basis rows `phi` that kc_conv_fwd_tc can
+ * emit for kc_conv_wgrad_tc (which=4), and of the wgrad workspace when `phi` is supplied (which=5). */
 size_t kc_tc_bytes(const kc_desc* d, int which);
 /* dz (fp32 NCHW) -> bf16 "flat" layout [n*(h+pad_h)*(w+pad_w)][round_up(cout,16)], zeros at padding positions: the
  * operand format of the tensor-core dgrad / wgrad kernels (pass it as their `workspace` / `dz_flat`). */
@@ -140,14 +142,19 @@ int kc_tc_dz_flat(const kc_desc* d, const float* dz, void* dz_flat, void* stream
  * pointer may be NULL to skip that image. */
 int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const float* w_basis, void* packed_fwd,
                        void* packed_dgrad, void* stream);
+/* `phi_out` (NULL, or kc_tc_bytes(d, 4) bytes): the bf16 basis / base-activation rows the kernel evaluates anyway are
+ * also written in the plane-major layout the weight-gradient kernel consumes, so the backward pass does not have to
+ * re-evaluate them (the reference keeps the expanded basis tensor alive for autograd in the same way). */
 int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float* x_basis, const void* packed_fwd,
-                   const float* beta, float* z, void* stream);
+                   const float* beta, float* z, void* phi_out, void* stream);
 int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                      const void* packed_dgrad, const float* beta, float* dx_base, float* dx_basis, float* dbeta,
                      void* workspace, void* stream);
-/* `dz_flat` = buffer filled by kc_tc_dz_flat; `workspace` = kc_tc_bytes(d, 3) bytes of split-K partial sums. */
+/* `dz_flat` = buffer filled by kc_tc_dz_flat; `phi` = rows saved by kc_conv_fwd_tc, or NULL to re-evaluate them from x;
+ * `workspace` = kc_tc_bytes(d, phi ? 5 : 3) bytes. */
 int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base, const float* x_basis,
-                     const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream);
+                     const float* beta, const void* phi, float* dw_base, float* dw_basis, void* workspace,
+                     void* stream);
 
 /* Self-test of the tcgen05 shared-memory descriptor conventions this library relies on: runs a 128xNx64 bf16 GEMM
  * through the same UMMA helpers as the convolution kernels and returns the max abs error against a CUDA-core

@@ -8,10 +8,15 @@ topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 extra = sys.argv[3:]  # e.g. -k regex:wgrad
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+# one "Address,..." header per kernel in the report; KERNEL_INDEX env picks which (default 0)
+import os
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+which = int(os.environ.get("KERNEL_INDEX", "0"))
+hi = his[which]
+end = his[which + 1] if which + 1 < len(his) else len(rows)
 hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
 tot = sum(int(r[col["# Samples"]]) for r in data)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 agg = {s: sum(int(r[col[s]]) for r in data) for s in stalls}
