@@ -572,77 +572,140 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     const int c0 = nt * 16 + cgrp * 4;
     Tracer tre(3, threadIdx.x == 0);
     tre.stamp();                                     // epilogue entered (producer loop done)
-    float dbl[KC_MAX_BASIS];
+    if (g.fast_cubic && !gram && same_x) {
+      // ---- closed-form cubic path (nb == 8): everything stays in registers ----------------------------------------
+      // x of sub-tile i+1 is fetched while sub-tile i is evaluated, and the TMEM read of channel c+1 is issued before
+      // channel c is evaluated, so neither latency is exposed.
+      const int nint = B->nparams - 1, act = d.act;
+      const float t0 = g.t0, inv_h = g.inv_h;
+      const int nch = min(4, d.cin - c0);                             // warp-uniform, may be <= 0
+      const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgrp * 4 * wb);
+      const float* xch = a.x_basis + (long long)c0 * HW;
+      float* dxo = a.dx_basis + (long long)c0 * HW;
+      float* dxb = (!alias && has_base && a.dx_base != nullptr) ? a.dx_base + (long long)c0 * HW : nullptr;
+      auto locate = [&](int i) -> int {                               // element offset of the flat position in x, or -1
+        const long long q = m0 + i * kTileM + quarter * 32 + lane;
+        if (q >= g.L) return -1;
+        const unsigned uq = (unsigned)q, n = uq / (unsigned)g.IMG, rem = uq - n * (unsigned)g.IMG;
+        const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
+        return (y < (unsigned)d.h && x < (unsigned)d.w) ? (int)((long long)n * d.x_batch_stride + y * d.w + x) : -1;
+      };
+      auto fetch = [&](int off, float (&xv)[4]) {
 #pragma unroll
-    for (int j = 0; j < KC_MAX_BASIS; ++j) dbl[j] = 0.0f;
-    bool waited = false;
+        for (int c4 = 0; c4 < 4; ++c4) xv[c4] = (off >= 0 && c4 < nch) ? ldg_early(xch + off + (long long)c4 * HW) : 0.0f;
+      };
+      auto ld9 = [&](uint32_t taddr, uint32_t (&r)[9]) {
+        tmem_ld8(taddr, r);
+        if (has_base) tmem_ld1(taddr + 8u, r + 8); else r[8] = 0u;
+      };
+      float xn[4];
+      int offn = locate(0);
+      fetch(offn, xn);
+      tre.stamp();
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      tre.stamp();                                   // accumulator ready
 #pragma unroll 1
-    for (int i = 0; i < g.nsub; ++i) {
-      const long long q = m0 + i * kTileM + quarter * 32 + lane;
-      long long off = -1;
-      if (q < g.L) {
-        int n = (int)(q / g.IMG);
-        int rem = (int)(q - (long long)n * g.IMG);
-        int y = rem / g.P, x = rem - y * g.P;
-        if (y < d.h && x < d.w) off = (long long)n * d.x_batch_stride + y * d.w + x;
-      }
-      float xs[4], xb[4];
+      for (int i = 0; i < g.nsub; ++i) {
+        float xc[4];
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const bool ok = off >= 0 && c0 + c4 < d.cin;
-        xs[c4] = ok ? ldg_early(a.x_basis + off + (long long)(c0 + c4) * HW) : 0.0f;
-        xb[c4] = (ok && has_base && !same_x) ? ldg_early(a.x_base + off + (long long)(c0 + c4) * HW) : xs[c4];
-      }
-      if (!waited) {                                 // the x loads of the first sub-tile fly while the MMAs drain
-        tre.stamp();
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        tre.stamp();                                 // accumulator ready
-        waited = true;
-      }
-      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * g.ntile);
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int c = c0 + c4;
-        if (c >= d.cin) break;                       // warp-uniform
-        uint32_t r[16];
-        tmem_ld16(trow + (uint32_t)((cgrp * 4 + c4) * wb), r);
+        for (int c4 = 0; c4 < 4; ++c4) xc[c4] = xn[c4];
+        const int off = offn;
+        if (i + 1 < g.nsub) { offn = locate(i + 1); fetch(offn, xn); }
+        const uint32_t trow = tq + (uint32_t)(i * g.ntile);
+        auto emit = [&](int c4, const uint32_t (&r)[9]) {
+          if (off < 0) return;
+          const float gs = cubic8_dot_grad(xc[c4], t0, inv_h, nint, r);
+          const float gb = has_base ? __uint_as_float(r[8]) * act_grad_fast(act, xc[c4]) : 0.0f;
+          const long long o = off + (long long)c4 * HW;
+          if (dxb != nullptr) { dxo[o] = gs; dxb[o] = gb; } else { dxo[o] = alias ? gs + gb : gs; }
+        };
+        uint32_t ra[9], rb[9];
+        if (nch > 0) ld9(trow, ra);
         tmem_ld_wait();
-        if (off >= 0) {
-          const long long o = off + (long long)c * HW;
-          float gs;
-          if (g.fast_cubic) gs = cubic8_dot_grad(xs[c4], g.t0, g.inv_h, B->nparams - 1, r);
-          else gs = dgrad_generic(*B, xs[c4], r, gram ? dbl : nullptr);
-          float gb = 0.0f;
-          if (has_base) {
-            float ga = __uint_as_float(r[8]);          // nb == 8 (the common case); other widths: pick column nb
-            if (nb != 8) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (j == nb) ga = __uint_as_float(r[j]);
+        for (int c4 = 0; c4 < 4; c4 += 2) {
+          if (c4 + 1 < nch) ld9(trow + (uint32_t)((c4 + 1) * wb), rb);
+          if (c4 < nch) emit(c4, ra);
+          tmem_ld_wait();
+          if (c4 + 2 < nch) ld9(trow + (uint32_t)((c4 + 2) * wb), ra);
+          if (c4 + 1 < nch) emit(c4 + 1, rb);
+          tmem_ld_wait();
+        }
+      }
+    } else {
+      float dbl[KC_MAX_BASIS];
+#pragma unroll
+      for (int j = 0; j < KC_MAX_BASIS; ++j) dbl[j] = 0.0f;
+      bool waited = false;
+  #pragma unroll 1
+      for (int i = 0; i < g.nsub; ++i) {
+        const long long q = m0 + i * kTileM + quarter * 32 + lane;
+        long long off = -1;
+        if (q < g.L) {
+          int n = (int)(q / g.IMG);
+          int rem = (int)(q - (long long)n * g.IMG);
+          int y = rem / g.P, x = rem - y * g.P;
+          if (y < d.h && x < d.w) off = (long long)n * d.x_batch_stride + y * d.w + x;
+        }
+        float xs[4], xb[4];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const bool ok = off >= 0 && c0 + c4 < d.cin;
+          xs[c4] = ok ? ldg_early(a.x_basis + off + (long long)(c0 + c4) * HW) : 0.0f;
+          xb[c4] = (ok && has_base && !same_x) ? ldg_early(a.x_base + off + (long long)(c0 + c4) * HW) : xs[c4];
+        }
+        if (!waited) {                                 // the x loads of the first sub-tile fly while the MMAs drain
+          tre.stamp();
+          mbar_wait(acc_full, 0);
+          tc_fence_after();
+          tre.stamp();                                 // accumulator ready
+          waited = true;
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * g.ntile);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int c = c0 + c4;
+          if (c >= d.cin) break;                       // warp-uniform
+          uint32_t r[16];
+          tmem_ld16(trow + (uint32_t)((cgrp * 4 + c4) * wb), r);
+          tmem_ld_wait();
+          if (off >= 0) {
+            const long long o = off + (long long)c * HW;
+            float gs;
+            if (g.fast_cubic) gs = cubic8_dot_grad(xs[c4], g.t0, g.inv_h, B->nparams - 1, r);
+            else gs = dgrad_generic(*B, xs[c4], r, gram ? dbl : nullptr);
+            float gb = 0.0f;
+            if (has_base) {
+              float ga = __uint_as_float(r[8]);          // nb == 8 (the common case); other widths: pick column nb
+              if (nb != 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j == nb) ga = __uint_as_float(r[j]);
+              }
+              gb = ga * act_grad_fast(d.act, xb[c4]);
             }
-            gb = ga * act_grad_fast(d.act, xb[c4]);
+            if (alias) {
+              a.dx_basis[o] = gs + gb;
+            } else {
+              a.dx_basis[o] = gs;
+              if (has_base && a.dx_base != nullptr) a.dx_base[o] = gb;
+            }
           }
-          if (alias) {
-            a.dx_basis[o] = gs + gb;
-          } else {
-            a.dx_basis[o] = gs;
-            if (has_base && a.dx_base != nullptr) a.dx_base[o] = gb;
-          }
+        }
+      }
+      if (gram) {
+        for (int nn = 1; nn <= nb - 2; ++nn) {
+          float v = 0.0f;
+#pragma unroll
+          for (int j = 0; j < KC_MAX_BASIS; ++j)
+            if (j == nn) v = dbl[j];
+          v = kc_warp_sum(v);
+          if (lane == 0 && v != 0.0f) atomicAdd(&a.dbeta[nn], v);
         }
       }
     }
     tre.stamp();                                     // dx written
-    if (gram) {
-      for (int nn = 1; nn <= nb - 2; ++nn) {
-        float v = 0.0f;
-#pragma unroll
-        for (int j = 0; j < KC_MAX_BASIS; ++j)
-          if (j == nn) v = dbl[j];
-        v = kc_warp_sum(v);
-        if (lane == 0 && v != 0.0f) atomicAdd(&a.dbeta[nn], v);
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
