@@ -46,6 +46,8 @@ _SIGNATURES = {
     "kc_conv_fwd_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 7),
     "kc_conv_dgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 10),
     "kc_conv_wgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 9),
+    "kc_maxpool2d_fwd": (ctypes.c_int, [c_vp] * 3 + [ctypes.c_longlong] + [ctypes.c_int] * 6 + [c_vp]),
+    "kc_maxpool2d_bwd": (ctypes.c_int, [c_vp] * 3 + [ctypes.c_longlong] + [ctypes.c_int] * 6 + [c_vp]),
     "kc_tc_selftest": (ctypes.c_int, [ctypes.c_int, _P(ctypes.c_float), c_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

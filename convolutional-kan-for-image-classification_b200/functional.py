@@ -376,3 +376,51 @@ def norm_act(spec: NormSpec, z: torch.Tensor, gammas: Sequence[torch.Tensor] = (
     if spec.out_act == L.OUT_PRELU:
         params += list(alphas)
     return _NormActFn.apply(spec, z, given_mean, given_rstd, *params)
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k: int, s: int):
+        lib = L.load()
+        _require_cuda(x, "max_pool2d")
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        if h < k or w < k:
+            raise ValueError(f"max_pool2d: input {h}x{w} smaller than the window {k}")
+        ho, wo = (h - k) // s + 1, (w - k) // s + 1
+        y = torch.empty((n, c, ho, wo), device=x.device, dtype=torch.float32)
+        idx = torch.empty((n, c, ho, wo), device=x.device, dtype=torch.uint8)
+        L.check(_timed("kc_maxpool_fwd_kernel", 0.0, 4.0 * x.numel() + 5.0 * y.numel(), lambda: lib.kc_maxpool2d_fwd(
+            _ptr(x), _ptr(y), _ptr(idx), n * c, h, w, k, s, ho, wo, _stream())), "kc_maxpool2d_fwd")
+        ctx.save_for_backward(idx)
+        ctx.geom = (n, c, h, w, k, s, ho, wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        (idx,) = ctx.saved_tensors
+        n, c, h, w, k, s, ho, wo = ctx.geom
+        dy = dy.contiguous()
+        dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
+        L.check(_timed("kc_maxpool_bwd_kernel", 0.0, 4.0 * dx.numel() + 5.0 * dy.numel(), lambda: lib.kc_maxpool2d_bwd(
+            _ptr(dy), _ptr(idx), _ptr(dx), n * c, h, w, k, s, ho, wo, _stream())), "kc_maxpool2d_bwd")
+        return dx, None, None
+
+
+def max_pool2d(x: torch.Tensor, kernel_size: int, stride: Optional[int] = None) -> torch.Tensor:
+    """nn.MaxPool2d(kernel_size, stride) (no padding / dilation / ceil_mode) on the library's own kernels."""
+    return _MaxPoolFn.apply(x, int(kernel_size), int(stride if stride is not None else kernel_size))
+
+
+class MaxPool2d(torch.nn.MaxPool2d):
+    """``nn.MaxPool2d`` whose CUDA fp32 path runs kc_maxpool2d_fwd / _bwd (same constructor, repr and semantics); the
+    configurations the kernels do not cover (padding, dilation, ceil_mode, return_indices, non-square) use ATen."""
+
+    def forward(self, x):
+        k, s = self.kernel_size, self.stride
+        plain = (isinstance(k, int) and isinstance(s, int) and self.padding == 0 and self.dilation == 1 and not self.ceil_mode
+                 and not self.return_indices and k <= 11)
+        if plain and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4:
+            return max_pool2d(x, k, s)
+        return super().forward(x)

@@ -17,6 +17,7 @@ except Exception:  # pragma: no cover
     class PyTorchModelHubMixin:  # type: ignore
         pass
 
+from ..functional import MaxPool2d
 from ..layers.kan_conv import CONV_KAN_FACTORY, conv
 from .kans import MLP_KAN_FACTORY
 
@@ -81,7 +82,7 @@ class VGG(nn.Module):
         in_channels = num_input_features
         for idx, v in enumerate(cfg):
             if v == "M":
-                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+                layers.append(MaxPool2d(kernel_size=2, stride=2))
                 continue
             out_channels = cast(int, v) * width_scale
             layers.append((first_fn if idx == 0 else conv_fn)(in_channels, out_channels))

@@ -111,6 +111,17 @@ int kc_conv_wgrad_f32(const kc_desc* d, const float* dz, const float* x_base, co
                       const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Max pooling between convolution stages (nn.MaxPool2d(k, s), no padding / dilation; models/kan_vgg.py "M" entries).
+ * x is [planes][h][w] fp32 (planes = n*c), y / idx are [planes][ho][wo] with ho = (h-k)/s + 1; idx holds the
+ * row-major position of the maximum inside its window (one byte, k <= 11).  Ties keep the first maximum and NaN
+ * propagates, as in ATen.  bwd is a deterministic gather and writes every element of dx.
+ * ------------------------------------------------------------------------------------------------------- */
+int kc_maxpool2d_fwd(const float* x, float* y, unsigned char* idx, long long planes, int h, int w, int k, int s,
+                     int ho, int wo, void* stream);
+int kc_maxpool2d_bwd(const float* dy, const unsigned char* idx, float* dx, long long planes, int h, int w, int k, int s,
+                     int ho, int wo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Normalisation + output activation (memory-bound, vectorised):  y = out_act(gamma * (z-mean)*rstd + beta)
  * [kan_layers.py:242-243, gram:187, cheby:98; fast:106 uses it on the INPUT with out_act = NONE].
  * mean/rstd are [n*c] (instance) or [c] (batch) and are outputs of fwd / inputs of bwd.

@@ -392,3 +392,26 @@ def test_full_size_padding_lives_in_basis_space():
     with torch.no_grad():
         z0 = KF.kan_conv(spec, xz, None, None, wb, ws, "bf16")
     assert not torch.allclose(z0[:, :, 0, 0], z0[:, :, 16, 16])
+
+
+@pytest.mark.parametrize("shape,k,s", [((3, 5, 16, 24), 2, 2), ((2, 3, 15, 17), 2, 2), ((2, 4, 13, 13), 3, 2), ((1, 2, 9, 10), 3, 1),
+                                       ((2, 2, 8, 8), 2, 3)])
+def test_max_pool_matches_aten_bit_exact(shape, k, s):
+    """kc_maxpool2d_fwd / _bwd against ATen's max_pool2d: selection only, so values, ties and gradients are bit-exact."""
+    import torch.nn.functional as F
+    from kanconv_b200 import functional as KF
+    torch.manual_seed(0)
+    x = torch.randn(*shape, device="cuda")
+    x[0, 0, :4, :4] = 1.0                      # ties: the first maximum of a window wins
+    x[-1, -1, 5, 5] = float("nan")            # NaN propagates
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    ya = F.max_pool2d(xa, k, s)
+    yb = KF.max_pool2d(xb, k, s)
+    assert torch.equal(torch.nan_to_num(ya, nan=123.0), torch.nan_to_num(yb, nan=123.0))
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    assert torch.equal(xa.grad, xb.grad)
+    m = KF.MaxPool2d(kernel_size=k, stride=s)
+    assert torch.equal(torch.nan_to_num(m(x), nan=123.0), torch.nan_to_num(ya.detach(), nan=123.0))

@@ -43,3 +43,4 @@ for q in range(len(mm) // 11):
 print("tap: copy_issued  b_full_seen  (latency)   next_copy_issue - this b_full")
 for k in range(36, min(54, len(lo), len(mma_tap))):
     print(f"  {k:3d}: {lo[k]:8d} {mma_tap[k]:8d}  ({mma_tap[k]-lo[k]:6d})")
+print("mma first/last events", mm[:3], mm[-3:], "producer last", [int(v) - t0 for v in t[0] if v > 0][-2:])
