@@ -851,12 +851,15 @@ size_t tc_fixed_smem() { return (size_t)kNumBars * 8 + 16 + sizeof(KcBasisCtx) +
 // kcores = total number of 16-byte k-cores per tap in the weight image of one N tile.
 int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
   const size_t btap = (size_t)kPL * g->ntile * 16;
-  // nsub: as many 128-row sub-tiles per CTA as TMEM (512 columns), the producer row mapping (1024 rows), shared memory
-  // and the wish for >= 2 waves of CTAs allow.  tps: a ring stage carries a whole filter row (kw taps) when at least 4
-  // such stages fit - the per-stage cost of the issuing warp (barrier wait, fence, commits ~ several hundred cycles) is
-  // then paid once per kw taps - else a single tap.
+  // nsub: 128-row sub-tiles per CTA, bounded by TMEM (512 columns), the producer row mapping (1024 rows) and shared memory.
+  // Among the nsub that fit, take the one with the smallest estimated kernel time:
+  //   waves(nsub) * [ max(nsub * MMA cycles of the K loop, weight-image bytes / ~32 B per cycle from L2) + fixed + nsub * epilogue ]
+  // (a CTA streams the whole weight image of its N tile whatever nsub is, so nsub = 1 is L2-bandwidth bound; large nsub
+  // leaves SMs idle when the batch is small).
   bool found = false;
-  for (int nsub = 4; nsub >= 1 && !found; --nsub) {
+  double best_cost = 0.0;
+  const int nchunks = (kcores + kPL - 1) / kPL;
+  for (int nsub = 4; nsub >= 1; --nsub) {
     if (nsub * g->ntile > 512) continue;
     const int mcta = nsub * kTileM;
     const int seglen = round_up(mcta + d->kw - 1, 8);
@@ -864,11 +867,20 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
     const int nrows = (d->kh - 1) * SS + seglen;
     if (nrows > kRB * kRowThreads) continue;
     const long long mtiles = (g->L + mcta - 1) / mcta;
-    if (nsub > 1 && mtiles * g->n_ntiles < 2 * 148) continue;
+    const long long ctas = mtiles * g->n_ntiles;
+    // CTAs do not run in lockstep, so wave quantisation only matters while the grid is a wave or two
+    const double waves = ctas < 2 * 148 ? (double)((ctas + 147) / 148) : (double)ctas / 148.0;
+    const double mma_cyc = (double)nchunks * T * 2.0 * (g->ntile / 2 > 48 ? g->ntile / 2 : 48);     // per sub-tile
+    const double b_cyc = (double)nchunks * T * (double)btap / 32.0;
+    const double cta_cyc = (nsub * mma_cyc > b_cyc ? nsub * mma_cyc : b_cyc) + 8000.0 + nsub * 3000.0;
+    const double cost = waves * cta_cyc;
+    if (found && cost >= best_cost) continue;
     const int plane_bytes = nrows * 16 + 16;       // +16 B: consecutive planes start 4 banks apart
     // preference: whole-filter-row stages with a 3-deep A ring, then with a 2-deep A ring, then single-tap stages
+    // (a ring stage that carries kw taps pays the issuing warp's per-stage cost - barrier wait, fence, commits, several
+    // hundred cycles - once per filter row)
     const int cand_na[4] = {3, 2, 3, 2}, cand_tps[4] = {d->kw, d->kw, 1, 1};
-    for (int ci = 0; ci < 4 && !found; ++ci) {
+    for (int ci = 0; ci < 4; ++ci) {
       const int na = cand_na[ci], tps = cand_tps[ci];
       if (ci >= 2 && d->kw == 1) break;
       const size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
@@ -879,6 +891,8 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
       g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps;
       g->na = na; g->bstages = bst; g->mtiles = mtiles; g->smem_bytes = fixed + bst * bstage;
       found = true;
+      best_cost = cost;
+      break;
     }
   }
   if (!found) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path: tile does not fit shared memory");
@@ -1334,6 +1348,16 @@ extern "C" int kc_debug_bulk_bench(const void* src, long long span, int bytes, i
 }
 
 // Debug only (not part of include/kanconv.h): enable/disable the timeline trace of kc_fwd_tc_kernel.
+// Debug only: tile geometry chosen for a shape.  which 0 = forward, 1 = dgrad; out = {nsub, ntile, n_ntiles, na, tps, bstages, mtiles, smem}
+extern "C" int kc_debug_tc_geometry(const kc_desc* d, int which, long long* out) {
+  TcGeom g;
+  int rc = which == 0 ? tc_forward_geometry(d, &g) : tc_dgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  out[0] = g.nsub; out[1] = g.ntile; out[2] = g.n_ntiles; out[3] = g.na; out[4] = g.tps; out[5] = g.bstages; out[6] = g.mtiles;
+  out[7] = (long long)g.smem_bytes;
+  return KC_OK;
+}
+
 extern "C" int kc_debug_trace(void* device_buffer) {
   long long* p = (long long*)device_buffer;
   KC_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
