@@ -284,6 +284,14 @@ def run_b200(args):
                     "traffic": None, "launches_per_step": st["calls"], "ms_per_launch": st["ms"] / st["calls"],
                     "share_of_library_time": st["ms"] / total_ms, "peak_source": peak_src}
         roof["by_kernel_ms"] = {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        # DRAM bytes per launch of that kernel from the committed ncu capture of this workload (profiles/), if any
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic_b64.json")
+        if args.workload == "kan_vgg16_224" and batch == 64 and os.path.exists(tpath):
+            with open(tpath) as fh:
+                tk = json.load(fh)["kernels"].get(name)
+            if tk:
+                roof["traffic"] = tk["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/r1_traffic_b64.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
 
     if rank != 0:
         if world > 1:
