@@ -82,6 +82,7 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 // ---- optional timeline trace (debug): kc_debug_trace() points g_trace at a device buffer of 4 x 1024 clock stamps;
 // one CTA records one stamp per pipeline event of representative threads.  nullptr (default) = disabled.
 __device__ long long* g_trace = nullptr;
+__device__ int g_dbg_flag = 0;          // EXPERIMENT: bit0 = weight loader copies half of each stage (timing probe, wrong results)
 struct Tracer {
   long long* p; int n;
   __device__ Tracer(int role, bool on) {
@@ -513,8 +514,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
         for (int t = 0; t < T; t += g.tps) {
           mbar_wait(&b_empty[stage], bphase ^ 1);
           trl.stamp();                               // b_empty acquired
-          mbar_arrive_expect_tx(&b_full[stage], bytes);
-          bulk_g2s(bst0 + stage * bstage_bytes, wsrc, bytes, &b_full[stage]);
+          const uint32_t cbytes = (g_dbg_flag & 1) ? bytes / 2 : bytes;
+          mbar_arrive_expect_tx(&b_full[stage], cbytes);
+          bulk_g2s(bst0 + stage * bstage_bytes, wsrc, cbytes, &b_full[stage]);
           wsrc += bytes;
           if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
         }
@@ -717,58 +719,121 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------------
 struct TcPackArgs { kc_desc d; TcGeom g; const float* w_base; const float* w_basis; uint4* out; };
 
+// One thread = one (N tile, chunk, k-core, column) and ALL taps: for the B-spline / RBF / Chebyshev layouts the 8 x T
+// source floats of a spline k-core (8 basis functions of one channel, T taps) and of a base k-core (8 channels, T taps)
+// are one contiguous run, so every 32-byte sector that is fetched is fully used; the T output vectors go to the T tap
+// images of the chunk (consecutive threads = consecutive columns -> contiguous 16-byte stores).
+constexpr int kPackMaxT = 9;          // taps held in registers per pass (larger filters take several passes)
+
 __global__ void __launch_bounds__(256) kc_pack_fwd_kernel(const __grid_constant__ TcPackArgs a) {
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
   const int T = d.kh * d.kw, nb = d.nb;
   const bool has_base = d.act != KC_ACT_NONE;
+  const int nchunks = g.nsc + (has_base ? g.nbc : 0);
   const long long vec_per_ntile = g.wimg_bytes_per_ntile / 16;
-  const long long total = vec_per_ntile * g.n_ntiles;
   const long long full_chunk = (long long)T * kPL * g.ntile;
-  const long long spline_vecs = (long long)g.nsc * full_chunk;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
-    const int nt = (int)(v / vec_per_ntile);
-    long long vl = v - (long long)nt * vec_per_ntile;
-    float f[8];
+  const long long per_chunk = (long long)kPL * g.ntile;                        // threads per (N tile, chunk)
+  const long long total = (long long)g.n_ntiles * nchunks * per_chunk;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+    const int nt = (int)(u / (nchunks * per_chunk));
+    const long long ul = u - (long long)nt * nchunks * per_chunk;
+    const int q = (int)(ul / per_chunk);
+    const int rem = (int)(ul - (long long)q * per_chunk);
+    const int kc = rem / g.ntile, nl = rem - kc * g.ntile;
+    const int co = nt * g.ntile + nl;
+    const bool spline = q < g.nsc;
+    const int bq = q - g.nsc;
+    const int ncols = (spline || bq != g.nbc - 1) ? kPL : g.last_base_cols;
+    if (kc >= ncols) continue;
+    // element e of the vector reads src[e * estride + t]; estride < 0 marks "zero"
+    const float* src[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = 0.0f;
-    if (vl < spline_vecs) {
-      int q = (int)(vl / full_chunk);
-      long long rem = vl - (long long)q * full_chunk;
-      int t = (int)(rem / (kPL * g.ntile));
-      int rem2 = (int)(rem - (long long)t * kPL * g.ntile);
-      int kc = rem2 / g.ntile, nl = rem2 - kc * g.ntile;
-      int co = nt * g.ntile + nl;
-      if (co < d.cout) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int c, j;
-          if (nb > 4) { c = q * 4 + kc; j = e; } else { c = q * 8 + kc * 2 + (e >> 2); j = e & 3; }
-          if (c < d.cin && j < nb) f[e] = a.w_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + t];
-        }
-      }
-    } else if (has_base) {
-      long long vb = vl - spline_vecs;
-      int bq = (int)min((long long)(g.nbc - 1), vb / full_chunk);
-      long long rem = vb - (long long)bq * full_chunk;
-      int ncols = (bq == g.nbc - 1) ? g.last_base_cols : kPL;
-      int t = (int)(rem / (ncols * g.ntile));
-      int rem2 = (int)(rem - (long long)t * ncols * g.ntile);
-      int kc = rem2 / g.ntile, nl = rem2 - kc * g.ntile;
-      int co = nt * g.ntile + nl, grp = bq * kPL + kc;
-      if (co < d.cout && grp < g.ngroups) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int c = grp * 8 + e;
-          if (c < d.cin) f[e] = a.w_base[((long long)co * d.cin + c) * T + t];
-        }
+    for (int e = 0; e < 8; ++e) {
+      src[e] = nullptr;
+      if (co >= d.cout) continue;
+      if (spline) {
+        int c, jj;
+        if (nb > 4) { c = q * 4 + kc; jj = e; } else { c = q * 8 + kc * 2 + (e >> 2); jj = e & 3; }
+        if (c < d.cin && jj < nb) src[e] = a.w_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, jj, d.cin, nb)) * T;
+      } else {
+        const int c = (bq * kPL + kc) * 8 + e;
+        if (c < d.cin) src[e] = a.w_base + ((long long)co * d.cin + c) * T;
       }
     }
-    a.out[v] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    uint4* dst = a.out + (long long)nt * vec_per_ntile + (spline ? (long long)q * full_chunk : (long long)g.nsc * full_chunk + (long long)bq * full_chunk) +
+                 (long long)kc * g.ntile + nl;
+    const long long tstride = (long long)ncols * g.ntile;
+    for (int t0 = 0; t0 < T; t0 += kPackMaxT) {
+      float f[kPackMaxT][8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int tt = 0; tt < kPackMaxT; ++tt) f[tt][e] = (src[e] != nullptr && t0 + tt < T) ? __ldg(src[e] + t0 + tt) : 0.0f;
+#pragma unroll
+      for (int tt = 0; tt < kPackMaxT; ++tt)
+        if (t0 + tt < T)
+          dst[(long long)(t0 + tt) * tstride] = make_uint4(pack_bf16(f[tt][0], f[tt][1]), pack_bf16(f[tt][2], f[tt][3]),
+                                                            pack_bf16(f[tt][4], f[tt][5]), pack_bf16(f[tt][6], f[tt][7]));
+    }
+  }
+}
+
+// Forward image through a shared-memory transpose (channel-major weight layouts, T <= 9): the source of one (chunk, cout)
+// is ONE contiguous run of nk x 8 x T floats (nk k-cores), read coalesced by a warp; the tile [32 couts][run] is then
+// re-read column-wise (pitch run+1: conflict-free) to emit the 16-byte vectors with consecutive threads = consecutive
+// couts.  grid = (cout tiles of 32, chunks, N tiles).
+constexpr int kPackTileCo = 32;
+constexpr int kPackRunMax = kPL * 8 * kPackMaxT;
+
+__global__ void __launch_bounds__(256) kc_pack_fwd_tile_kernel(const __grid_constant__ TcPackArgs a) {
+  __shared__ float tile[kPackTileCo][kPackRunMax + 1];
+  const kc_desc& d = a.d;
+  const TcGeom& g = a.g;
+  const int T = d.kh * d.kw, nb = d.nb;
+  const int nt = blockIdx.z, q = blockIdx.y, nl0 = blockIdx.x * kPackTileCo;
+  const bool spline = q < g.nsc;
+  const int bq = q - g.nsc;
+  const int ncols = (spline || bq != g.nbc - 1) ? kPL : g.last_base_cols;
+  const long long vec_per_ntile = g.wimg_bytes_per_ntile / 16;
+  const long long full_chunk = (long long)T * kPL * g.ntile;
+  // source run of one cout: channels [ch0, ch0 + nch) x (nb | 1) x T floats, zero beyond cin
+  const int ch_per_core = spline ? (nb > 4 ? 1 : 2) : 8, per_ch = spline ? nb : 1;
+  const int ch0 = spline ? q * kPL * ch_per_core : bq * kPL * 8;
+  const int nch_live = max(0, min(ncols * ch_per_core, d.cin - ch0));
+  const int run = nch_live * per_ch * T;                                  // floats actually present
+  const float* base = spline ? a.w_basis : a.w_base;
+  const long long co_stride = (long long)d.cin * per_ch * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cl = warp; cl < kPackTileCo; cl += 8) {
+    const int co = nt * g.ntile + nl0 + cl;
+    const bool ok = nl0 + cl < g.ntile && co < d.cout;
+    const float* src = base + (long long)co * co_stride + (long long)ch0 * per_ch * T;
+    for (int i = lane; i < run; i += 32) tile[cl][i] = ok ? __ldg(src + i) : 0.0f;
+  }
+  __syncthreads();
+  uint4* dst = a.out + (long long)nt * vec_per_ntile + (spline ? (long long)q * full_chunk : (long long)g.nsc * full_chunk + (long long)bq * full_chunk);
+  const int nvec = T * ncols * kPackTileCo;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    const int cl = v % kPackTileCo, rest = v / kPackTileCo, kc = rest % ncols, t = rest / ncols;
+    if (nl0 + cl >= g.ntile) continue;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int idx;                                                            // float index inside the run, or -1
+      if (!spline) idx = (kc * 8 + e < nch_live) ? (kc * 8 + e) * T + t : -1;
+      else if (nb > 4) idx = (kc < nch_live && e < nb) ? (kc * nb + e) * T + t : -1;
+      else idx = (kc * 2 + (e >> 2) < nch_live && (e & 3) < nb) ? ((kc * 2 + (e >> 2)) * nb + (e & 3)) * T + t : -1;
+      f[e] = idx >= 0 ? tile[cl][idx] : 0.0f;
+    }
+    dst[((long long)t * ncols + kc) * g.ntile + nl0 + cl] =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
   }
 }
 
 // dgrad weights: [ntile = 16 input channels][chunk of 32 couts][flipped tap][k-core = 8 couts][n = (cl, j)][8]
+// Same thread mapping (all taps per thread): the T floats of one (cout, channel, j) are contiguous and consecutive threads
+// (consecutive j, then channel) read adjacent runs.
 __global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constant__ TcPackArgs a) {
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
@@ -776,30 +841,41 @@ __global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constan
   const bool has_base = d.act != KC_ACT_NONE;
   const int wb = nb + (has_base ? 1 : 0);
   const long long vec_per_ntile = g.wimg_bytes_per_ntile / 16;
-  const long long total = vec_per_ntile * g.n_ntiles;
   const long long full_chunk = (long long)T * kPL * g.ntile;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
-    const int nt = (int)(v / vec_per_ntile);
-    long long vl = v - (long long)nt * vec_per_ntile;
-    int bq = (int)min((long long)(g.nbc - 1), vl / full_chunk);
-    long long rem = vl - (long long)bq * full_chunk;
-    int ncols = (bq == g.nbc - 1) ? g.last_base_cols : kPL;
-    int t = (int)(rem / (ncols * g.ntile));
-    int rem2 = (int)(rem - (long long)t * ncols * g.ntile);
-    int kc = rem2 / g.ntile, nl = rem2 - kc * g.ntile;
-    const int c = nt * 16 + nl / wb, j = nl % wb, tap = T - 1 - t;
-    float f[8];
+  const long long per_chunk = (long long)kPL * g.ntile;
+  const long long total = (long long)g.n_ntiles * g.nbc * per_chunk;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+    const int nt = (int)(u / (g.nbc * per_chunk));
+    const long long ul = u - (long long)nt * g.nbc * per_chunk;
+    const int bq = (int)(ul / per_chunk);
+    const int rem = (int)(ul - (long long)bq * per_chunk);
+    const int kc = rem / g.ntile, nl = rem - kc * g.ntile;
+    const int ncols = (bq == g.nbc - 1) ? g.last_base_cols : kPL;
+    if (kc >= ncols) continue;
+    const int c = nt * 16 + nl / wb, jj = nl % wb;
+    const float* src[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int co = (bq * kPL + kc) * 8 + e;
-      float w = 0.0f;
-      if (co < d.cout && c < d.cin) {
-        if (j < nb) w = a.w_basis[((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + tap];
-        else w = a.w_base[((long long)co * d.cin + c) * T + tap];
-      }
-      f[e] = w;
+      src[e] = nullptr;
+      if (co < d.cout && c < d.cin)
+        src[e] = jj < nb ? a.w_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, jj, d.cin, nb)) * T
+                         : a.w_base + ((long long)co * d.cin + c) * T;
     }
-    a.out[v] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    uint4* dst = a.out + (long long)nt * vec_per_ntile + (long long)bq * full_chunk + (long long)kc * g.ntile + nl;
+    const long long tstride = (long long)ncols * g.ntile;
+    for (int t0 = 0; t0 < T; t0 += kPackMaxT) {
+      float f[kPackMaxT][8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int tt = 0; tt < kPackMaxT; ++tt) f[tt][e] = (src[e] != nullptr && t0 + tt < T) ? __ldg(src[e] + t0 + tt) : 0.0f;
+#pragma unroll
+      for (int tt = 0; tt < kPackMaxT; ++tt)
+        if (t0 + tt < T)     // image tap index is the flipped filter tap
+          dst[(long long)(T - 1 - (t0 + tt)) * tstride] = make_uint4(pack_bf16(f[tt][0], f[tt][1]), pack_bf16(f[tt][2], f[tt][3]),
+                                                                      pack_bf16(f[tt][4], f[tt][5]), pack_bf16(f[tt][6], f[tt][7]));
+    }
   }
 }
 
@@ -1075,11 +1151,18 @@ extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const f
   if (d->act != KC_ACT_NONE && !w_base) KC_FAIL(KC_ERR_INVALID, "kc_tc_pack_weights: base branch needs w_base");
   TcPackArgs a;
   a.d = *d; a.g = g; a.w_base = w_base; a.w_basis = w_basis; a.out = (uint4*)packed_fwd;
-  long long total = g.wimg_bytes_per_ntile / 16 * g.n_ntiles;
+  const int T = d->kh * d->kw;
+  long long total = g.wimg_bytes_per_ntile / 16 * g.n_ntiles / T + (long long)kPL * g.ntile * g.n_ntiles;   // one thread per (vector, all taps)
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (packed_fwd != nullptr) {
-    kc_pack_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    const int nchunks = g.nsc + (d->act != KC_ACT_NONE ? g.nbc : 0);
+    if (d->basis != KC_BASIS_GRAM && T <= kPackMaxT && nchunks <= 65535 && g.n_ntiles <= 65535) {
+      dim3 pgrid((unsigned)((g.ntile + kPackTileCo - 1) / kPackTileCo), (unsigned)nchunks, (unsigned)g.n_ntiles);
+      kc_pack_fwd_tile_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a);
+    } else {
+      kc_pack_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    }
     KC_LAUNCH_CHECK("kc_pack_fwd_kernel");
   }
   if (packed_dgrad != nullptr) {
@@ -1087,7 +1170,7 @@ extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const f
     rc = tc_dgrad_geometry(d, &gd);
     if (rc != KC_OK) return rc;
     a.g = gd; a.out = (uint4*)packed_dgrad;
-    total = gd.wimg_bytes_per_ntile / 16 * gd.n_ntiles;
+    total = gd.wimg_bytes_per_ntile / 16 * gd.n_ntiles / T + (long long)kPL * gd.ntile * gd.n_ntiles;
     blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     kc_pack_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
@@ -1355,6 +1438,11 @@ extern "C" int kc_debug_tc_geometry(const kc_desc* d, int which, long long* out)
   if (rc != KC_OK) return rc;
   out[0] = g.nsub; out[1] = g.ntile; out[2] = g.n_ntiles; out[3] = g.na; out[4] = g.tps; out[5] = g.bstages; out[6] = g.mtiles;
   out[7] = (long long)g.smem_bytes;
+  return KC_OK;
+}
+
+extern "C" int kc_debug_flag(int v) {
+  KC_CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_flag, &v, sizeof(v)));
   return KC_OK;
 }
 
