@@ -414,6 +414,57 @@ __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_kernel(const __grid_co
   }
 }
 
+// Same reduction through a shared-memory transpose (filters with kh*kw <= 9): a block owns 32 expanded rows x 32 couts of one
+// (cout tile, chunk) for ALL taps, sums the splits with coalesced 128-byte reads, and writes runs that are contiguous in
+// the reference layout ([cout][(c, j)][kh][kw]: 32 rows x T taps = 288 consecutive floats per cout for nb = 8).
+constexpr int kRedT = 9;
+__global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_tile_kernel(const __grid_constant__ kc_desc d, const __grid_constant__ WgGeom g,
+                                                                      const float* __restrict__ ws, float* __restrict__ dw_base,
+                                                                      float* __restrict__ dw_basis) {
+  __shared__ float tile[32][32 * kRedT + 1];
+  const int nb = d.nb, T = d.kh * d.kw;
+  const int nsub_n = (g.ntile + 31) / 32;
+  const int n0 = (blockIdx.x % nsub_n) * 32, m0 = (blockIdx.x / nsub_n) * 32;
+  const int chunk = blockIdx.y % g.nchunks, ct = blockIdx.y / g.nchunks;
+  const long long unit_sz = (long long)d.kw * 128 * g.ntile;
+  const long long total = (long long)g.units * unit_sz;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool ncol_ok = n0 + lane < g.ntile;
+  for (int r = 0; r < d.kh; ++r) {
+    const int unit = (ct * g.nchunks + chunk) * d.kh + r;
+    for (int s = 0; s < d.kw; ++s)
+#pragma unroll
+      for (int mm = 0; mm < 4; ++mm) {
+        const int ml = warp + 8 * mm;
+        const long long i = (long long)unit * unit_sz + ((long long)s * 128 + m0 + ml) * g.ntile + n0 + lane;
+        float acc = 0.0f;
+        if (ncol_ok)
+          for (int k = 0; k < g.nsplit; ++k) acc += ws[(long long)k * total + i];
+        tile[lane][ml * T + r * d.kw + s] = acc;
+      }
+  }
+  __syncthreads();
+  const int run = 32 * T;
+  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
+    const int col = idx / run, i = idx - col * run;
+    const int ml = i / T, t = i - ml * T;
+    const int co = ct * g.ntile + n0 + col, m = m0 + ml;
+    if (n0 + col >= g.ntile || co >= d.cout) continue;
+    float* dst;
+    if (chunk < g.nsc) {
+      const int nbp = nb > 4 ? 8 : 4;
+      const int c = chunk * g.cps + m / nbp, j = m % nbp;
+      if (c >= d.cin || j >= nb) continue;
+      dst = dw_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + t;
+    } else {
+      const int c = (chunk - g.nsc) * 128 + m;
+      if (c >= d.cin) continue;
+      dst = dw_base + ((long long)co * d.cin + c) * T + t;
+    }
+    *dst = tile[col][i];
+  }
+}
+
 bool knots_uniform_cubic_w(const kc_desc* d, float* t0, float* inv_h) {
   if (d->basis != KC_BASIS_BSPLINE || d->order != 3 || d->nb != 8 || d->nparams != 12) return false;
   double h = ((double)d->params[11] - (double)d->params[0]) / 11.0;
@@ -543,7 +594,15 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   long long total = (long long)g.units * d->kw * 128 * g.ntile;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  kc_wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
+  // the tile kernel needs enough (cout tile, chunk) pairs to fill the machine; few-channel layers (many splits, few
+  // units) keep the element-parallel kernel
+  const long long tile_blocks = (long long)((g.ntile + 31) / 32) * 4 * g.n_ct * g.nchunks;
+  if (d->kh * d->kw <= kRedT && (long long)g.n_ct * g.nchunks <= 65535 && tile_blocks >= 2 * 148) {
+    dim3 rgrid((unsigned)(((g.ntile + 31) / 32) * 4), (unsigned)(g.n_ct * g.nchunks));
+    kc_wgrad_tc_reduce_tile_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
+  } else {
+    kc_wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
+  }
   KC_LAUNCH_CHECK("kc_wgrad_tc_reduce_kernel");
   return KC_OK;
 }
