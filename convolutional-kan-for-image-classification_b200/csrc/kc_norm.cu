@@ -8,6 +8,10 @@
 namespace {
 
 constexpr int kNT = 256;
+constexpr int kNTBig = 1024;      // planes of >= 16 K elements: one or two planes per SM in flight, so that the second and
+                                  // third pass over a plane hit L2 (8 resident 256-thread CTAs x 200 KB planes overflow it)
+constexpr int kBigPlane = 16384;
+
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   // all threads of the block must call; returns the total to every thread
@@ -54,7 +58,7 @@ __device__ __forceinline__ void plane_foreach(const float* __restrict__ p, int h
 // Plane statistics: mean and M2 = sum (z-mean)^2 of plane (n, c).   One block per plane.
 // Instance norm: finalised in the same kernel (and y written).  Batch norm: plane stats are combined per channel.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT)
+__global__ void __launch_bounds__(kNTBig)
 kc_instnorm_fwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ z,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        const float* __restrict__ alpha_p, float* __restrict__ y, float* __restrict__ mean_out,
@@ -101,7 +105,7 @@ kc_instnorm_fwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __re
 }
 
 // Batch norm step 1: per-plane mean and M2 (block per plane) -> partials[0][plane], partials[1][plane]
-__global__ void __launch_bounds__(kNT)
+__global__ void __launch_bounds__(kNTBig)
 kc_plane_stats_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ z, float* __restrict__ pmean,
                       float* __restrict__ pm2) {
   __shared__ float sh[32];
@@ -141,7 +145,7 @@ __global__ void kc_batch_stats_combine_kernel(const __grid_constant__ kc_norm_de
 //   dz = rstd * (dzhat - mean_G(dzhat) - zhat * mean_G(dzhat*zhat)),  G = plane (instance) | channel over n (batch)
 //   partials[0][plane] = sum dv*zhat (-> dgamma), [1] = sum dv (-> dbeta), [2] = sum dy*v*[v<=0] (-> dalpha)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT)
+__global__ void __launch_bounds__(kNTBig)
 kc_norm_bwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ dy, const float* __restrict__ z,
                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha_p,
@@ -271,16 +275,17 @@ extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const floa
   if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
   const int planes = d->n * d->c;
+  const int nt = d->hw >= kBigPlane ? kNTBig : kNT;
   if (d->norm == KC_NORM_BATCH) {
     if (!scratch) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: batch norm needs a 2*n*c float scratch buffer");
     float* pmean = scratch;
     float* pm2 = scratch + planes;
-    kc_plane_stats_kernel<<<planes, kNT, 0, st>>>(*d, z, pmean, pm2);
+    kc_plane_stats_kernel<<<planes, nt, 0, st>>>(*d, z, pmean, pm2);
     KC_LAUNCH_CHECK("kc_plane_stats_kernel");
     kc_batch_stats_combine_kernel<<<(d->c + 7) / 8, 256, 0, st>>>(*d, pmean, pm2, mean, rstd);
     KC_LAUNCH_CHECK("kc_batch_stats_combine_kernel");
   }
-  kc_instnorm_fwd_kernel<<<planes, kNT, 0, st>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
+  kc_instnorm_fwd_kernel<<<planes, nt, 0, st>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
   KC_LAUNCH_CHECK("kc_instnorm_fwd_kernel");
   return KC_OK;
 }
@@ -294,24 +299,25 @@ extern "C" int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const flo
   if (d->norm != KC_NORM_NONE && (!mean || !rstd)) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: mean/rstd required");
   if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
+  const int nt = d->hw >= kBigPlane ? kNTBig : kNT;
   const int planes = d->n * d->c;
   if (d->norm == KC_NORM_BATCH) {
     // partials layout: [3][planes] plane sums, then [2][c] channel sums
     float* chan = partials + 3 * (size_t)planes;
-    kc_norm_bwd_kernel<<<planes, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 1);
+    kc_norm_bwd_kernel<<<planes, nt, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 1);
     KC_LAUNCH_CHECK("kc_norm_bwd_kernel(phase1)");
     // chan[0][c] = sum dv*zhat, chan[1][c] = sum dv ; kernel phase 2 expects [0] = sum dzhat (=dv) and [1] = sum dzhat*zhat,
     // both up to the factor gamma applied inside the kernel -> pass them swapped.
     kc_partials_reduce_kernel<<<d->c + 1, kNT, 0, st>>>(*d, partials, chan + d->c, chan, dalpha);
     KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
-    kc_norm_bwd_kernel<<<planes, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, chan, 2);
+    kc_norm_bwd_kernel<<<planes, nt, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, chan, 2);
     KC_LAUNCH_CHECK("kc_norm_bwd_kernel(phase2)");
     if (dgamma || dbeta) {
       kc_partials_reduce_kernel<<<d->c, kNT, 0, st>>>(*d, partials, dgamma, dbeta, nullptr);
       KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
     }
   } else {
-    kc_norm_bwd_kernel<<<planes, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 0);
+    kc_norm_bwd_kernel<<<planes, nt, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 0);
     KC_LAUNCH_CHECK("kc_norm_bwd_kernel");
     if (dgamma || dbeta || dalpha) {
       kc_partials_reduce_kernel<<<d->c + 1, kNT, 0, st>>>(*d, partials, dgamma, dbeta, dalpha);
