@@ -524,38 +524,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     }
     __syncwarp();
   }
-  if (MODE == kModeFwd && warp < 4) {
+  if (MODE == kModeFwd && warp < 16) {
     // ================================ epilogue: TMEM -> registers -> z (fp32 NCHW) =====================
+    // All 16 producer warps: warp w reads the TMEM lanes of its hardware quarter (w % 4) and every fourth group of 16
+    // columns (w / 4); a store instruction writes one output channel of 32 consecutive positions (128 B).
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int HoWo = d.ho * d.wo;
     const int n0 = nt * g.ntile;
+    const int quarter = warp & 3, cgrp = warp >> 2;
     for (int i = 0; i < g.nsub; ++i) {
-      const long long q = m0 + i * kTileM + warp * 32 + lane;
+      const long long q = m0 + i * kTileM + quarter * 32 + lane;
       bool valid = false;
       long long zoff = 0;
       if (q < g.L) {
-        int n = (int)(q / g.IMG);
-        int rem = (int)(q - (long long)n * g.IMG);
-        int y = rem / g.P, x = rem - y * g.P;
-        if (y < d.ho && x < d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + y * d.wo + x; }
+        const unsigned uq = (unsigned)q, n = uq / (unsigned)g.IMG, rem = uq - n * (unsigned)g.IMG;
+        const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
+        if (y < (unsigned)d.ho && x < (unsigned)d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + y * d.wo + x; }
       }
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * g.ntile);
-      for (int c0 = 0; c0 < g.ntile; c0 += 32) {
-        uint32_t r[32];
-        if (g.ntile - c0 >= 32) {
-          tmem_ld32(trow + (uint32_t)c0, r);
-        } else {
-          tmem_ld16(trow + (uint32_t)c0, r);
-#pragma unroll
-          for (int j = 16; j < 32; ++j) r[j] = 0u;
-        }
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * g.ntile);
+      for (int c0 = cgrp * 16; c0 < g.ntile; c0 += 64) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)c0, r);          // ntile is a multiple of 16
         tmem_ld_wait();
-        const int lim = min(32, g.ntile - c0);
+        float* zp = a.z + zoff + (long long)(n0 + c0) * HoWo;
+        const int lim = min(16, d.cout - (n0 + c0));
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int co = n0 + c0 + j;
-          if (valid && j < lim && co < d.cout) a.z[zoff + (long long)co * HoWo] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j)
+            if (j < lim) zp[(long long)j * HoWo] = __uint_as_float(r[j]);
         }
       }
     }
