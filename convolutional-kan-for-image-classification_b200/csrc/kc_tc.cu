@@ -528,8 +528,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     // ================================ epilogue: TMEM -> registers -> z (fp32 NCHW) =====================
     // All 16 producer warps: warp w reads the TMEM lanes of its hardware quarter (w % 4) and every fourth group of 16
     // columns (w / 4); a store instruction writes one output channel of 32 consecutive positions (128 B).
+    Tracer tre(3, threadIdx.x == 0);
+    tre.stamp();                                     // producer work done
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    tre.stamp();                                     // accumulator ready
     const int HoWo = d.ho * d.wo;
     const int n0 = nt * g.ntile;
     const int quarter = warp & 3, cgrp = warp >> 2;
@@ -556,6 +559,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
         }
       }
     }
+    tre.stamp();                                     // z written
   }
   if (MODE == kModeDgrad && warp < 16) {
     // ================================ dgrad epilogue: dPhi (TMEM) x analytic basis derivative -> dx =======

@@ -63,6 +63,6 @@ def run_fwd_bwd(m, x, g):
 
 def rel_err(a, b):
     """max |a-b| / max |b| (scale-relative max error)."""
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     denom = float(b.abs().max())
     return float((a - b).abs().max()) / (denom if denom > 0 else 1.0)

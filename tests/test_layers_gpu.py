@@ -415,3 +415,55 @@ def test_max_pool_matches_aten_bit_exact(shape, k, s):
     assert torch.equal(xa.grad, xb.grad)
     m = KF.MaxPool2d(kernel_size=k, stride=s)
     assert torch.equal(torch.nan_to_num(m(x), nan=123.0), torch.nan_to_num(ya.detach(), nan=123.0))
+
+
+def _kan_conv_op_oracle(ora, x, g, k, pad):
+    """fp64 pre-norm output and gradients of a (possibly grouped) B-spline KAN convolution from the oracle's pieces."""
+    import torch.nn.functional as F
+    xx = x.double().requires_grad_(True)
+    G = len(ora.base_conv)
+    xs = torch.chunk(xx, G, dim=1)
+    zs = []
+    for gi in range(G):
+        wb, ws = ora.base_conv[gi].weight, ora.spline_conv[gi].weight
+        wb.grad = ws.grad = None
+        zs.append(F.conv2d(F.silu(xs[gi]), wb, padding=pad) + F.conv2d(O._expand(O.bspline_basis(xs[gi], ora.knots, 3)), ws, padding=pad))
+    z = torch.cat(zs, dim=1)
+    z.backward(g.double())
+    return z.detach(), xx.grad, [ora.base_conv[gi].weight.grad for gi in range(G)], [ora.spline_conv[gi].weight.grad for gi in range(G)]
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,k,pad,groups", [
+    (1, 8, 16, 1, 1, 1, 0, 1),          # a single pixel, pointwise
+    (2, 8, 16, 7, 5, 1, 0, 1),          # pointwise, ragged image
+    (3, 5, 7, 6, 9, 3, 1, 1),           # channel counts far from any tile size
+    (2, 16, 24, 12, 10, 3, 0, 1),       # "valid" convolution: output smaller than the input
+    (2, 8, 8, 11, 13, 5, 2, 1),         # 5x5 filter
+    (1, 12, 20, 10, 10, 3, 2, 1),       # padding wider than "same": output larger than the input
+    (2, 32, 48, 9, 9, 3, 1, 2),         # two groups
+    (2, 24, 24, 8, 8, 3, 1, 3),         # three groups
+    (1, 3, 300, 17, 19, 3, 1, 1),       # cout spans two N tiles, cin = 3 (first layer of the models)
+    (5, 72, 40, 3, 3, 3, 1, 1),         # image smaller than a tile row
+])
+def test_bf16_tensor_core_conv_op_odd_shapes(n, cin, cout, h, w, k, pad, groups):
+    """Forward, dgrad and wgrad of the tcgen05 kernels on shapes that stress tile edges: 1x1 / 5x5 filters, no / wide padding,
+    groups, ragged images, channel counts that are not multiples of the tile sizes."""
+    from kanconv_b200 import functional as KF
+    okw = dict(input_dim=cin, output_dim=cout, kernel_size=k, padding=pad, groups=groups)
+    ora, mod = _oracle_and_module("kan", dict(okw, base_activation="silu"), dict(okw, base_activation=nn.SiLU))
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    torch.manual_seed(5)
+    x = torch.randn(n, cin, h, w)
+    g = torch.randn(n, cout, ho, wo)
+    zo, dxo, gbo, gso = _kan_conv_op_oracle(ora, x, g, k, pad)
+    xg = x.cuda().requires_grad_(True)
+    wb = [m.weight for m in mod.base_conv]
+    ws = [m.weight for m in mod.spline_conv]
+    z = KF.kan_conv(mod._spec, xg, None, None, wb, ws, "bf16")      # "bf16": error out instead of falling back to FP32
+    z.backward(g.cuda())
+    errs = {"z": rel_err(z, zo), "dx": rel_err(xg.grad, dxo)}
+    for gi in range(groups):
+        errs[f"dw_base{gi}"] = rel_err(wb[gi].grad, gbo[gi])
+        errs[f"dw_spline{gi}"] = rel_err(ws[gi].grad, gso[gi])
+    print({k_: f"{v:.2e}" for k_, v in errs.items()})
+    assert max(errs.values()) < BF16_TOL, errs

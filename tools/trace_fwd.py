@@ -19,7 +19,7 @@ t = buf.cpu().view(4, 1024)
 t0 = int(t[t > 0].min())
 nsc = (cin + 7) // 8; nch = nsc + (cin // 8 + 7) // 8
 names = ["producer tp=0", "mma", "loader", "producer tp=300"]
-for role in (0, 3):
+for role in (0,):
     ev = [int(v) - t0 for v in t[role] if v > 0]
     print(names[role], "events", len(ev))
     for q in range(min(nch, 6)):
@@ -44,3 +44,4 @@ print("tap: copy_issued  b_full_seen  (latency)   next_copy_issue - this b_full"
 for k in range(36, min(54, len(lo), len(mma_tap))):
     print(f"  {k:3d}: {lo[k]:8d} {mma_tap[k]:8d}  ({mma_tap[k]-lo[k]:6d})")
 print("mma first/last events", mm[:3], mm[-3:], "producer last", [int(v) - t0 for v in t[0] if v > 0][-2:])
+print("epilogue (tid 0): producer done, acc ready, z written:", [int(v) - t0 for v in t[3] if v > 0])
