@@ -18,6 +18,7 @@
 // ~250 cycles of per-ring-step bookkeeping of one issuer would otherwise leave the pipe idle at small N.
 // The MMA issuer is the highest warp id on purpose: the scheduler arbitrates highest-warp-id-first, and the single issuing
 // thread must never wait behind the 16 ALU-heavy producer warps (measured: 245 -> ~50 cycles per tcgen05.mma).
+#include <limits.h>
 #include <string.h>
 
 #include "kc_common.cuh"
@@ -50,6 +51,8 @@ struct TcGeom {
   int SS, nrows, plane_bytes;
   int ntile, n_ntiles, tmem_cols, bstages, na;
   int tps;                     // filter taps per B ring stage (1, or kw = a whole filter row)
+  int cpt;                     // dgrad: input channels per N tile (16, or 14 for the persistent kernel with a base column)
+  int persistent;              // dgrad: 1 = kc_dgrad_persistent_kernel (double-buffered TMEM, epilogue overlaps the MMAs)
   long long mtiles;
   long long wimg_bytes_per_ntile;
   size_t smem_bytes;
@@ -716,6 +719,258 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Persistent dgrad (closed-form cubic basis): one CTA per SM walks the (position tile, channel tile) list.  The TMEM holds
+// TWO accumulator sets (2 sub-tiles x 128 columns each), so the 16 epilogue warps contract tile t with the basis
+// derivative while the MMA warps already accumulate tile t+1; dz rows are fed by four dedicated cp.async warps.
+//   warps 0-15 epilogue | 16-19 dz producers | 20 weight loader | 21-22 MMA issuers (one sub-tile each)
+// N tile = cpt channels x (nb + base) columns padded to 128 (14 channels with a base branch, 16 without).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kDgThreads = 640, kDgEpiWarps = 16, kDgProdWarp0 = 16, kDgLoaderWarp = 17, kDgMmaWarp0 = 18;
+constexpr int kDgBars = 2 * kMaxA + 2 * kMaxBStages + 4;
+
+__global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(const __grid_constant__ TcFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const kc_desc& d = a.d;
+  const TcGeom& g = a.g;
+  const int abuf_bytes = kPL * g.plane_bytes;
+  const int btap_bytes = kPL * g.ntile * 16;
+  const int bstage_bytes = g.tps * btap_bytes;
+  unsigned char* abuf0 = smem;
+  unsigned char* bst0 = abuf0 + g.na * abuf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bst0 + g.bstages * bstage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kMaxA;
+  uint64_t* b_full = bars + 2 * kMaxA;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* acc_full = b_empty + kMaxBStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kDgBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = d.kh * d.kw, HW = d.h * d.w;
+  const bool has_base = d.act != KC_ACT_NONE;
+  const int wb = d.nb + (has_base ? 1 : 0);
+  const int nchunks = g.nbc;
+  const long long ntiles = g.mtiles * g.n_ntiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], kDgEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == kDgMmaWarp0) tmem_alloc(tmem_ptr, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kDgProdWarp0) {
+    // ================================ dz loader: bulk copies (TMA engine) of the flat dz planes ====================
+    // The rows of a chunk are kh strips of consecutive flat positions per plane: lane (r, pl) copies strip r of plane pl
+    // with one cp.async.bulk.  Rows outside the flat sequence (first / last position tiles only) are zero-filled.
+    const int r = lane / kPL, pl = lane % kPL;
+    const int len = r < d.kh - 1 ? g.SS : g.nrows - (d.kh - 1) * g.SS;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    Tracer trp(0, lane == 0);
+    int buf = 0;
+    uint32_t ph = 1;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long qs = (tile / g.n_ntiles) * g.mcta - (long long)g.ph * g.P - g.pw + (long long)r * g.P;
+      long long lo = qs < 0 ? -qs : 0, hi = qs + len > g.L ? g.L - qs : len;
+      if (lo > len) lo = len;
+      if (hi < lo) hi = lo;
+      for (int q = 0; q < nchunks; ++q) {
+        const int ncols = chunk_cols(g, q);
+        const bool active = r < d.kh && pl < ncols;
+        trp.stamp();
+        mbar_wait(&a_empty[buf], ph);
+        trp.stamp();
+        unsigned char* dst = abuf0 + buf * abuf_bytes + pl * g.plane_bytes + (r * g.SS) * 16;
+        const bool edge = active && (lo > 0 || hi < len);
+        if (__any_sync(0xffffffffu, edge)) {
+          if (edge) {
+            for (int i = 0; i < (int)lo; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = zero4;
+            for (int i = (int)hi; i < len; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = zero4;
+          }
+          fence_proxy_async_smem();
+        }
+        const uint32_t mybytes = active ? (uint32_t)(hi - lo) * 16u : 0u;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, mybytes);
+        if (lane == 0) mbar_arrive_expect_tx(&a_full[buf], total);
+        __syncwarp();
+        if (mybytes != 0u)
+          bulk_g2s(dst + lo * 16, a.dzf + ((long long)(q * kPL + pl) * g.L + qs + lo) * 16, mybytes, &a_full[buf]);
+        if (++buf == g.na) { buf = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kDgLoaderWarp) {
+    // ================================ weight loader (TMA engine bulk copies) ==========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t bphase = 1;
+      Tracer trl(2, true);
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = (int)(tile % g.n_ntiles);
+        const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
+        for (int q = 0; q < nchunks; ++q) {
+          const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
+          for (int t = 0; t < T; t += g.tps) {
+            mbar_wait(&b_empty[stage], bphase);
+            trl.stamp();
+            mbar_arrive_expect_tx(&b_full[stage], bytes);
+            bulk_g2s(bst0 + stage * bstage_bytes, wsrc, bytes, &b_full[stage]);
+            wsrc += bytes;
+            if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kDgMmaWarp0) {
+    // ================================ MMA issuers: warp mw accumulates sub-tile mw ====================
+    const int mw = warp - kDgMmaWarp0;
+    const uint32_t idesc = make_idesc_bf16(kTileM, g.ntile, 0, 0);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_c = ((uint32_t)(g.plane_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t b_lo_c = ((uint32_t)(g.ntile) & 0x3FFFu) << 16;
+    const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * g.ntile);
+    const uint32_t abuf_u = smem_u32(abuf0) >> 4, bst_u = smem_u32(bst0) >> 4;
+    const uint32_t abuf_sz = (uint32_t)abuf_bytes >> 4, bst_sz = (uint32_t)bstage_bytes >> 4;
+    const int ntile = g.ntile, kw = d.kw, SS = g.SS, tps = g.tps;
+    int stage = 0, buf = 0;
+    uint32_t bphase = 0, aphase = 0;
+    uint32_t it = 0;
+    Tracer trm(1, lane == 0 && mw == 0);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      trm.stamp();                                           // tile start
+      mbar_wait(&acc_empty[acc], ((it >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator set
+      tc_fence_after();
+      trm.stamp();                                           // accumulator set free
+      const uint32_t tacc = tmem_base + acc * (uint32_t)(2 * ntile);
+      for (int q = 0; q < nchunks; ++q) {
+        const int nk2 = chunk_cols(g, q) >> 1;
+        const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);
+        mbar_wait(&a_full[buf], aphase);
+        tc_fence_after();
+        trm.stamp();                                         // a_full acquired
+        uint32_t arow = abuf_u + (uint32_t)buf * abuf_sz;
+        int s = 0;
+        for (int t = 0; t < T; t += tps) {
+          mbar_wait(&b_full[stage], bphase);
+          tc_fence_after();
+          trm.stamp();                                       // b_full acquired
+          uint32_t b_lo = b_lo_c + bst_u + (uint32_t)stage * bst_sz;
+          const bool two = nk2 == 2;
+          const bool leader = elect_one_sync();
+          for (int tt = 0; tt < tps; ++tt) {
+            const uint32_t first = (q | (t + tt)) != 0 ? 1u : 0u;
+            if (leader) issue_step<1>(tacc, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, 1);
+            b_lo += btap_u;
+            if (++s == kw) { s = 0; arow += (uint32_t)(SS - (kw - 1)); } else { arow += 1u; }
+          }
+          if (leader) {
+            tc_commit(&b_empty[stage]);
+            if (t + tps >= T) tc_commit(&a_empty[buf]);
+          }
+          __syncwarp();
+          if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
+        }
+        if (++buf == g.na) { buf = 0; aphase ^= 1; }
+      }
+      if (elect_one_sync()) tc_commit(&acc_full[acc]);
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue: dPhi (TMEM) x analytic basis derivative -> dx =========
+    // warp w: TMEM lanes of quarter w % 4, channel group w / 4 (cpt channels split 4 ways, 3 or 4 channels each)
+    const bool alias = a.dx_base == a.dx_basis, same_x = a.x_base == a.x_basis;
+    const int quarter = warp & 3, cgrp = warp >> 2;
+    const int chs = (cgrp * g.cpt) / 4, chn = ((cgrp + 1) * g.cpt) / 4 - chs;
+    const int nint = d.nparams - 1, act = d.act;
+    const float t0 = g.t0, inv_h = g.inv_h;
+    const long long nsteps = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * 2;     // (tile, sub-tile) pairs of this CTA
+    auto locate = [&](long long step, int& c0) -> int {           // x offset of this lane's position in step, or -1
+      const long long tile = blockIdx.x + (step >> 1) * gridDim.x;
+      const long long mt = tile / g.n_ntiles;
+      c0 = (int)(tile - mt * g.n_ntiles) * g.cpt + chs;
+      const long long q = mt * g.mcta + (step & 1) * kTileM + quarter * 32 + lane;
+      if (q >= g.L) return -1;
+      const unsigned uq = (unsigned)q, n = uq / (unsigned)g.IMG, rem = uq - n * (unsigned)g.IMG;
+      const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
+      return (y < (unsigned)d.h && x < (unsigned)d.w) ? (int)((long long)n * d.x_batch_stride + y * d.w + x) : -1;
+    };
+    auto fetch = [&](int off, int c0, float (&xv)[4]) {
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4)
+        xv[c4] = (off >= 0 && c4 < chn && c0 + c4 < d.cin) ? ldg_early(a.x_basis + off + (long long)(c0 + c4) * HW) : 0.0f;
+    };
+    auto ld9 = [&](uint32_t taddr, uint32_t (&r)[9]) {
+      tmem_ld8(taddr, r);
+      if (has_base) tmem_ld1(taddr + 8u, r + 8); else r[8] = 0u;
+    };
+    Tracer tre(3, threadIdx.x == 0);
+    float xn[4];
+    int c0n = 0;
+    int offn = nsteps > 0 ? locate(0, c0n) : -1;
+    fetch(offn, c0n, xn);
+#pragma unroll 1
+    for (long long step = 0; step < nsteps; ++step) {
+      const uint32_t it = (uint32_t)(step >> 1), acc = it & 1u, sub = (uint32_t)(step & 1);
+      float xc[4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) xc[c4] = xn[c4];
+      const int off = offn, c0 = c0n;
+      if (step + 1 < nsteps) { offn = locate(step + 1, c0n); fetch(offn, c0n, xn); }
+      if (sub == 0) {
+        tre.stamp();
+        mbar_wait(&acc_full[acc], (it >> 1) & 1u);
+        tc_fence_after();
+        tre.stamp();                                           // accumulator ready
+      }
+      const int nch = min(chn, d.cin - c0);                      // warp-uniform, may be <= 0
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)(2 * g.ntile) + sub * (uint32_t)g.ntile +
+                            (uint32_t)(chs * wb);
+      auto emit = [&](int c4, const uint32_t (&r)[9]) {
+        if (off < 0) return;
+        const long long o = off + (long long)(c0 + c4) * HW;
+        const float gs = cubic8_dot_grad(xc[c4], t0, inv_h, nint, r);
+        float gb = 0.0f;
+        if (has_base) gb = __uint_as_float(r[8]) * act_grad_fast(act, same_x ? xc[c4] : __ldg(a.x_base + o));
+        if (alias) {
+          a.dx_basis[o] = gs + gb;
+        } else {
+          a.dx_basis[o] = gs;
+          if (has_base && a.dx_base != nullptr) a.dx_base[o] = gb;
+        }
+      };
+      uint32_t ra[9], rb[9];
+      if (nch > 0) ld9(trow, ra);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4 += 2) {
+        if (c4 + 1 < nch) ld9(trow + (uint32_t)((c4 + 1) * wb), rb);
+        if (c4 < nch) emit(c4, ra);
+        tmem_ld_wait();
+        if (c4 + 2 < nch) ld9(trow + (uint32_t)((c4 + 2) * wb), ra);
+        if (c4 + 1 < nch) emit(c4 + 1, rb);
+        tmem_ld_wait();
+      }
+      if (sub == 1) {                                            // both sub-tiles of this accumulator set are in registers / stored
+        tre.stamp();                                             // tile written
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kDgMmaWarp0) tmem_dealloc(tmem_base, 512u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // weight packing: fp32 reference layout -> bf16 K-major no-swizzle images [ntile][chunk][tap][k-core][cout][8]
 // ---------------------------------------------------------------------------------------------------------
 struct TcPackArgs { kc_desc d; TcGeom g; const float* w_base; const float* w_basis; uint4* out; };
@@ -853,13 +1108,13 @@ __global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constan
     const int kc = rem / g.ntile, nl = rem - kc * g.ntile;
     const int ncols = (bq == g.nbc - 1) ? g.last_base_cols : kPL;
     if (kc >= ncols) continue;
-    const int c = nt * 16 + nl / wb, jj = nl % wb;
+    const int cl = nl / wb, c = nt * g.cpt + cl, jj = nl % wb;
     const float* src[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int co = (bq * kPL + kc) * 8 + e;
       src[e] = nullptr;
-      if (co < d.cout && c < d.cin)
+      if (co < d.cout && c < d.cin && cl < g.cpt)
         src[e] = jj < nb ? a.w_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, jj, d.cin, nb)) * T
                          : a.w_base + ((long long)co * d.cin + c) * T;
     }
@@ -1005,6 +1260,38 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
   g->IMG = (d->h + d->pad_h) * g->P;
   g->L = (long long)d->n * g->IMG;
   if (g->L >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core dgrad needs < 2^31 flat positions");
+  // Persistent kernel (closed-form cubic basis): N tile = cpt channels x wb columns padded to 128, two sub-tiles per
+  // accumulator set, two sets in TMEM (4 x 128 = 512 columns).
+  float t0, inv_h;
+  if (knots_uniform_cubic(d, &t0, &inv_h) && d->kh * d->kw <= 64) {
+    const int cpt = 128 / wb, ntile = 128;
+    const int mcta = 2 * kTileM;
+    const int seglen = round_up(mcta + d->kw - 1, 8);
+    const int SS = g->P < seglen ? g->P : seglen;
+    const int nrows = (d->kh - 1) * SS + seglen;
+    const int plane_bytes = nrows * 16 + 16;
+    const size_t btap = (size_t)kPL * ntile * 16;
+    const size_t fixed0 = (size_t)kDgBars * 8 + 16 + 128;
+    if (d->kh * kPL <= 32) {
+      const int cand_na[4] = {3, 2, 3, 2}, cand_tps[4] = {d->kw, d->kw, 1, 1};
+      for (int ci = 0; ci < 4; ++ci) {
+        const int na = cand_na[ci], tps = cand_tps[ci];
+        if (ci >= 2 && d->kw == 1) break;
+        const size_t fixed = fixed0 + (size_t)na * kPL * plane_bytes;
+        const size_t bstage = btap * tps;
+        if (fixed + (tps == 1 ? 6 : 4) * bstage > kSmemLimit) continue;
+        int bst = (int)((kSmemLimit - fixed) / bstage);
+        if (bst > kMaxBStages) bst = kMaxBStages;
+        g->persistent = 1; g->cpt = cpt; g->ntile = ntile; g->n_ntiles = (d->cin + cpt - 1) / cpt;
+        g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps; g->na = na;
+        g->bstages = bst; g->mtiles = (g->L + mcta - 1) / mcta; g->smem_bytes = fixed + bst * bstage; g->tmem_cols = 512;
+        g->wimg_bytes_per_ntile = (long long)T * ntile * 16 * planes;
+        g->fast_cubic = 1; g->t0 = t0; g->inv_h = inv_h;
+        return KC_OK;
+      }
+    }
+  }
+  g->cpt = 16;
   g->ntile = 16 * wb;
   g->n_ntiles = (d->cin + 15) / 16;
   return tc_fit(d, g, T, planes);
@@ -1246,6 +1533,16 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.wp = (const unsigned char*)packed_dgrad; a.beta = beta;
   a.dzf = (const unsigned char*)workspace; a.cq = g.Cp; a.dx_base = dx_base; a.dx_basis = dx_basis;
   a.dbeta = (d->basis == KC_BASIS_GRAM) ? dbeta : nullptr;
+  if (g.persistent) {
+    int dev = 0, sms = 148;
+    KC_CUDA_CHECK(cudaGetDevice(&dev));
+    KC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long ntiles = g.mtiles * g.n_ntiles;
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kc_dgrad_persistent_kernel<<<(unsigned)(ntiles < sms ? ntiles : sms), kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    KC_LAUNCH_CHECK("kc_dgrad_persistent_kernel");
+    return KC_OK;
+  }
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
   kc_tc_kernel<kModeDgrad><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);

@@ -1,4 +1,5 @@
-"""Timeline of one CTA of the dgrad kernel (debug)."""
+"""Timeline of one CTA of the dgrad kernel (debug).  Persistent kernel: per tile the MMA warp stamps [tile start, accumulator
+free, then per chunk: a_full, b_full x stages]; the epilogue stamps [wait start, accumulator ready, tile written]."""
 import argparse, ctypes, os, sys
 import torch, torch.nn as nn
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,4 +20,6 @@ t = buf.cpu().view(4, 1024)
 t0 = int(t[t > 0].min())
 for role, name in ((0, "producer t0"), (1, "mma w0"), (2, "loader"), (3, "epilogue t0")):
     ev = [int(v) - t0 for v in t[role] if v > 0]
-    print(name, len(ev), ev[:44])
+    print(name, len(ev), ev[:60])
+    if role in (1, 2) and len(ev) > 3:
+        print("   gaps", [ev[i + 1] - ev[i] for i in range(min(len(ev) - 1, 70))])
