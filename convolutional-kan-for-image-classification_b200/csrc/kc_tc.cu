@@ -1687,6 +1687,80 @@ extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, int nsub, int 
   return KC_OK;
 }
 
+// Debug only: does the A-operand collector hint relieve the shared-memory bound of narrow MMAs?  Pattern of the weight-
+// gradient kernel: per k-step one A tile feeds three MMAs (three taps = three accumulators, B read from shifted rows).
+__global__ void __launch_bounds__(576, 1) kc_mma_rate3_kernel(int N, int mn_major, int iters, int reuse, int writers, float* out) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); done = 0; fence_barrier_init(); }
+  if (warp == 17) tmem_alloc(&tmem_ptr, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_ptr;
+  if (warp == 17) {
+    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
+    const uint32_t au = smem_u32(sm) >> 4, bu = (smem_u32(sm) + 100 * 1024) >> 4;
+    const uint32_t a_pitch = mn_major ? 1168u : 15456u, b_pitch = mn_major ? 1168u : (uint32_t)N * 16u + 64u;
+    const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
+    const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
+    const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + (ks & 1) * a_step + (ks >> 1) * 3u));
+          const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + (ks & 1) * b_step));
+          if (reuse) {
+            tc_mma_bf16_keep<1>(tb, ad, bd, idesc, 1u);
+            tc_mma_bf16_keep<2>(tb + N, ad, bd + 1u, idesc, 1u);
+            tc_mma_bf16_keep<3>(tb + 2 * N, ad, bd + 2u, idesc, 1u);
+          } else {
+            tc_mma_bf16(tb, ad, bd, idesc, 1u);
+            tc_mma_bf16(tb + N, ad, bd + 1u, idesc, 1u);
+            tc_mma_bf16(tb + 2 * N, ad, bd + 2u, idesc, 1u);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) tc_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 17 * 32) { out[0] = (float)(t1 - t0) / (float)(iters * 12); done = 1; }
+  } else if (warp < writers) {
+    uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + threadIdx.x;
+    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+    while (!done) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[(k * 512) & 1023] = v;
+      v.x += 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc(tb, 512);
+}
+
+extern "C" int kc_debug_mma_rate3(int N, int mn_major, int iters, int reuse, int writers, float* cycles) {
+  float* dev = nullptr;
+  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  kc_mma_rate3_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, reuse, writers, dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate3: %s", cudaGetErrorString(e));
+  return KC_OK;
+}
+
 // Debug only: latency / throughput of cp.async.bulk global->shared.  Each CTA issues `depth` copies of `bytes` back to back
 // (ring of `depth` buffers), `iters` rounds; same_addr != 0 makes every CTA read the same global range.
 __global__ void __launch_bounds__(32, 1) kc_bulk_bench_kernel(const unsigned char* src, int bytes, int depth, int iters,

@@ -14,3 +14,13 @@ def run(N, mn=0, nsub=1, commit=0, writers=0, shift=0, iters=256):
 for N, ns in ((64, 4), (128, 4), (144, 3), (256, 2)):
     print(f"N={N} (floor {N//2}): 1 acc {run(N)} | {ns} acc {run(N, 0, ns)} | +commit/step {run(N, 0, ns, 1)} | +shift 1 row {run(N, 0, ns, 1, 0, 1)}"
           f" | +4 writer warps {run(N, 0, ns, 1, 4, 1)} | +16 writer warps {run(N, 0, ns, 1, 16, 1)} | MN-major {run(N, 1, min(ns, 3), 1)}")
+g = lib.kc_debug_mma_rate3
+g.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_float)]
+def run3(N, mn, reuse, writers=0, iters=256):
+    c = ctypes.c_float()
+    assert g(N, mn, iters, reuse, writers, ctypes.byref(c)) == 0, lib.kc_last_error()
+    return round(c.value, 1)
+print("A shared by three MMAs (wgrad pattern), cycles per MMA: plain | collector fill/use/lastuse | same with 16 writer warps")
+for N in (64, 128, 160):
+    for mn in (0, 1):
+        print(f"  N={N} {'MN' if mn else 'K '}-major: {run3(N, mn, 0)} | {run3(N, mn, 1)} | {run3(N, mn, 0, 16)} -> {run3(N, mn, 1, 16)}")
