@@ -444,6 +444,10 @@ def _kan_conv_op_oracle(ora, x, g, k, pad):
     (2, 24, 24, 8, 8, 3, 1, 3),         # three groups
     (1, 3, 300, 17, 19, 3, 1, 1),       # cout spans two N tiles, cin = 3 (first layer of the models)
     (5, 72, 40, 3, 3, 3, 1, 1),         # image smaller than a tile row
+    (1, 8, 16, 12, 600, 3, 1, 1),       # rows wider than a position tile: the filter rows of a tile are separate strips
+    (1, 16, 8, 70, 300, 3, 1, 1),       # strips in the dgrad tiles only (row pitch between 264 and 520)
+    (3, 40, 24, 33, 47, 3, 1, 1),       # more tiles than fit one wave of the persistent dgrad, ragged last tiles
+    (2, 16, 16, 9, 9, 3, 1, 1),         # a single 32-cout chunk (shortest K loop)
 ])
 def test_bf16_tensor_core_conv_op_odd_shapes(n, cin, cout, h, w, k, pad, groups):
     """Forward, dgrad and wgrad of the tcgen05 kernels on shapes that stress tile edges: 1x1 / 5x5 filters, no / wide padding,
