@@ -497,7 +497,7 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->nbc = has_base ? (d->cin + 127) / 128 : 0;
   g->nchunks = g->nsc + g->nbc;
   int nmax = (512 / d->kw) / 16 * 16;
-  if (nmax > 256) nmax = 256;
+  if (nmax > 192) nmax = 192;            // 64 positions x (ntile / 8) dz planes must fit the producer mapping (3 vectors per thread)
   int want = (g->cq + nmax - 1) / nmax;
   g->ntile = round_up_w((g->cq + want - 1) / want, 16);
   g->n_ct = (g->cq + g->ntile - 1) / g->ntile;
