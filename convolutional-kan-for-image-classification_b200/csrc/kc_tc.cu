@@ -546,7 +546,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       if (q < g.L) {
         const unsigned uq = (unsigned)q, n = uq / (unsigned)g.IMG, rem = uq - n * (unsigned)g.IMG;
         const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
-        if (y < (unsigned)d.ho && x < (unsigned)d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + y * d.wo + x; }
+        unsigned yo = y, xo = x;
+        bool on_grid = true;
+        if (d.stride_h != 1 || d.stride_w != 1) {
+          yo = y / (unsigned)d.stride_h; xo = x / (unsigned)d.stride_w;
+          on_grid = yo * (unsigned)d.stride_h == y && xo * (unsigned)d.stride_w == x;
+        }
+        if (on_grid && yo < (unsigned)d.ho && xo < (unsigned)d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + yo * d.wo + xo; }
       }
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * g.ntile);
       for (int c0 = cgrp * 16; c0 < g.ntile; c0 += 64) {
@@ -1150,8 +1156,9 @@ __global__ void __launch_bounds__(256) kc_dz_flat_kernel(const __grid_constant__
   const int n = (int)(q / IMG);
   const int rem = (int)(q - (long long)n * IMG);
   const int y = rem / P, x = rem - y * P;
-  if (y < d.ho && x < d.wo) {
-    const float* src = dz + (long long)n * d.z_batch_stride + y * d.wo + x;
+  const int yo = y / d.stride_h, xo = x / d.stride_w;
+  if (yo * d.stride_h == y && xo * d.stride_w == x && yo < d.ho && xo < d.wo) {
+    const float* src = dz + (long long)n * d.z_batch_stride + yo * d.wo + xo;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       if (pl * 8 + e < d.cout) f[e] = __ldg(src + (long long)(pl * 8 + e) * HoWo);
@@ -1236,7 +1243,11 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
 }
 
 int tc_common_checks(const kc_desc* d) {
-  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs stride 1 and dilation 1");
+  // A strided convolution is the stride-1 convolution sampled at every stride-th position: the kernels run on the stride-1
+  // position grid, the forward epilogue stores only the sampled outputs and dz_flat scatters dz onto that grid (zeros in
+  // between).  Costs stride_h * stride_w times the MMA work - meant for the strided stem / downsampling layers of a model.
+  if (d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs dilation 1");
+  if (d->stride_h < 1 || d->stride_w < 1 || d->stride_h > 4 || d->stride_w > 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs stride <= 4");
   if (d->nb < 1 || d->nb > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs basis width <= 8 (got %d)", d->nb);
   if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs padding < kernel size");
   if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core path needs kernel size <= 8");

@@ -480,7 +480,8 @@ bool knots_uniform_cubic_w(const kc_desc* d, float* t0, float* inv_h) {
 }
 
 int wgrad_geometry(const kc_desc* d, WgGeom* g) {
-  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs stride 1 and dilation 1");
+  if (d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs dilation 1");
+  if (d->stride_h < 1 || d->stride_w < 1 || d->stride_h > 4 || d->stride_w > 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs stride <= 4");
   if (d->nb < 1 || d->nb > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs basis width <= 8 (got %d)", d->nb);
   if (d->pad_h > d->kh - 1 || d->pad_w > d->kw - 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs padding < kernel size");
   if (d->kw > 8 || d->kh > 8) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs kernel size <= 8");

@@ -417,7 +417,7 @@ def test_max_pool_matches_aten_bit_exact(shape, k, s):
     assert torch.equal(torch.nan_to_num(m(x), nan=123.0), torch.nan_to_num(ya.detach(), nan=123.0))
 
 
-def _kan_conv_op_oracle(ora, x, g, k, pad):
+def _kan_conv_op_oracle(ora, x, g, k, pad, stride=1):
     """fp64 pre-norm output and gradients of a (possibly grouped) B-spline KAN convolution from the oracle's pieces."""
     import torch.nn.functional as F
     xx = x.double().requires_grad_(True)
@@ -427,7 +427,8 @@ def _kan_conv_op_oracle(ora, x, g, k, pad):
     for gi in range(G):
         wb, ws = ora.base_conv[gi].weight, ora.spline_conv[gi].weight
         wb.grad = ws.grad = None
-        zs.append(F.conv2d(F.silu(xs[gi]), wb, padding=pad) + F.conv2d(O._expand(O.bspline_basis(xs[gi], ora.knots, 3)), ws, padding=pad))
+        zs.append(F.conv2d(F.silu(xs[gi]), wb, padding=pad, stride=stride) +
+                  F.conv2d(O._expand(O.bspline_basis(xs[gi], ora.knots, 3)), ws, padding=pad, stride=stride))
     z = torch.cat(zs, dim=1)
     z.backward(g.double())
     return z.detach(), xx.grad, [ora.base_conv[gi].weight.grad for gi in range(G)], [ora.spline_conv[gi].weight.grad for gi in range(G)]
@@ -469,5 +470,32 @@ def test_bf16_tensor_core_conv_op_odd_shapes(n, cin, cout, h, w, k, pad, groups)
     for gi in range(groups):
         errs[f"dw_base{gi}"] = rel_err(wb[gi].grad, gbo[gi])
         errs[f"dw_spline{gi}"] = rel_err(ws[gi].grad, gso[gi])
+    print({k_: f"{v:.2e}" for k_, v in errs.items()})
+    assert max(errs.values()) < BF16_TOL, errs
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,k,pad,stride", [
+    (2, 3, 32, 33, 31, 3, 1, 2),        # strided stem of the MobileNetV2 stack, odd image size
+    (2, 16, 24, 16, 16, 3, 1, 2),
+    (1, 8, 8, 15, 14, 1, 0, 2),         # strided pointwise
+    (2, 8, 16, 20, 20, 3, 1, 3),
+])
+def test_bf16_tensor_core_strided_conv_op(n, cin, cout, h, w, k, pad, stride):
+    """Strided convolutions run on the tensor cores as the stride-1 convolution sampled on the stride grid: z, dX and dW
+    against the fp64 oracle."""
+    from kanconv_b200 import functional as KF
+    okw = dict(input_dim=cin, output_dim=cout, kernel_size=k, padding=pad, stride=stride)
+    ora, mod = _oracle_and_module("kan", dict(okw, base_activation="silu"), dict(okw, base_activation=nn.SiLU))
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    torch.manual_seed(6)
+    x = torch.randn(n, cin, h, w)
+    g = torch.randn(n, cout, ho, wo)
+    zo, dxo, gbo, gso = _kan_conv_op_oracle(ora, x, g, k, pad, stride)
+    xg = x.cuda().requires_grad_(True)
+    wb, ws = [mod.base_conv[0].weight], [mod.spline_conv[0].weight]
+    z = KF.kan_conv(mod._spec, xg, None, None, wb, ws, "bf16")
+    assert z.shape == zo.shape
+    z.backward(g.cuda())
+    errs = {"z": rel_err(z, zo), "dx": rel_err(xg.grad, dxo), "dw_base": rel_err(wb[0].grad, gbo[0]), "dw_spline": rel_err(ws[0].grad, gso[0])}
     print({k_: f"{v:.2e}" for k_, v in errs.items()})
     assert max(errs.values()) < BF16_TOL, errs
