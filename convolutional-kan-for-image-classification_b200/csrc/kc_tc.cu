@@ -1200,8 +1200,13 @@ __global__ void __launch_bounds__(256) kc_dz_flat_kernel(const __grid_constant__
   const int n = (int)(q / IMG);
   const int rem = (int)(q - (long long)n * IMG);
   const int y = rem / P, x = rem - y * P;
-  const int yo = y / d.stride_h, xo = x / d.stride_w;
-  if (yo * d.stride_h == y && xo * d.stride_w == x && yo < d.ho && xo < d.wo) {
+  int yo = y, xo = x;
+  bool on_grid = true;
+  if (d.stride_h != 1 || d.stride_w != 1) {       // strided layer: dz lives on every stride-th position of the stride-1 grid
+    yo = y / d.stride_h; xo = x / d.stride_w;
+    on_grid = yo * d.stride_h == y && xo * d.stride_w == x;
+  }
+  if (on_grid && yo < d.ho && xo < d.wo) {
     const float* src = dz + (long long)n * d.z_batch_stride + yo * d.wo + xo;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
