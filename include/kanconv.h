@@ -136,8 +136,10 @@ int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, cons
                     float* dbeta, float* dalpha, float* partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * BF16 tensor-core path (tcgen05.mma, fp32 accumulate in TMEM).  Stride 1, dilation 1, nb in {4, 8},
- * cin % 8 == 0 after the binding's zero padding.  kc_tc_supported() tells the binding which path a shape takes.
+ * BF16 tensor-core path (tcgen05.mma, fp32 accumulate in TMEM).  Dilation 1, stride 1..4 (a strided layer runs on the
+ * stride-1 position grid and stores the sampled outputs), kernel size <= 8, padding < kernel size, basis width
+ * nb <= 8 (zero-padded to 4 or 8 inside), any channel counts.  kc_tc_supported() tells the binding which path a
+ * shape takes.
  * Parity target: <= 2e-2 relative / 1e-3 absolute to the reference fp32 modules.
  * ------------------------------------------------------------------------------------------------------- */
 int kc_tc_supported(const kc_desc* d);
