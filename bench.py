@@ -247,20 +247,42 @@ def run_b200(args):
     # ---- end-to-end leg: host inputs, H2D per step, loss read back per step ----------------------------------------
     for _ in range(min(2, args.warmup)):
         step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item()
-    barrier()
-    t0 = time.perf_counter()
     f0 = torch.cuda.Event(enable_timing=True)
     f1 = torch.cuda.Event(enable_timing=True)
+    # Every step's batch is copied from pinned host memory inside the timed region and every step's loss is copied back to
+    # pinned host memory.  Like a prefetching data loader, the copy of step i+1 runs on a second stream while step i
+    # computes (two device buffers), and the loss read-back is asynchronous (checked when the loop ends), so the GPU never
+    # waits for the host between steps.
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            if i >= 2:
+                copy_stream.wait_event(consumed[i % 2])      # step i-2 has finished reading this buffer
+            bufs[i % 2][0].copy_(x_host, non_blocking=True)
+            bufs[i % 2][1].copy_(y_host, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    barrier()
+    t0 = time.perf_counter()
     f0.record()
-    last = 0.0
-    for _ in range(args.steps):
-        xb = x_host.to(dev, non_blocking=True)
-        yb = y_host.to(dev, non_blocking=True)
-        last = step(xb, yb).item()              # device -> host read of the loss
+    prefetch(0)
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        loss = step(*bufs[i % 2])
+        consumed[i % 2].record()
+        loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)      # device -> host read of the loss
+        if i + 1 < args.steps:
+            prefetch(i + 1)
     f1.record()
     barrier()
     ms_e2e = max_over_ranks(f0.elapsed_time(f1)) / args.steps
     wall_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+    last = float(loss_host[-1])
 
     # ---- roofline of the dominant kernel (instrumented pass of the same step, CUDA events per library call) --------
     KF.profile_begin()
