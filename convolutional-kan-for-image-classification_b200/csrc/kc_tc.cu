@@ -768,6 +768,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
+// d(basis_j)/dx for the RBF and Chebyshev families, j < 8, registers only (every index is a compile-time constant):
+// the epilogue of the persistent dgrad for the layers that have no closed-form cubic basis.
+__device__ __forceinline__ void tc_basis_grad8(const KcBasisCtx& B, float x, float (&dphi)[8]) {
+  const int nb = B.nb;
+  if (B.kind == KC_BASIS_RBF) {
+    const float inv_den = __fdividef(1.0f, B.p[nb]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float q = (x - B.p[j]) * inv_den;
+      dphi[j] = j < nb ? __expf(-(q * q)) * (-2.0f * q * inv_den) : 0.0f;
+    }
+  } else {      // KC_BASIS_CHEBY: d T_j(c) / dx = j U_{j-1}(c) (1 - t^2), c = clamp(tanh x)
+    const float lo = -1.0f + 1e-7f, hi = 1.0f - 1e-7f;
+    const float t = tc_tanh(x);
+    float c = fminf(fmaxf(t, lo), hi);
+    if (t != t) c = t;
+    const float dc = (t < lo || t > hi) ? 0.0f : 1.0f - t * t;
+    float U0 = 0.0f, U1 = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dphi[j] = j < nb ? (float)j * U0 * dc : 0.0f;
+      const float U2 = 2.0f * c * U1 - U0;
+      U0 = U1; U1 = U2;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Persistent dgrad (closed-form cubic basis): one CTA per SM walks the (position tile, channel tile) list.  The TMEM holds
 // TWO accumulator sets (2 sub-tiles x 128 columns each), so the 16 epilogue warps contract tile t with the basis
@@ -778,6 +805,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 constexpr int kDgThreads = 640, kDgEpiWarps = 16, kDgProdWarp0 = 16, kDgLoaderWarp = 17, kDgMmaWarp0 = 18;
 constexpr int kDgBars = 2 * kMaxA + 2 * kMaxBStages + 4;
 
+template <bool CUBIC>
 __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(const __grid_constant__ TcFwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
@@ -795,6 +823,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   uint64_t* acc_full = b_empty + kMaxBStages;      // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kDgBars);
+  KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);      // !CUBIC only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = d.kh * d.kw, HW = d.h * d.w;
@@ -802,6 +831,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   const int wb = d.nb + (has_base ? 1 : 0);
   const int nchunks = g.nbc;
   const long long ntiles = g.mtiles * g.n_ntiles;
+  if (!CUBIC) kc_load_basis_ctx(B, d, a.beta);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
@@ -934,11 +964,12 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     }
   } else {
     // ================================ epilogue: dPhi (TMEM) x analytic basis derivative -> dx =========
-    // warp w: TMEM lanes of quarter w % 4, channel group w / 4 (cpt channels split 4 ways, 3 or 4 channels each)
+    // warp w: TMEM lanes of quarter w % 4, channel group w / 4 (the cpt channels of the tile are split four ways)
+    constexpr int kCh = CUBIC ? 4 : 8;                             // channels per warp (cpt <= 4 * kCh)
     const bool alias = a.dx_base == a.dx_basis, same_x = a.x_base == a.x_basis;
     const int quarter = warp & 3, cgrp = warp >> 2;
     const int chs = (cgrp * g.cpt) / 4, chn = ((cgrp + 1) * g.cpt) / 4 - chs;
-    const int nint = d.nparams - 1, act = d.act;
+    const int nint = d.nparams - 1, act = d.act, nb = d.nb;
     const float t0 = g.t0, inv_h = g.inv_h;
     const long long nsteps = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * 2;     // (tile, sub-tile) pairs of this CTA
     auto locate = [&](long long step, int& c0) -> int {           // x offset of this lane's position in step, or -1
@@ -951,26 +982,26 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
       return (y < (unsigned)d.h && x < (unsigned)d.w) ? (int)((long long)n * d.x_batch_stride + y * d.w + x) : -1;
     };
-    auto fetch = [&](int off, int c0, float (&xv)[4]) {
+    auto fetch = [&](int off, int c0, float (&xv)[kCh]) {
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4)
+      for (int c4 = 0; c4 < kCh; ++c4)
         xv[c4] = (off >= 0 && c4 < chn && c0 + c4 < d.cin) ? ldg_early(a.x_basis + off + (long long)(c0 + c4) * HW) : 0.0f;
     };
-    auto ld9 = [&](uint32_t taddr, uint32_t (&r)[9]) {
+    auto ld9 = [&](uint32_t taddr, uint32_t (&r)[9]) {            // the wb <= 9 gradient columns of one channel
       tmem_ld8(taddr, r);
-      if (has_base) tmem_ld1(taddr + 8u, r + 8); else r[8] = 0u;
+      if (wb > 8) tmem_ld1(taddr + 8u, r + 8); else r[8] = 0u;
     };
     Tracer tre(3, threadIdx.x == 0);
-    float xn[4];
+    float xn[kCh];
     int c0n = 0;
     int offn = nsteps > 0 ? locate(0, c0n) : -1;
     fetch(offn, c0n, xn);
 #pragma unroll 1
     for (long long step = 0; step < nsteps; ++step) {
       const uint32_t it = (uint32_t)(step >> 1), acc = it & 1u, sub = (uint32_t)(step & 1);
-      float xc[4];
+      float xc[kCh];
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) xc[c4] = xn[c4];
+      for (int c4 = 0; c4 < kCh; ++c4) xc[c4] = xn[c4];
       const int off = offn, c0 = c0n;
       if (step + 1 < nsteps) { offn = locate(step + 1, c0n); fetch(offn, c0n, xn); }
       if (sub == 0) {
@@ -985,9 +1016,23 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       auto emit = [&](int c4, const uint32_t (&r)[9]) {
         if (off < 0) return;
         const long long o = off + (long long)(c0 + c4) * HW;
-        const float gs = cubic8_dot_grad(xc[c4], t0, inv_h, nint, r);
+        float gs, ga;                                           // spline-branch gradient, incoming base-branch gradient
+        if (CUBIC) {
+          gs = cubic8_dot_grad(xc[c4], t0, inv_h, nint, r);
+          ga = __uint_as_float(r[8]);
+        } else {
+          float dphi[8];
+          tc_basis_grad8(*B, xc[c4], dphi);
+          gs = 0.0f;
+          ga = __uint_as_float(r[8]);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            gs = fmaf(__uint_as_float(r[jj]), dphi[jj], gs);      // dphi is zero for jj >= nb
+            if (jj == nb) ga = __uint_as_float(r[jj]);
+          }
+        }
         float gb = 0.0f;
-        if (has_base) gb = __uint_as_float(r[8]) * act_grad_fast(act, same_x ? xc[c4] : __ldg(a.x_base + o));
+        if (has_base) gb = ga * act_grad_fast(act, same_x ? xc[c4] : __ldg(a.x_base + o));
         if (alias) {
           a.dx_basis[o] = gs + gb;
         } else {
@@ -999,7 +1044,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       if (nch > 0) ld9(trow, ra);
       tmem_ld_wait();
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4 += 2) {
+      for (int c4 = 0; c4 < kCh; c4 += 2) {
         if (c4 + 1 < nch) ld9(trow + (uint32_t)((c4 + 1) * wb), rb);
         if (c4 < nch) emit(c4, ra);
         tmem_ld_wait();
@@ -1322,16 +1367,22 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
   if (g->L >= (1LL << 31)) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core dgrad needs < 2^31 flat positions");
   // Persistent kernel (closed-form cubic basis): N tile = cpt channels x wb columns padded to 128, two sub-tiles per
   // accumulator set, two sets in TMEM (4 x 128 = 512 columns).
-  float t0, inv_h;
-  if (knots_uniform_cubic(d, &t0, &inv_h) && d->kh * d->kw <= 64) {
-    const int cpt = 128 / wb, ntile = 128;
+  float t0 = 0.0f, inv_h = 0.0f;
+  const bool cubic = knots_uniform_cubic(d, &t0, &inv_h);
+  if ((cubic || d->basis == KC_BASIS_RBF || d->basis == KC_BASIS_CHEBY) && d->kh * d->kw <= 64) {
+    // channels per N tile: cpt * wb <= 128 columns, <= 4 (8) channels per epilogue warp, and the 8-column TMEM read of the
+    // last channel must stay inside the tile ((cpt - 1) * wb + 8 <= 128)
+    int cpt = 128 / wb;
+    if (cpt > 120 / wb + 1) cpt = 120 / wb + 1;
+    if (cpt > (cubic ? 16 : 32)) cpt = cubic ? 16 : 32;
+    const int ntile = 128;
     const int mcta = 2 * kTileM;
     const int seglen = round_up(mcta + d->kw - 1, 8);
     const int SS = g->P < seglen ? g->P : seglen;
     const int nrows = (d->kh - 1) * SS + seglen;
     const int plane_bytes = nrows * 16 + 16;
     const size_t btap = (size_t)kPL * ntile * 16;
-    const size_t fixed0 = (size_t)kDgBars * 8 + 16 + 128;
+    const size_t fixed0 = (size_t)kDgBars * 8 + 16 + sizeof(KcBasisCtx) + 128;
     if (d->kh * kPL <= 32) {
       const int cand_na[4] = {3, 2, 3, 2}, cand_tps[4] = {d->kw, d->kw, 1, 1};
       for (int ci = 0; ci < 4; ++ci) {
@@ -1346,7 +1397,7 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
         g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps; g->na = na;
         g->bstages = bst; g->mtiles = (g->L + mcta - 1) / mcta; g->smem_bytes = fixed + bst * bstage; g->tmem_cols = 512;
         g->wimg_bytes_per_ntile = (long long)T * ntile * 16 * planes;
-        g->fast_cubic = 1; g->t0 = t0; g->inv_h = inv_h;
+        g->fast_cubic = cubic ? 1 : 0; g->t0 = t0; g->inv_h = inv_h;
         return KC_OK;
       }
     }
@@ -1598,8 +1649,14 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
     KC_CUDA_CHECK(cudaGetDevice(&dev));
     KC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long ntiles = g.mtiles * g.n_ntiles;
-    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    kc_dgrad_persistent_kernel<<<(unsigned)(ntiles < sms ? ntiles : sms), kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    const unsigned nctas = (unsigned)(ntiles < sms ? ntiles : sms);
+    if (g.fast_cubic) {
+      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      kc_dgrad_persistent_kernel<true><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    } else {
+      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      kc_dgrad_persistent_kernel<false><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    }
     KC_LAUNCH_CHECK("kc_dgrad_persistent_kernel");
     return KC_OK;
   }
