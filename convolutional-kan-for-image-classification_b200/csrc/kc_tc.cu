@@ -176,6 +176,33 @@ __device__ inline void tc_eval_basis(const KcBasisCtx& B, float x, float* phi, f
 
 // generic (any family) evaluators are kept out of line so that their local arrays do not inflate the register
 // allocation of the closed-form cubic fast path
+// RBF / Chebyshev values j < 8 packed to bf16, registers only (compile-time indices); out of line so that the closed-form
+// cubic path of the producers keeps its register budget.
+__device__ __noinline__ uint4 basis8_lean(const KcBasisCtx& B, float x) {
+  const int nb = B.nb;
+  float phi[8];
+  if (B.kind == KC_BASIS_RBF) {
+    const float inv_den = __fdividef(1.0f, B.p[nb]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float q = (x - B.p[j]) * inv_den;
+      phi[j] = j < nb ? __expf(-(q * q)) : 0.0f;
+    }
+  } else {
+    const float lo = -1.0f + 1e-7f, hi = 1.0f - 1e-7f;
+    const float t = tc_tanh(x);
+    float c = fminf(fmaxf(t, lo), hi);
+    if (t != t) c = t;
+    float T0 = 1.0f, T1 = c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      phi[j] = j < nb ? T0 : 0.0f;
+      const float T2 = 2.0f * c * T1 - T0;
+      T0 = T1; T1 = T2;
+    }
+  }
+  return make_uint4(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]), pack_bf16(phi[4], phi[5]), pack_bf16(phi[6], phi[7]));
+}
 __device__ __noinline__ uint4 basis8_generic(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
 #pragma unroll
@@ -185,9 +212,14 @@ __device__ __noinline__ uint4 basis8_generic(const KcBasisCtx& B, float x) {
 }
 __device__ __forceinline__ uint4 basis8(const KcBasisCtx& B, const TcGeom& g, float x, bool valid) {
   if (g.fast_cubic) return cubic8(x, g.t0, g.inv_h, B.nparams - 1, valid);
-  return valid ? basis8_generic(B, x) : make_uint4(0u, 0u, 0u, 0u);
+  if (!valid) return make_uint4(0u, 0u, 0u, 0u);
+  return (B.kind == KC_BASIS_RBF || B.kind == KC_BASIS_CHEBY) ? basis8_lean(B, x) : basis8_generic(B, x);
 }
 __device__ __noinline__ uint2 basis4(const KcBasisCtx& B, float x) {
+  if (B.kind == KC_BASIS_RBF || B.kind == KC_BASIS_CHEBY) {
+    const uint4 v = basis8_lean(B, x);
+    return make_uint2(v.x, v.y);
+  }
   float phi[KC_MAX_BASIS];
 #pragma unroll
   for (int j = 0; j < 4; ++j) phi[j] = 0.0f;      // widths 1..3 are zero-padded to 4
