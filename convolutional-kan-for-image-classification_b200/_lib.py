@@ -40,6 +40,7 @@ _SIGNATURES = {
     "kc_norm_act_fwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 9),
     "kc_norm_act_bwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 13),
     "kc_tc_supported": (ctypes.c_int, [_P(KcDesc)]),
+    "kc_tc_fwd_needs_phi": (ctypes.c_int, [_P(KcDesc)]),
     "kc_tc_bytes": (c_sz, [_P(KcDesc), ctypes.c_int]),
     "kc_tc_pack_weights": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 5),
     "kc_tc_dz_flat": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 3),

@@ -23,9 +23,11 @@
 
 #include "kc_common.cuh"
 #include "kc_umma.cuh"
+#include "kc_tc_basis.cuh"
 
 size_t kc_tc_wgrad_ws_bytes(const kc_desc* d, int which);                                              // kc_tc_wgrad.cu
 int kc_tc_wgrad_phi_layout(const kc_desc* d, long long* L, int* spline_planes, int* base_planes);    // kc_tc_wgrad.cu
+int kc_tc_phi_prepass(const kc_desc* d, const float* x_base, const float* x_basis, const float* beta, void* phi, void* stream);
 
 namespace {
 
@@ -53,6 +55,7 @@ struct TcGeom {
   int tps;                     // filter taps per B ring stage (1, or kw = a whole filter row)
   int cpt;                     // dgrad: input channels per N tile (16, or 14 for the persistent kernel with a base column)
   int persistent;              // dgrad: 1 = kc_dgrad_persistent_kernel (double-buffered TMEM, epilogue overlaps the MMAs)
+  int from_phi;                // forward of a 1x1 convolution: basis rows come from the phi buffer (pre-pass + persistent GEMM)
   long long mtiles;
   long long wimg_bytes_per_ntile;
   size_t smem_bytes;
@@ -128,50 +131,6 @@ __device__ __forceinline__ uint4 cubic8(float x, float t0, float inv_h, int nint
   const unsigned long long lo = shl64(v, sh) | shr64(v, -sh);
   const unsigned long long hi = shr64(v, 64 - sh) | shl64(v, sh - 64);
   return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
-}
-
-// Basis value (and optionally derivative) for the tensor-core path: same formulas as kc_eval_basis, evaluated with fast
-// intrinsics (ex2-based exp / tanh / sigmoid, Chebyshev polynomials by recurrence instead of cos(j acos c)); the results
-// are rounded to bf16 anyway.  B-splines that are not the uniform cubic case go through the exact evaluator.
-__device__ __forceinline__ float tc_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
-__device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ inline void tc_eval_basis(const KcBasisCtx& B, float x, float* phi, float* dphi) {
-  const int nb = B.nb;
-  if (B.kind == KC_BASIS_RBF) {
-    const float inv_den = __fdividef(1.0f, B.p[nb]);
-    for (int j = 0; j < nb; ++j) {
-      const float q = (x - B.p[j]) * inv_den;
-      const float e = __expf(-(q * q));
-      phi[j] = e;
-      if (dphi) dphi[j] = e * (-2.0f * q * inv_den);
-    }
-  } else if (B.kind == KC_BASIS_CHEBY) {
-    const float lo = -1.0f + 1e-7f, hi = 1.0f - 1e-7f;
-    const float t = tc_tanh(x);
-    float c = fminf(fmaxf(t, lo), hi);
-    if (t != t) c = t;
-    const float dc = (t < lo || t > hi) ? 0.0f : 1.0f - t * t;       // d c / d x
-    float T0 = 1.0f, T1 = c, U0 = 0.0f, U1 = 1.0f;                   // T_j, U_{j-1}
-    for (int j = 0; j < nb; ++j) {
-      phi[j] = T0;
-      if (dphi) dphi[j] = (float)j * U0 * dc;
-      const float T2 = 2.0f * c * T1 - T0, U2 = 2.0f * c * U1 - U0;
-      T0 = T1; T1 = T2; U0 = U1; U1 = U2;
-    }
-  } else if (B.kind == KC_BASIS_GRAM) {
-    const float t = tc_tanh(x), dt = 1.0f - t * t;
-    float p0 = 1.0f, p1 = t, d0 = 0.0f, d1 = 1.0f;
-    for (int i = 0; i < nb; ++i) {
-      const float sg = tc_sigmoid(p0);
-      phi[i] = p0 * sg;
-      if (dphi) dphi[i] = sg * fmaf(p0, 1.0f - sg, 1.0f) * d0 * dt;
-      const float b = (i + 1 < KC_MAX_BASIS) ? B.gbeta[i + 1] : 0.0f;   // p_{i+2} = t p_{i+1} - beta(i+1, i+2) p_i
-      const float p2 = t * p1 - b * p0, d2 = p1 + t * d1 - b * d0;
-      p0 = p1; p1 = p2; d0 = d1; d1 = d2;
-    }
-  } else {
-    kc_eval_basis(B, x, phi, dphi, 1);
-  }
 }
 
 // generic (any family) evaluators are kept out of line so that their local arrays do not inflate the register
@@ -828,17 +787,22 @@ __device__ __forceinline__ void tc_basis_grad8(const KcBasisCtx& B, float x, flo
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Persistent dgrad (closed-form cubic basis): one CTA per SM walks the (position tile, channel tile) list.  The TMEM holds
-// TWO accumulator sets (2 sub-tiles x 128 columns each), so the 16 epilogue warps contract tile t with the basis
-// derivative while the MMA warps already accumulate tile t+1; dz rows are fed by four dedicated cp.async warps.
-//   warps 0-15 epilogue | 16-19 dz producers | 20 weight loader | 21-22 MMA issuers (one sub-tile each)
-// N tile = cpt channels x (nb + base) columns padded to 128 (14 channels with a base branch, 16 without).
+// Persistent GEMM kernel with both operands fed by the TMA engine: one CTA per SM walks a list of (256-position tile, N tile)
+// pairs.  The TMEM holds TWO accumulator sets (2 sub-tiles x <= 128 columns each), so the 16 epilogue warps drain tile t
+// while the MMA warps already accumulate tile t+1.
+//   warps 0-15 epilogue | 16 A loader (strips of a plane-major flat buffer) | 17 weight loader | 18-19 MMA issuers
+// FAM 1: dgrad, closed-form cubic basis   (A = dz_flat, N tile = cpt channels x (nb + base) columns padded to 128)
+// FAM 0: dgrad, RBF / Chebyshev basis
+// FAM 2: forward of a 1x1 convolution from the saved basis rows (A = phi, N tile = output channels): pointwise layers have one
+//        tap of MMA work per K chunk, so evaluating the basis inside the GEMM kernel leaves the tensor cores idle; the basis is
+//        written once by the pre-pass (it is needed for the weight gradient anyway) and this kernel streams it back.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kDgThreads = 640, kDgEpiWarps = 16, kDgProdWarp0 = 16, kDgLoaderWarp = 17, kDgMmaWarp0 = 18;
 constexpr int kDgBars = 2 * kMaxA + 2 * kMaxBStages + 4;
 
-template <bool CUBIC>
+template <int FAM>
 __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(const __grid_constant__ TcFwdArgs a) {
+  constexpr bool CUBIC = FAM == 1, FWD = FAM == 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
@@ -861,9 +825,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   const int T = d.kh * d.kw, HW = d.h * d.w;
   const bool has_base = d.act != KC_ACT_NONE;
   const int wb = d.nb + (has_base ? 1 : 0);
-  const int nchunks = g.nbc;
+  const int nchunks = FWD ? g.nsc + (has_base ? g.nbc : 0) : g.nbc;
   const long long ntiles = g.mtiles * g.n_ntiles;
-  if (!CUBIC) kc_load_basis_ctx(B, d, a.beta);
+  if (FAM == 0) kc_load_basis_ctx(B, d, a.beta);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
@@ -911,8 +875,10 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
         const uint32_t total = __reduce_add_sync(0xffffffffu, mybytes);
         if (lane == 0) mbar_arrive_expect_tx(&a_full[buf], total);
         __syncwarp();
+        // plane of the flat buffer: dz_flat planes are consecutive; in phi the base planes follow the (padded) spline planes
+        const int plane = (!FWD || q < g.nsc) ? q * kPL + pl : a.phi_base_plane0 + (q - g.nsc) * kPL + pl;
         if (mybytes != 0u)
-          bulk_g2s(dst + lo * 16, a.dzf + ((long long)(q * kPL + pl) * g.L + qs + lo) * 16, mybytes, &a_full[buf]);
+          bulk_g2s(dst + lo * 16, a.dzf + ((long long)plane * g.L + qs + lo) * 16, mybytes, &a_full[buf]);
         if (++buf == g.na) { buf = 0; ph ^= 1; }
       }
     }
@@ -995,6 +961,55 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       __syncwarp();
     }
   } else {
+    if (FWD) {
+      // ============================== epilogue (forward from phi): TMEM -> z (fp32 NCHW) ===========================
+      const int quarter = warp & 3, cgrp = warp >> 2;
+      const int HoWo = d.ho * d.wo;
+      const long long nsteps = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * 2;
+#pragma unroll 1
+      for (long long step = 0; step < nsteps; ++step) {
+        const uint32_t it = (uint32_t)(step >> 1), acc = it & 1u, sub = (uint32_t)(step & 1);
+        const long long tile = blockIdx.x + (step >> 1) * gridDim.x;
+        const long long mt = tile / g.n_ntiles;
+        const int n0 = (int)(tile - mt * g.n_ntiles) * g.ntile;
+        const long long q = mt * g.mcta + sub * kTileM + quarter * 32 + lane;
+        bool valid = false;
+        long long zoff = 0;
+        if (q < g.L) {
+          const unsigned uq = (unsigned)q, n = uq / (unsigned)g.IMG, rem = uq - n * (unsigned)g.IMG;
+          const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
+          unsigned yo = y, xo = x;
+          bool on_grid = true;
+          if (d.stride_h != 1 || d.stride_w != 1) {
+            yo = y / (unsigned)d.stride_h; xo = x / (unsigned)d.stride_w;
+            on_grid = yo * (unsigned)d.stride_h == y && xo * (unsigned)d.stride_w == x;
+          }
+          if (on_grid && yo < (unsigned)d.ho && xo < (unsigned)d.wo) { valid = true; zoff = (long long)n * d.z_batch_stride + yo * d.wo + xo; }
+        }
+        if (sub == 0) {
+          mbar_wait(&acc_full[acc], (it >> 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)(2 * g.ntile) + sub * (uint32_t)g.ntile;
+        for (int c0 = cgrp * 16; c0 < g.ntile; c0 += 64) {
+          uint32_t r[16];
+          tmem_ld16(trow + (uint32_t)c0, r);
+          tmem_ld_wait();
+          float* zp = a.z + zoff + (long long)(n0 + c0) * HoWo;
+          const int lim = min(16, d.cout - (n0 + c0));
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < lim) zp[(long long)j * HoWo] = __uint_as_float(r[j]);
+          }
+        }
+        if (sub == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+      }
+    } else {
     // ================================ epilogue: dPhi (TMEM) x analytic basis derivative -> dx =========
     // warp w: TMEM lanes of quarter w % 4, channel group w / 4 (the cpt channels of the tile are split four ways)
     constexpr int kCh = CUBIC ? 4 : 8;                             // channels per warp (cpt <= 4 * kCh)
@@ -1090,6 +1105,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc]);
       }
+    }
     }
   }
   tc_fence_before();
@@ -1459,7 +1475,29 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
   int want_tiles = (d->cout + 255) / 256;
   g->ntile = round_up((d->cout + want_tiles - 1) / want_tiles, 16);
   g->n_ntiles = (d->cout + g->ntile - 1) / g->ntile;
-  return tc_fit(d, g, T, (has_base ? (g->nbc - 1) * kPL + g->last_base_cols : 0) + g->nsc * kPL);
+  const int kcores = (has_base ? (g->nbc - 1) * kPL + g->last_base_cols : 0) + g->nsc * kPL;
+  // Pointwise layers: persistent GEMM over the saved basis rows (see kc_dgrad_persistent_kernel, FAM 2)
+  long long Lw = 0;
+  int splanes = 0, bplanes = 0;
+  if (T == 1 && kc_tc_wgrad_phi_layout(d, &Lw, &splanes, &bplanes) == KC_OK && Lw == g->L) {
+    const int ntile = d->cout >= 128 ? 128 : round_up(d->cout, 16);
+    const int mcta = 2 * kTileM;
+    const int seglen = mcta, SS = g->P < seglen ? g->P : seglen, nrows = seglen;
+    const int plane_bytes = nrows * 16 + 16;
+    const size_t btap = (size_t)kPL * ntile * 16;
+    const size_t fixed = (size_t)kDgBars * 8 + 16 + sizeof(KcBasisCtx) + 128 + (size_t)3 * kPL * plane_bytes;
+    int bst = (int)((kSmemLimit - fixed) / btap);
+    if (bst > kMaxBStages) bst = kMaxBStages;
+    if (bst >= 4) {
+      g->from_phi = 1; g->persistent = 1; g->ntile = ntile; g->n_ntiles = (d->cout + ntile - 1) / ntile;
+      g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = 1; g->na = 3;
+      g->bstages = bst; g->mtiles = (g->L + mcta - 1) / mcta; g->smem_bytes = fixed + bst * btap; g->tmem_cols = 512;
+      g->wimg_bytes_per_ntile = (long long)T * ntile * 16 * kcores;
+      g->fast_cubic = knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
+      return KC_OK;
+    }
+  }
+  return tc_fit(d, g, T, kcores);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1556,6 +1594,12 @@ extern "C" int kc_tc_supported(const kc_desc* d) {
   return tc_forward_geometry(d, &g) == KC_OK ? 1 : 0;
 }
 
+extern "C" int kc_tc_fwd_needs_phi(const kc_desc* d) {
+  if (kc_validate_desc(d) != KC_OK) return 0;
+  TcGeom g;
+  return (tc_forward_geometry(d, &g) == KC_OK && g.from_phi) ? 1 : 0;
+}
+
 extern "C" size_t kc_tc_bytes(const kc_desc* d, int which) {
   if (kc_validate_desc(d) != KC_OK) return 0;
   TcGeom g;
@@ -1637,6 +1681,26 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
   TcFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.wp = (const unsigned char*)packed_fwd; a.beta = beta; a.z = z;
+  if (g.from_phi) {
+    // pointwise layer: basis rows by the pre-pass, then the persistent GEMM streams them back through the TMA engine
+    if (phi_out == nullptr) KC_FAIL(KC_ERR_INVALID, "kc_conv_fwd_tc: 1x1 layers need the phi buffer (kc_tc_fwd_needs_phi, kc_tc_bytes(d, 4))");
+    long long Lw = 0;
+    int splanes = 0, bplanes = 0;
+    rc = kc_tc_wgrad_phi_layout(d, &Lw, &splanes, &bplanes);
+    if (rc != KC_OK) return rc;
+    rc = kc_tc_phi_prepass(d, x_base, x_basis, beta, phi_out, stream);
+    if (rc != KC_OK) return rc;
+    a.dzf = (const unsigned char*)phi_out;
+    a.phi_base_plane0 = splanes;
+    int dev = 0, sms = 148;
+    KC_CUDA_CHECK(cudaGetDevice(&dev));
+    KC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long ntiles = g.mtiles * g.n_ntiles;
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kc_dgrad_persistent_kernel<2><<<(unsigned)(ntiles < sms ? ntiles : sms), kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    KC_LAUNCH_CHECK("kc_tc_kernel<fwd>");
+    return KC_OK;
+  }
   if (phi_out != nullptr) {
     long long Lw = 0;
     int splanes = 0, bplanes = 0;
@@ -1683,11 +1747,11 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
     const long long ntiles = g.mtiles * g.n_ntiles;
     const unsigned nctas = (unsigned)(ntiles < sms ? ntiles : sms);
     if (g.fast_cubic) {
-      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-      kc_dgrad_persistent_kernel<true><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      kc_dgrad_persistent_kernel<1><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
     } else {
-      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-      kc_dgrad_persistent_kernel<false><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      kc_dgrad_persistent_kernel<0><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
     }
     KC_LAUNCH_CHECK("kc_dgrad_persistent_kernel");
     return KC_OK;

@@ -16,6 +16,7 @@
 
 #include "kc_common.cuh"
 #include "kc_umma.cuh"
+#include "kc_tc_basis.cuh"
 
 namespace {
 
@@ -107,14 +108,14 @@ __device__ __noinline__ uint4 basis8w_generic(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
 #pragma unroll
   for (int j = 0; j < 8; ++j) phi[j] = 0.0f;
-  kc_eval_basis(B, x, phi, nullptr, 1);
+  tc_eval_basis(B, x, phi, nullptr);          // same evaluator as the forward producers: the rows must match what they store
   return make_uint4(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]), pack_bf16(phi[4], phi[5]), pack_bf16(phi[6], phi[7]));
 }
 __device__ __noinline__ uint2 basis4w(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
 #pragma unroll
   for (int j = 0; j < 4; ++j) phi[j] = 0.0f;
-  kc_eval_basis(B, x, phi, nullptr, 1);
+  tc_eval_basis(B, x, phi, nullptr);
   return make_uint2(pack_bf16(phi[0], phi[1]), pack_bf16(phi[2], phi[3]));
 }
 
@@ -556,6 +557,20 @@ int kc_tc_wgrad_phi_layout(const kc_desc* d, long long* L, int* spline_planes, i
   int rc = wgrad_geometry(d, &g);
   if (rc != KC_OK) return rc;
   *L = g.L; *spline_planes = g.nsc * 16; *base_planes = g.nbc * 16;
+  return KC_OK;
+}
+
+// Basis rows of a layer input in the phi layout (the pre-pass of the weight gradient, also used by the pointwise forward).
+int kc_tc_phi_prepass(const kc_desc* d, const float* x_base, const float* x_basis, const float* beta, void* phi, void* stream) {
+  WgGeom g;
+  int rc = wgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = *d; a.g = g; a.x_base = x_base; a.x_basis = x_basis; a.beta = beta;
+  dim3 pgrid((unsigned)((g.L + 255) / 256), (unsigned)g.nchunks);
+  kc_phi_flat_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a, (unsigned char*)phi);
+  KC_LAUNCH_CHECK("kc_phi_flat_kernel");
   return KC_OK;
 }
 

@@ -191,7 +191,7 @@ class _KanConvFn(torch.autograd.Function):
                 L.check(_timed("kc_pack_fwd_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
                     ctypes.byref(d), _ptr(wbg), _ptr(wsg), _ptr(packed), None, stream)), "kc_tc_pack_weights")
                 phi = None
-                if want_phi and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
+                if (want_phi or lib.kc_tc_fwd_needs_phi(ctypes.byref(d))) and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
                     phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=xb.device, dtype=torch.uint8)
                 phis.append(phi)
                 L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(

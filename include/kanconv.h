@@ -143,6 +143,9 @@ int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, cons
  * Parity target: <= 2e-2 relative / 1e-3 absolute to the reference fp32 modules.
  * ------------------------------------------------------------------------------------------------------- */
 int kc_tc_supported(const kc_desc* d);
+/* 1 when kc_conv_fwd_tc needs a phi_out buffer even for inference: 1x1 layers run as a basis pre-pass into phi followed by
+ * a GEMM that streams phi back (fusing the basis into the GEMM leaves the tensor cores idle when there is one tap). */
+int kc_tc_fwd_needs_phi(const kc_desc* d);
 /* Bytes of the packed bf16 weight images of the forward (which=0) and dgrad (which=1) kernels, of the flat bf16
  * dz buffer that kc_tc_dz_flat fills (which=2), of the wgrad workspace when the forward did not save its basis rows
  * (which=3: split-K partial sums + a transient basis buffer), of the saved basis rows `phi` that kc_conv_fwd_tc can

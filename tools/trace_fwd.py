@@ -3,10 +3,10 @@ import argparse, ctypes, os, sys
 import torch, torch.nn as nn
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kanconv_b200 as K
-ap = argparse.ArgumentParser(); ap.add_argument("--shape", default="16,64,64,224"); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--shape", default="16,64,64,224"); ap.add_argument("--k", type=int, default=3); a = ap.parse_args()
 n, cin, cout, hw = [int(v) for v in a.shape.split(",")]
 lib = K._lib.load()
-m = K.KANConv2DLayer(cin, cout, 3, padding=1, base_activation=nn.SiLU).cuda()
+m = K.KANConv2DLayer(cin, cout, a.k, padding=a.k // 2, base_activation=nn.SiLU).cuda()
 x = torch.randn(n, cin, hw, hw, device="cuda")
 with torch.no_grad():
     m(x); torch.cuda.synchronize()
