@@ -22,7 +22,7 @@ namespace {
 
 using namespace kc;
 
-constexpr int kThreadsW = 544;       // warps 0-15 producers / epilogue, 16 MMA issuer (highest warp id)
+constexpr int kThreadsW = 576;       // warps 0-15 producers / epilogue, 16-17 MMA issuers (highest warp ids)
 constexpr int kProdW = 512;
 constexpr int kMmaWarpW = 16;
 constexpr int kMaxStagesW = 6;
@@ -261,11 +261,11 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
 
 // Straight-line issue of the KW x (kKS/16) MMAs of one stage (tap s reads the Phi planes from row s; k-step ks advances both
 // operands by 16 rows).  Descriptor low words differ by small constants only.
-template <int KW, int KS>
+template <int S0, int S1, int KS>          // taps [S0, S1)
 __device__ __forceinline__ void wg_issue(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
                                          uint32_t b_hi, uint32_t idesc, uint32_t first) {
 #pragma unroll
-  for (int s = 0; s < KW; ++s) {
+  for (int s = S0; s < S1; ++s) {
     const uint32_t td = tmem_base + (uint32_t)s * ntile;
 #pragma unroll
     for (int ks = 0; ks < KS / 16; ++ks)
@@ -297,8 +297,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   const int nblocks = (int)(blk1 - blk0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxStagesW; ++i) { mbar_init(&full[i], kProdW); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
+    const uint32_t nmw = d.kw == 3 ? 2u : 1u;          // MMA-issuing warps: with three taps, warp 16 takes taps 0-1, warp 17 tap 2
+    for (int i = 0; i < kMaxStagesW; ++i) { mbar_init(&full[i], kProdW); mbar_init(&empty[i], nmw); }
+    mbar_init(acc_full, nmw);
     fence_barrier_init();
   }
   if (warp == kMmaWarpW) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
@@ -312,8 +313,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     // ============================ producers: Phi (A) evaluated on the fly, dz (B) copied ===========================
     wg_produce<KS>(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
   }
-  if (warp == kMmaWarpW) {
-    // ============================ MMA issuer (whole warp uniform, one elected lane issues) ==========================
+  if (warp >= kMmaWarpW && (warp == kMmaWarpW || d.kw == 3)) {
+    // ============================ MMA issuers (whole warp uniform, one elected lane issues) =========================
+    // The taps have separate accumulators, so two warps can issue independently: the barrier wait / commit overhead of one
+    // overlaps the MMAs of the other.
+    const int mw = warp - kMmaWarpW;
     const uint32_t idesc = make_idesc_bf16(128, g.ntile, 1, 1);        // both operands MN-major
     const uint32_t lo_c = (128u >> 4) << 16;                            // LBO = 128 B between 8-row K groups
     const uint32_t a_hi = ((uint32_t)g.aplane_bytes >> 4) | (1u << 14); // SBO = plane pitch (8 M rows), version 1
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     const int kw = d.kw, ntile = g.ntile;
     int st = 0;
     uint32_t ph = 0;
-    TracerW trm(1, lane == 0);
+    TracerW trm(1, lane == 0 && mw == 0);
     for (int bi = 0; bi < nblocks; ++bi) {
       trm.stamp();
       mbar_wait(&full[st], ph);
@@ -332,8 +336,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
       const uint32_t first = bi != 0 ? 1u : 0u;
       if (elect_one_sync()) {
         const uint32_t a_lo = lo_c | au, b_lo = lo_c | bu;
-        if (kw == 3) wg_issue<3, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
-        else if (kw == 1) wg_issue<1, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        if (kw == 3 && mw == 0) wg_issue<0, 2, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else if (kw == 3) wg_issue<2, 3, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else if (kw == 1) wg_issue<0, 1, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
         else {
           for (int s = 0; s < kw; ++s) {
             const uint32_t td = tmem_base + (uint32_t)(s * ntile);
