@@ -5,11 +5,11 @@
 // GEMM view per CTA: D[M = 128 expanded input rows (16 channels x 8 basis, or 128 base channels)][N = cout tile] for the
 // kw taps of ONE filter row r, reduced over a range of 128-position blocks (split-K).  Both operands are "MN-major"
 // no-swizzle UMMA layouts whose K dimension (positions) runs along 16-byte rows:
-//   A = Phi  planes [channel (8 j) | 8-channel group][row = position + tap shift][8 x bf16]   - evaluated on the fly
+//   A = Phi  planes [channel (8 j) | 8-channel group][row = position + tap shift][8 x bf16]   - 16-byte copies of phi, the
+//                                                                 rows the forward kernel saved (or kc_phi_flat_kernel)
 //   B = dz   planes [8 couts][row = position][8 x bf16]                                        - 16-byte copies of the
 //                                                                                               flat bf16 dz buffer
-// so the three taps of the filter row are again shifted VIEWS (start row + s) of the same Phi buffer and the expanded
-// tensor never exists in HBM.  Each tap has its own TMEM accumulator (kw * N <= 512 columns).  Partial sums go to a
+// so the three taps of the filter row are again shifted VIEWS (start row + s) of the same Phi stage.  Each tap has its own TMEM accumulator (kw * N <= 512 columns).  Partial sums go to a
 // workspace [split][unit][s][128][N] and kc_wgrad_tc_reduce_kernel adds the splits in fixed order (deterministic) while
 // scattering into the reference's parameter layouts.
 #include <string.h>
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 16) {
-    // ============================ producers: Phi (A) evaluated on the fly, dz (B) copied ===========================
+    // ============================ producers: cp.async copies of the Phi (A) and dz (B) planes ===========================
     wg_produce<KS>(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
   }
   if (warp >= kMmaWarpW && (warp == kMmaWarpW || d.kw == 3)) {
