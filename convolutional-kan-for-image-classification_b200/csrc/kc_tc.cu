@@ -1371,7 +1371,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
       if (ci >= 2 && d->kw == 1) break;
       const size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
       const size_t bstage = btap * tps;
-      if (fixed + (tps == 1 ? 6 : 4) * bstage > kSmemLimit) continue;
+      if (fixed + (tps == 1 ? 6 : 3) * bstage > kSmemLimit) continue;
       int bst = (int)((kSmemLimit - fixed) / bstage);
       if (bst > kMaxBStages) bst = kMaxBStages;
       g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps;
@@ -1443,7 +1443,7 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
         if (ci >= 2 && d->kw == 1) break;
         const size_t fixed = fixed0 + (size_t)na * kPL * plane_bytes;
         const size_t bstage = btap * tps;
-        if (fixed + (tps == 1 ? 6 : 4) * bstage > kSmemLimit) continue;
+        if (fixed + (tps == 1 ? 6 : 3) * bstage > kSmemLimit) continue;
         int bst = (int)((kSmemLimit - fixed) / bstage);
         if (bst > kMaxBStages) bst = kMaxBStages;
         g->persistent = 1; g->cpt = cpt; g->ntile = ntile; g->n_ntiles = (d->cin + cpt - 1) / cpt;
