@@ -310,9 +310,13 @@ def run_b200(args):
         tpath = os.path.join(ROOT, "profiles", "r1_traffic_b64.json")
         if args.workload == "kan_vgg16_224" and batch == 64 and os.path.exists(tpath):
             with open(tpath) as fh:
-                tk = json.load(fh)["kernels"].get(name)
-            if tk:
-                roof["traffic"] = tk["dram_bytes_per_launch"]
+                kern = json.load(fh)["kernels"]
+            # template instantiations of one kernel are listed separately in the capture (kc_wgrad_tc_kernel<64>, <128>)
+            hits = [v for k, v in kern.items() if k == name or k.startswith(name + "<")]
+            if hits:
+                nl = sum(v["launches_per_step"] for v in hits)
+                tot = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in hits)
+                roof["traffic"] = int(tot / max(nl, 1e-9))
                 roof["traffic_source"] = "profiles/r1_traffic_b64.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
 
     if rank != 0:
