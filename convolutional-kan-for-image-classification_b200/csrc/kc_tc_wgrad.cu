@@ -189,7 +189,7 @@ constexpr int kPrefetchW = 3;          // max stages in flight per producer thre
 template <int KS>
 __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int r, int chunk,
                                            int ct, long long blk0, int nblocks) {
-  constexpr int kItems = KS == 64 ? 3 : 5;       // 16-byte vectors per producer thread and operand per stage
+  constexpr int kItems = KS == 64 ? 3 : KS == 96 ? 4 : 5;       // 16-byte vectors per producer thread and operand per stage
   const kc_desc& d = a.d;
   const WgGeom& g = a.g;
   const int tid = threadIdx.x;
@@ -509,19 +509,27 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->ntile = round_up_w((g->cq + want - 1) / want, 16);
   g->n_ct = (g->cq + g->ntile - 1) / g->ntile;
   g->units = g->n_ct * g->nchunks * d->kh;
-  g->ks = g->ntile <= 64 ? 128 : 64;     // small cout tiles: more MMAs per barrier round
-  g->arows = round_up_w(g->ks + d->kw - 1, 8);
-  g->aplane_bytes = g->arows * 16 + 16;
-  g->a_bytes = 16 * g->aplane_bytes;
+  // positions per ring stage: as many MMAs per barrier round as the producer mapping and a >= 3-deep ring allow
+  // (128 -> 24 MMAs per tap row for cout tiles <= 64, else 96 -> 18, else 64 -> 12)
   g->bplanes = g->ntile / 8;
-  g->bplane_bytes = g->ks * 16 + 16;
-  g->stage_bytes = round_up_w(g->a_bytes + g->bplanes * g->bplane_bytes, 128);
-  const int items = g->ks == 64 ? 3 : 5;
-  if (g->arows * 16 > items * kProdW || g->ks * g->bplanes > items * kProdW) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage too large for the producer mapping");
+  const int cand[3] = {g->ntile <= 64 ? 128 : 96, 96, 64};
   size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 128;
-  g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
-  if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
-  if (g->stages < 2) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory");
+  bool ok = false;
+  for (int ci = 0; ci < 3 && !ok; ++ci) {
+    g->ks = cand[ci];
+    g->arows = round_up_w(g->ks + d->kw - 1, 8);
+    g->aplane_bytes = g->arows * 16 + 16;
+    g->a_bytes = 16 * g->aplane_bytes;
+    g->bplane_bytes = g->ks * 16 + 16;
+    g->stage_bytes = round_up_w(g->a_bytes + g->bplanes * g->bplane_bytes, 128);
+    const int items = g->ks == 64 ? 3 : g->ks == 96 ? 4 : 5;
+    if (g->arows * 16 > items * kProdW || g->ks * g->bplanes > items * kProdW) continue;
+    g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
+    if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
+    if (g->stages < (g->ks == 64 ? 2 : 3)) continue;
+    ok = true;
+  }
+  if (!ok) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory / the producer mapping");
   g->prefetch = g->stages - 2 < kPrefetchW ? g->stages - 2 : kPrefetchW;      // keep two slack stages for the MMA side
   if (g->prefetch < 1) g->prefetch = 1;
   g->smem_bytes = fixed + (size_t)g->stages * g->stage_bytes;
@@ -604,7 +612,10 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
     KC_LAUNCH_CHECK("kc_phi_flat_kernel");
   }
   dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
-  if (g.ks == 128) {
+  if (g.ks == 96) {
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kc_wgrad_tc_kernel<96><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  } else if (g.ks == 128) {
     KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     kc_wgrad_tc_kernel<128><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
   } else {
