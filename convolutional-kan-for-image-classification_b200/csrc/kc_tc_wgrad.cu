@@ -512,7 +512,7 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   // positions per ring stage: as many MMAs per barrier round as the producer mapping and a >= 3-deep ring allow
   // (128 -> 24 MMAs per tap row for cout tiles <= 64, else 96 -> 18, else 64 -> 12)
   g->bplanes = g->ntile / 8;
-  const int cand[3] = {g->ntile <= 64 ? 128 : 96, 96, 64};
+  const int cand[3] = {128, 96, 64};
   size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 128;
   bool ok = false;
   for (int ci = 0; ci < 3 && !ok; ++ci) {
