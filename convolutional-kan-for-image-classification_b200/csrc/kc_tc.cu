@@ -1437,13 +1437,16 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
     const size_t btap = (size_t)kPL * ntile * 16;
     const size_t fixed0 = (size_t)kDgBars * 8 + 16 + sizeof(KcBasisCtx) + 128;
     if (d->kh * kPL <= 32) {
-      const int cand_na[4] = {3, 2, 3, 2}, cand_tps[4] = {d->kw, d->kw, 1, 1};
-      for (int ci = 0; ci < 4; ++ci) {
+      // weight ring granularity, coarsest first: a whole 32-cout chunk (all taps) per stage, a filter row, a single tap -
+      // the barrier round of a stage costs the issuing warps a few hundred cycles, so fewer and larger stages win as long
+      // as the ring stays >= 2-3 deep
+      const int cand_na[6] = {3, 2, 3, 2, 3, 2}, cand_tps[6] = {T, T, d->kw, d->kw, 1, 1}, cand_min[6] = {2, 2, 3, 3, 6, 6};
+      for (int ci = 0; ci < 6; ++ci) {
         const int na = cand_na[ci], tps = cand_tps[ci];
-        if (ci >= 2 && d->kw == 1) break;
+        if (ci >= 2 && tps == cand_tps[ci - 2]) continue;                 // kw == T or kw == 1: same as a coarser candidate
         const size_t fixed = fixed0 + (size_t)na * kPL * plane_bytes;
         const size_t bstage = btap * tps;
-        if (fixed + (tps == 1 ? 6 : 3) * bstage > kSmemLimit) continue;
+        if (fixed + cand_min[ci] * bstage > kSmemLimit) continue;
         int bst = (int)((kSmemLimit - fixed) / bstage);
         if (bst > kMaxBStages) bst = kMaxBStages;
         g->persistent = 1; g->cpt = cpt; g->ntile = ntile; g->n_ntiles = (d->cin + cpt - 1) / cpt;
