@@ -1365,13 +1365,17 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
     // preference: whole-filter-row stages with a 3-deep A ring, then with a 2-deep A ring, then single-tap stages
     // (a ring stage that carries kw taps pays the issuing warp's per-stage cost - barrier wait, fence, commits, several
     // hundred cycles - once per filter row)
-    const int cand_na[4] = {3, 2, 3, 2}, cand_tps[4] = {d->kw, d->kw, 1, 1};
-    for (int ci = 0; ci < 4; ++ci) {
+    // coarsest first: all taps of a chunk per stage (>= 2 stages), a filter row (>= 3), a single tap (>= 6)
+    // (a filter row with a 4-deep ring is preferred over a deeper A ring with only 3 stages)
+    const int cand_na[8] = {3, 2, 3, 2, 3, 2, 3, 2}, cand_tps[8] = {T, T, d->kw, d->kw, d->kw, d->kw, 1, 1};
+    const int cand_min[8] = {2, 2, 4, 4, 3, 3, 6, 6};
+    for (int ci = 0; ci < 8; ++ci) {
       const int na = cand_na[ci], tps = cand_tps[ci];
-      if (ci >= 2 && d->kw == 1) break;
+      if (ci >= 2 && ci < 4 && tps == T) continue;                        // kw == T: covered by the first pair
+      if (ci >= 6 && d->kw == 1) continue;                                // kw == 1: covered by the filter-row candidates
       const size_t fixed = tc_fixed_smem() + (size_t)na * kPL * plane_bytes;
       const size_t bstage = btap * tps;
-      if (fixed + (tps == 1 ? 6 : 3) * bstage > kSmemLimit) continue;
+      if (fixed + cand_min[ci] * bstage > kSmemLimit) continue;
       int bst = (int)((kSmemLimit - fixed) / bstage);
       if (bst > kMaxBStages) bst = kMaxBStages;
       g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps;
