@@ -14,6 +14,7 @@ ACT_NONE, ACT_IDENTITY, ACT_GELU, ACT_SILU = -1, 0, 1, 2
 NORM_NONE, NORM_INSTANCE, NORM_BATCH = 0, 1, 2
 OUT_NONE, OUT_PRELU, OUT_SILU = 0, 1, 2
 KC_MAX_BASIS, KC_MAX_PARAMS = 16, 40
+KC_ABI_VERSION = 2
 
 
 class KcDesc(ctypes.Structure):
@@ -27,6 +28,10 @@ class KcNormDesc(ctypes.Structure):
                [("batch_stride", c_i64), ("eps", c_f32)]
 
 
+class KcRowNormDesc(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("rows", "features", "out_act", "affine")] + [("eps", c_f32)]
+
+
 _P = ctypes.POINTER
 _SIGNATURES = {
     "kc_version": (ctypes.c_int, []),
@@ -38,7 +43,10 @@ _SIGNATURES = {
     "kc_wgrad_workspace_bytes": (c_sz, [_P(KcDesc)]),
     "kc_conv_wgrad_f32": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 8),
     "kc_norm_act_fwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 9),
-    "kc_norm_act_bwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 13),
+    "kc_norm_act_bwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 12 + [ctypes.c_int, c_vp]),
+    "kc_dbeta_floats": (c_sz, [_P(KcDesc), ctypes.c_int]),
+    "kc_layernorm_act_fwd": (ctypes.c_int, [_P(KcRowNormDesc)] + [c_vp] * 8),
+    "kc_layernorm_act_bwd": (ctypes.c_int, [_P(KcRowNormDesc)] + [c_vp] * 13),
     "kc_tc_supported": (ctypes.c_int, [_P(KcDesc)]),
     "kc_tc_fwd_needs_phi": (ctypes.c_int, [_P(KcDesc)]),
     "kc_tc_bytes": (c_sz, [_P(KcDesc), ctypes.c_int]),
@@ -49,6 +57,7 @@ _SIGNATURES = {
     "kc_conv_wgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 9),
     "kc_maxpool2d_fwd": (ctypes.c_int, [c_vp] * 3 + [ctypes.c_longlong] + [ctypes.c_int] * 6 + [c_vp]),
     "kc_maxpool2d_bwd": (ctypes.c_int, [c_vp] * 3 + [ctypes.c_longlong] + [ctypes.c_int] * 6 + [c_vp]),
+    "kc_tc_geometry": (ctypes.c_int, [_P(KcDesc), ctypes.c_int, _P(ctypes.c_longlong)]),
     "kc_tc_selftest": (ctypes.c_int, [ctypes.c_int, _P(ctypes.c_float), c_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -62,7 +71,9 @@ def library_path():
 
 
 def load():
-    """Load (building first if the sources are newer) and return the ctypes handle.  Raises if unavailable."""
+    """Load and return the ctypes handle; raises if unavailable.  The library is (re)built first when it is missing, when
+    KANCONV_REBUILD=1, or when the sources differ from the ones it was built from (content hash, build._stale); a box without nvcc
+    cannot rebuild and raises instead of running a stale library; an ABI version mismatch is a hard error either way."""
     global _lib
     if _lib is not None:
         return _lib
@@ -71,11 +82,16 @@ def load():
             path = _build.LIB
             if not os.path.exists(path) or os.environ.get("KANCONV_REBUILD") == "1":
                 path = _build.build(force=True)
+            elif _build._stale():
+                if not _build.have_nvcc():
+                    raise RuntimeError("libkanconv.so was built from different sources than the ones in the tree and nvcc is "
+                                       "not available to rebuild it (python -m kanconv_b200.build)")
+                path = _build.build(force=False)
             lib = ctypes.CDLL(path)
             for name, (res, args) in _SIGNATURES.items():
                 fn = getattr(lib, name)      # AttributeError if the library does not export the ABI
                 fn.restype, fn.argtypes = res, args
-            if lib.kc_version() != 1:
+            if lib.kc_version() != KC_ABI_VERSION:
                 raise RuntimeError("libkanconv.so ABI version mismatch")
             _lib = lib
     return _lib

@@ -35,6 +35,35 @@ extern "C" int kc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return KC_OK;
 }
 
+// Uniform cubic B-spline on G + 2K + 1 = 12 knots (the reference's default grid_size 5 / spline_order 3): the tensor-core
+// kernels then use the closed form of SURVEY Appendix A.2 with t0 and 1/h taken from the (fp32-rounded) knot vector.
+bool kc_knots_uniform_cubic(const kc_desc* d, float* t0, float* inv_h) {
+  if (d->basis != KC_BASIS_BSPLINE || d->order != 3 || d->nb != 8 || d->nparams != 12) return false;
+  double h = ((double)d->params[11] - (double)d->params[0]) / 11.0;
+  if (!(h > 0)) return false;
+  for (int i = 0; i < 12; ++i) {
+    double e = (double)d->params[0] + h * i - (double)d->params[i];
+    if (e < 0) e = -e;
+    if (e > 1e-5 * h) return false;
+  }
+  *t0 = d->params[0];
+  *inv_h = (float)(1.0 / h);
+  return true;
+}
+
+// Number of SMs of the current device (cached per device index); the persistent kernels launch one CTA per SM.
+int kc_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+    cached[dev] = sms;
+  }
+  return cached[dev];
+}
+
 int kc_validate_desc(const kc_desc* d) {
   if (!d) KC_FAIL(KC_ERR_INVALID, "null kc_desc");
   if (d->basis < KC_BASIS_BSPLINE || d->basis > KC_BASIS_RBF) KC_FAIL(KC_ERR_INVALID, "kc_desc: unknown basis kind %d", d->basis);

@@ -34,6 +34,10 @@ void kc_count_launch();   // per-process counter of kernels launched by this lib
   } while (0)
 
 int kc_validate_desc(const kc_desc* d);   // common argument checks (kc_api.cu)
+bool kc_knots_uniform_cubic(const kc_desc* d, float* t0, float* inv_h);   // kc_api.cu
+int kc_sm_count();                         // SMs of the current device (kc_api.cu)
+// GRAM d/d beta_weights: fixed-order sum of the `nrows` partial rows behind dbeta[0 .. KC_MAX_BASIS) into it (kc_norm.cu)
+int kc_dbeta_reduce(float* dbeta, long long nrows, void* stream);
 
 // ---------------------------------------------------------------------------------------------------------
 // Basis context: copied from kc_desc into shared memory at kernel start (dynamic indexing of knots).
@@ -69,6 +73,9 @@ __device__ inline void kc_load_basis_ctx(KcBasisCtx* B, const kc_desc& d, const 
   }
   __syncthreads();
 }
+
+// GRAM with dropout: the binding applies tanh and Dropout to the input itself and sets params[0] = 1 (nparams = 1)
+__device__ __forceinline__ bool kc_gram_presquashed(const KcBasisCtx& B) { return B.nparams > 0 && B.p[0] != 0.0f; }
 
 // ---------------------------------------------------------------------------------------------------------
 // base activations (kan_layers.py:199; gram:173; fast:103)
@@ -113,6 +120,7 @@ __device__ __forceinline__ int kc_bspline_local(const KcBasisCtx& B, float x, fl
   const float* t = B.p;
 #pragma unroll
   for (int r = 0; r <= KC_MAX_ORDER; ++r) { N[r] = 0.0f; dN[r] = 0.0f; }
+  if (!(fabsf(x) <= 3.402823466e38f)) x = __int_as_float(0x7fc00000);   // +-Inf: the reference's recursion gives 0 * Inf = NaN
   if (x != x) {                      // NaN propagates like in the reference (0 * NaN)
 #pragma unroll
     for (int r = 0; r <= KC_MAX_ORDER; ++r) { N[r] = x; dN[r] = x; }
@@ -211,8 +219,10 @@ __device__ inline void kc_eval_basis(const KcBasisCtx& B, float x, float* phi, f
     }
   } else if (B.kind == KC_BASIS_GRAM) {
     // gram_kan_layers.py:155-181: p0=1, p1=t, p_i = t p_{i-1} - beta(i-1,i) p_{i-2};  phi = SiLU(p)
-    float t = tanhf(x);
-    float dt = 1.0f - t * t;
+    // params[0] != 0 ("pre-squashed"): the input already is t = dropout(tanh(x)) (gram_kan_layers.py:176-179), no tanh here
+    const bool pre = kc_gram_presquashed(B);
+    float t = pre ? x : tanhf(x);
+    float dt = pre ? 1.0f : 1.0f - t * t;
     float p0 = 1.0f, p1 = t, d0 = 0.0f, d1 = 1.0f;
     phi[0] = kc_silu(1.0f);
     if (dphi) dphi[0] = 0.0f;
@@ -244,7 +254,7 @@ __device__ inline void kc_eval_basis(const KcBasisCtx& B, float x, float* phi, f
 // dphi_d = gradient arriving at Phi_{c,d}.  (autograd path through gram_kan_layers.py:150-170.)
 __device__ inline void kc_gram_dbeta(const KcBasisCtx& B, float x, const float* g, int gstride, float* acc) {
   const int nb = B.nb;
-  float t = tanhf(x);
+  float t = kc_gram_presquashed(B) ? x : tanhf(x);
   for (int n = 1; n <= nb - 2; ++n) {
     // q_i = d p_i / d beta_n : q_i = t q_{i-1} - [i-1 == n] p_{i-2} - beta_{i-1} q_{i-2}
     float p0 = 1.0f, p1 = t, q0 = 0.0f, q1 = 0.0f, s = 0.0f;

@@ -153,6 +153,7 @@ kc_norm_bwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __restri
                    int phase) {
   // phase 0: instance norm, everything in one kernel.  phase 1: batch norm, partial sums only.
   // phase 2: batch norm, write dz using the per-channel sums in chan_sums[0][c] (sum dzhat), [1][c] (sum dzhat*zhat).
+  // phase 3: batch norm with given (running) statistics: they are constants, no mean terms (m1 = m2 = 0).
   __shared__ float sh[32];
   const int plane = blockIdx.x, n = plane / d.c, ch = plane % d.c;
   const long long off = (long long)n * d.batch_stride + (long long)ch * d.hw;
@@ -201,7 +202,7 @@ kc_norm_bwd_kernel(const __grid_constant__ kc_norm_desc d, const float* __restri
     if (phase == 1) return;
   }
   float m1, m2;     // mean_G(dzhat), mean_G(dzhat*zhat)
-  if (d.norm == KC_NORM_NONE) { m1 = 0.0f; m2 = 0.0f; }
+  if (d.norm == KC_NORM_NONE || phase == 3) { m1 = 0.0f; m2 = 0.0f; }
   else if (phase == 0) { m1 = s_dv * g / (float)d.hw; m2 = s_dvz * g / (float)d.hw; }
   else {
     float cnt = (float)d.n * (float)d.hw;
@@ -255,6 +256,22 @@ kc_partials_reduce_kernel(const __grid_constant__ kc_norm_desc d, const float* _
   }
 }
 
+// GRAM d/d beta_weights: rows [1 + r][KC_MAX_BASIS] of per-block partial sums -> row 0.  One block; thread (j, s) adds rows
+// s, s + 64, ... in order, then the 64 strided sums are added in order: the result does not depend on scheduling.
+__global__ void __launch_bounds__(KC_MAX_BASIS * 64) kc_dbeta_reduce_kernel(float* __restrict__ buf, long long nrows) {
+  __shared__ float sh[64][KC_MAX_BASIS];
+  const int j = threadIdx.x % KC_MAX_BASIS, s = threadIdx.x / KC_MAX_BASIS;
+  float acc = 0.0f;
+  for (long long r = s; r < nrows; r += 64) acc += buf[(1 + r) * KC_MAX_BASIS + j];
+  sh[s][j] = acc;
+  __syncthreads();
+  if (s == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < 64; ++k) t += sh[k][j];
+    buf[j] = t;
+  }
+}
+
 int check_norm_desc(const kc_norm_desc* d) {
   if (!d) KC_FAIL(KC_ERR_INVALID, "null kc_norm_desc");
   if (d->n <= 0 || d->c <= 0 || d->hw <= 0) KC_FAIL(KC_ERR_INVALID, "kc_norm_desc: n, c, hw must be positive");
@@ -266,6 +283,150 @@ int check_norm_desc(const kc_norm_desc* d) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm over the features of a row + output activation: the tail of the fully-connected KANLayer
+// (kan_layers.py:110-112: layer_norm(base + spline) -> prelu).  Rows are few and short (MLP heads), one block per row.
+//   v = gamma[f] * zhat + beta[f],  y = act(v)
+//   dv = dy * act'(v), dzhat = dv * gamma[f], dz = rstd * (dzhat - mean_f(dzhat) - zhat * mean_f(dzhat * zhat))
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(kNT)
+kc_layernorm_fwd_kernel(const __grid_constant__ kc_rownorm_desc d, const float* __restrict__ z, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ alpha_p, float* __restrict__ y,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ float sh[32];
+  const int row = blockIdx.x, F = d.features;
+  const float* zp = z + (long long)row * F;
+  float* yp = y + (long long)row * F;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) s += zp[i];
+  const float mean = block_sum(s, sh) / (float)F;
+  float m2 = 0.0f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) { const float t = zp[i] - mean; m2 = fmaf(t, t, m2); }
+  const float rstd = rsqrtf(block_sum(m2, sh) / (float)F + d.eps);          // biased variance, like F.layer_norm
+  if (threadIdx.x == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float zh = (zp[i] - mean) * rstd;
+    const float v = d.affine ? fmaf(zh, gamma[i], beta[i]) : zh;
+    yp[i] = out_act(d.out_act, v, alpha);
+  }
+}
+
+__global__ void __launch_bounds__(kNT)
+kc_layernorm_bwd_kernel(const __grid_constant__ kc_rownorm_desc d, const float* __restrict__ dy, const float* __restrict__ z,
+                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ alpha_p, float* __restrict__ dz,
+                        float* __restrict__ row_dalpha) {
+  __shared__ float sh[32];
+  const int row = blockIdx.x, F = d.features;
+  const float* zp = z + (long long)row * F;
+  const float* gp = dy + (long long)row * F;
+  float* dzp = dz + (long long)row * F;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  float s1 = 0.0f, s2 = 0.0f, sa = 0.0f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float zh = (zp[i] - mean) * rstd;
+    const float g = d.affine ? gamma[i] : 1.0f;
+    const float v = d.affine ? fmaf(zh, g, beta[i]) : zh;
+    const float dzh = gp[i] * out_act_grad(d.out_act, v, alpha) * g;
+    s1 += dzh;
+    s2 = fmaf(dzh, zh, s2);
+    if (d.out_act == KC_OUT_PRELU && !(v > 0.0f)) sa = fmaf(gp[i], v, sa);
+  }
+  s1 = block_sum(s1, sh) / (float)F;
+  s2 = block_sum(s2, sh) / (float)F;
+  sa = block_sum(sa, sh);
+  if (threadIdx.x == 0) row_dalpha[row] = sa;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float zh = (zp[i] - mean) * rstd;
+    const float g = d.affine ? gamma[i] : 1.0f;
+    const float v = d.affine ? fmaf(zh, g, beta[i]) : zh;
+    const float dzh = gp[i] * out_act_grad(d.out_act, v, alpha) * g;
+    dzp[i] = rstd * (dzh - s1 - zh * s2);
+  }
+}
+
+// dgamma[f] = sum_rows dv * zhat, dbeta[f] = sum_rows dv (thread per feature, rows in order: coalesced and deterministic);
+// the block after the last feature block adds the per-row dalpha partials.
+__global__ void __launch_bounds__(kNT)
+kc_layernorm_param_grad_kernel(const __grid_constant__ kc_rownorm_desc d, const float* __restrict__ dy, const float* __restrict__ z,
+                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ alpha_p, const float* __restrict__ row_dalpha,
+                               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dalpha) {
+  __shared__ float sh[32];
+  const int F = d.features, nfb = (F + kNT - 1) / kNT;
+  if ((int)blockIdx.x == nfb) {
+    float a = 0.0f;
+    for (int r = threadIdx.x; r < d.rows; r += blockDim.x) a += row_dalpha[r];
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0 && dalpha) dalpha[0] = a;
+    return;
+  }
+  const int f = blockIdx.x * kNT + threadIdx.x;
+  if (f >= F || !d.affine) return;
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  const float g = gamma[f], b = beta[f];
+  float sg = 0.0f, sb = 0.0f;
+  for (int r = 0; r < d.rows; ++r) {
+    const float zh = (z[(long long)r * F + f] - mean_in[r]) * rstd_in[r];
+    const float dv = dy[(long long)r * F + f] * out_act_grad(d.out_act, fmaf(zh, g, b), alpha);
+    sg = fmaf(dv, zh, sg);
+    sb += dv;
+  }
+  if (dgamma) dgamma[f] = sg;
+  if (dbeta) dbeta[f] = sb;
+}
+
+int check_rownorm_desc(const kc_rownorm_desc* d) {
+  if (!d) KC_FAIL(KC_ERR_INVALID, "null kc_rownorm_desc");
+  if (d->rows <= 0 || d->features <= 0) KC_FAIL(KC_ERR_INVALID, "kc_rownorm_desc: rows and features must be positive");
+  if (d->out_act < KC_OUT_NONE || d->out_act > KC_OUT_SILU) KC_FAIL(KC_ERR_INVALID, "kc_rownorm_desc: bad out_act kind");
+  return KC_OK;
+}
+
+}  // namespace
+
+extern "C" int kc_layernorm_act_fwd(const kc_rownorm_desc* d, const float* z, const float* gamma, const float* beta,
+                                    const float* alpha, float* y, float* mean, float* rstd, void* stream) {
+  int rc = check_rownorm_desc(d);
+  if (rc != KC_OK) return rc;
+  if (!z || !y || !mean || !rstd) KC_FAIL(KC_ERR_INVALID, "kc_layernorm_act_fwd: null pointer");
+  if (d->affine && (!gamma || !beta)) KC_FAIL(KC_ERR_INVALID, "kc_layernorm_act_fwd: affine needs gamma and beta");
+  if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_layernorm_act_fwd: PReLU needs alpha");
+  kc_layernorm_fwd_kernel<<<d->rows, kNT, 0, (cudaStream_t)stream>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
+  KC_LAUNCH_CHECK("kc_layernorm_fwd_kernel");
+  return KC_OK;
+}
+
+extern "C" int kc_layernorm_act_bwd(const kc_rownorm_desc* d, const float* dy, const float* z, const float* mean,
+                                    const float* rstd, const float* gamma, const float* beta, const float* alpha, float* dz,
+                                    float* dgamma, float* dbeta, float* dalpha, float* partials, void* stream) {
+  int rc = check_rownorm_desc(d);
+  if (rc != KC_OK) return rc;
+  if (!dy || !z || !dz || !mean || !rstd || !partials) KC_FAIL(KC_ERR_INVALID, "kc_layernorm_act_bwd: null pointer");
+  if (d->affine && (!gamma || !beta)) KC_FAIL(KC_ERR_INVALID, "kc_layernorm_act_bwd: affine needs gamma and beta");
+  if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_layernorm_act_bwd: PReLU needs alpha");
+  cudaStream_t st = (cudaStream_t)stream;
+  kc_layernorm_bwd_kernel<<<d->rows, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials);
+  KC_LAUNCH_CHECK("kc_layernorm_bwd_kernel");
+  if (dgamma || dbeta || dalpha) {
+    const int nfb = (d->features + kNT - 1) / kNT;
+    kc_layernorm_param_grad_kernel<<<nfb + 1, kNT, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, partials, dgamma, dbeta, dalpha);
+    KC_LAUNCH_CHECK("kc_layernorm_param_grad_kernel");
+  }
+  return KC_OK;
+}
+
+int kc_dbeta_reduce(float* dbeta, long long nrows, void* stream) {
+  kc_dbeta_reduce_kernel<<<1, KC_MAX_BASIS * 64, 0, (cudaStream_t)stream>>>(dbeta, nrows);
+  KC_LAUNCH_CHECK("kc_dbeta_reduce_kernel");
+  return KC_OK;
+}
+
 extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const float* gamma, const float* beta,
                                const float* alpha, float* y, float* mean, float* rstd, float* scratch, void* stream) {
   int rc = check_norm_desc(d);
@@ -276,8 +437,7 @@ extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const int planes = d->n * d->c;
   const int nt = d->hw >= kBigPlane ? kNTBig : kNT;
-  if (d->norm == KC_NORM_BATCH) {
-    if (!scratch) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: batch norm needs a 2*n*c float scratch buffer");
+  if (d->norm == KC_NORM_BATCH && scratch != nullptr) {      // scratch == NULL: mean / rstd are given (eval mode)
     float* pmean = scratch;
     float* pm2 = scratch + planes;
     kc_plane_stats_kernel<<<planes, nt, 0, st>>>(*d, z, pmean, pm2);
@@ -292,7 +452,8 @@ extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const floa
 
 extern "C" int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, const float* mean,
                                const float* rstd, const float* gamma, const float* beta, const float* alpha,
-                               float* dz, float* dgamma, float* dbeta, float* dalpha, float* partials, void* stream) {
+                               float* dz, float* dgamma, float* dbeta, float* dalpha, float* partials, int given_stats,
+                               void* stream) {
   int rc = check_norm_desc(d);
   if (rc != KC_OK) return rc;
   if (!dy || !z || !dz || !partials) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: null pointer");
@@ -301,7 +462,17 @@ extern "C" int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const int nt = d->hw >= kBigPlane ? kNTBig : kNT;
   const int planes = d->n * d->c;
-  if (d->norm == KC_NORM_BATCH) {
+  if (d->norm == KC_NORM_BATCH && given_stats) {
+    // eval-mode batch norm: the statistics are constants, so dz = rstd * gamma * dy * act'(v) - the NONE formula with the
+    // given mean / rstd (m1 = m2 = 0).  The kernel only branches on d.norm for m1 / m2, so run it with a patched descriptor
+    // whose statistics are indexed per channel.
+    kc_norm_bwd_kernel<<<planes, nt, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 3);
+    KC_LAUNCH_CHECK("kc_norm_bwd_kernel(given stats)");
+    if (dgamma || dbeta || dalpha) {
+      kc_partials_reduce_kernel<<<d->c + 1, kNT, 0, st>>>(*d, partials, dgamma, dbeta, dalpha);
+      KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
+    }
+  } else if (d->norm == KC_NORM_BATCH) {
     // partials layout: [3][planes] plane sums, then [2][c] channel sums
     float* chan = partials + 3 * (size_t)planes;
     kc_norm_bwd_kernel<<<planes, nt, 0, st>>>(*d, dy, z, mean, rstd, gamma, beta, alpha, dz, partials, nullptr, 1);

@@ -113,7 +113,8 @@ int pool_check(long long planes, int h, int w, int k, int s, int ho, int wo) {
 
 int pool_blocks(long long total) {
   long long b = (total + 255) / 256;
-  return (int)(b > 148LL * 32 ? 148LL * 32 : (b < 1 ? 1 : b));
+  const long long cap = (long long)kc_sm_count() * 32;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
 bool fast2(const void* p0, const void* p1, const void* p2, int h, int w, int k, int s) {

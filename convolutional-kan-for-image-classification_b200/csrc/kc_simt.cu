@@ -141,8 +141,8 @@ kc_dgrad_simt_kernel(const __grid_constant__ kc_desc d, const float* __restrict_
   int* pix_n = reinterpret_cast<int*>(smem_raw + ((sizeof(KcBasisCtx) + 15) / 16) * 16);
   int* pix_iy = pix_n + kTilePix;
   int* pix_ix = pix_iy + kTilePix;
-  float* red = reinterpret_cast<float*>(pix_ix + kTilePix);          // KC_MAX_BASIS floats for the dbeta reduction
-  float* dz_s = red + KC_MAX_BASIS;                                   // [tch][kDgCo][64]
+  float* red = reinterpret_cast<float*>(pix_ix + kTilePix);          // [warps][KC_MAX_BASIS] floats for the dbeta reduction
+  float* dz_s = red + (kThreads / 32) * KC_MAX_BASIS;                 // [tch][kDgCo][64]
   float* W_s = dz_s + tch * kDgCo * kTilePix;                         // [tch][kDgCo][kDgCh][kDgWBP]
   const bool has_base = d.act != KC_ACT_NONE;
   const int nb = d.nb, WB = nb + (has_base ? 1 : 0);
@@ -254,16 +254,20 @@ kc_dgrad_simt_kernel(const __grid_constant__ kc_desc d, const float* __restrict_
     }
   }
   if (d.basis == KC_BASIS_GRAM && dbeta != nullptr) {
-    for (int nn = 1; nn <= nb - 2; ++nn) {
-      float v = 0.0f;
+    // deterministic: warp sums -> per-warp slots -> fixed-order block sum -> this block's row of the partials buffer
+    // (kc_dbeta_reduce_kernel adds the rows in fixed order; no atomics anywhere)
 #pragma unroll
-      for (int j = 0; j < KC_MAX_BASIS; ++j)
-        if (j == nn) v = dbl[j];
-      v = kc_warp_sum(v);
-      if ((tid & 31) == 0) atomicAdd(&red[nn], v);
+    for (int nn = 0; nn < KC_MAX_BASIS; ++nn) {
+      const float v = kc_warp_sum(dbl[nn]);
+      if ((tid & 31) == 0) red[(tid >> 5) * KC_MAX_BASIS + nn] = v;
     }
     __syncthreads();
-    if (tid >= 1 && tid <= nb - 2) atomicAdd(&dbeta[tid], red[tid]);
+    if (tid < KC_MAX_BASIS) {
+      float v = 0.0f;
+      for (int w = 0; w < kThreads / 32; ++w) v += red[w * KC_MAX_BASIS + tid];
+      const long long row = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+      dbeta[(1 + row) * KC_MAX_BASIS + tid] = (tid >= 1 && tid <= nb - 2) ? v : 0.0f;
+    }
   }
 }
 
@@ -411,7 +415,7 @@ WgradPlan plan_wgrad(const kc_desc* d) {
   pl.ntchunks = (T + pl.tch - 1) / pl.tch;
   const long long P = (long long)d->n * d->ho * d->wo;
   const long long base_blocks = (long long)d->cin * pl.ntchunks * ((d->cout + kTileCout - 1) / kTileCout);
-  long long want = (4LL * 148 + base_blocks - 1) / base_blocks;
+  long long want = (4LL * kc_sm_count() + base_blocks - 1) / base_blocks;
   long long max_split = (P + 4 * kWgPix - 1) / (4 * kWgPix);     // at least 128 pixels per split
   long long ns = want < 1 ? 1 : want;
   if (ns > max_split) ns = max_split;
@@ -450,6 +454,11 @@ extern "C" int kc_conv_fwd_f32(const kc_desc* d, const float* x_base, const floa
   return KC_OK;
 }
 
+long long kc_simt_dgrad_blocks(const kc_desc* d) {      // thread blocks of kc_dgrad_simt_kernel = rows of GRAM dbeta partials
+  const long long P = (long long)d->n * d->h * d->w;
+  return ((P + kTilePix - 1) / kTilePix) * ((d->cin + kDgCh - 1) / kDgCh);
+}
+
 extern "C" int kc_conv_dgrad_f32(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                                  const float* w_base, const float* w_basis, const float* beta, float* dx_base,
                                  float* dx_basis, float* dbeta, void* stream) {
@@ -460,7 +469,7 @@ extern "C" int kc_conv_dgrad_f32(const kc_desc* d, const float* dz, const float*
   if (has_base && (!x_base || !w_base)) KC_FAIL(KC_ERR_INVALID, "kc_conv_dgrad_f32: base branch needs x_base and w_base");
   if (d->basis == KC_BASIS_GRAM && !beta) KC_FAIL(KC_ERR_INVALID, "kc_conv_dgrad_f32: GRAM basis needs beta_weights");
   const int T = d->kh * d->kw;
-  size_t fixed = basis_ctx_bytes() + 3 * kTilePix * sizeof(int) + KC_MAX_BASIS * sizeof(float);
+  size_t fixed = basis_ctx_bytes() + 3 * kTilePix * sizeof(int) + (kThreads / 32) * KC_MAX_BASIS * sizeof(float);
   int per_tap = kDgCo * kTilePix + kDgCo * kDgCh * kDgWBP;
   int tch = pick_tch(T, per_tap, fixed, 96 * 1024);
   size_t smem = fixed + (size_t)tch * per_tap * 4;
@@ -470,6 +479,7 @@ extern "C" int kc_conv_dgrad_f32(const kc_desc* d, const float* dz, const float*
   kc_dgrad_simt_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(*d, dz, x_base, x_basis, w_base, w_basis, beta,
                                                                       dx_base, dx_basis, dbeta, tch);
   KC_LAUNCH_CHECK("kc_dgrad_simt_kernel");
+  if (d->basis == KC_BASIS_GRAM && dbeta != nullptr) return kc_dbeta_reduce(dbeta, (long long)grid.x * grid.y, stream);
   return KC_OK;
 }
 
@@ -497,7 +507,7 @@ extern "C" int kc_conv_wgrad_f32(const kc_desc* d, const float* dz, const float*
   const int WB = d->nb + (has_base ? 1 : 0), T = d->kh * d->kw;
   long long total = (long long)d->cout * d->cin * T * WB;
   int blocks = (int)((total + kThreads - 1) / kThreads);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > kc_sm_count() * 8) blocks = kc_sm_count() * 8;
   kc_wgrad_reduce_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(*d, (const float*)workspace, dw_base, dw_basis, pl.nsplit);
   KC_LAUNCH_CHECK("kc_wgrad_reduce_kernel");
   return KC_OK;

@@ -33,6 +33,7 @@
 size_t kc_tc_wgrad_ws_bytes(const kc_desc* d, int which);                                              // kc_tc_wgrad.cu
 int kc_tc_wgrad_phi_layout(const kc_desc* d, long long* L, int* spline_planes, int* base_planes);    // kc_tc_wgrad.cu
 int kc_tc_phi_prepass(const kc_desc* d, const float* x_base, const float* x_basis, const float* beta, void* phi, void* stream);
+long long kc_simt_dgrad_blocks(const kc_desc* d);                                                        // kc_simt.cu
 
 namespace {
 
@@ -90,53 +91,7 @@ constexpr int kModeFwd = 0, kModeDgrad = 1;
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-// ---- optional timeline trace (debug): kc_debug_trace() points g_trace at a device buffer of 4 x 1024 clock stamps;
-// one CTA records one stamp per pipeline event of representative threads.  nullptr (default) = disabled.
-__device__ long long* g_trace = nullptr;
-__device__ int g_dbg_flag = 0;          // EXPERIMENT: bit0 = weight loader copies half of each stage (timing probe, wrong results)
-struct Tracer {
-  long long* p; int n;
-  __device__ Tracer(int role, bool on) {
-    long long* t = g_trace;
-    p = (on && t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? t + role * 1024 : nullptr; n = 0;
-  }
-  __device__ __forceinline__ void stamp() { if (p != nullptr && n < 1024) p[n++] = clock64(); }
-};
-
-// ---------------------------------------------------------------------------------------------------------
-// basis -> 8 packed bf16
-// ---------------------------------------------------------------------------------------------------------
-// Uniform cubic B-spline, closed form: the 4 non-zero weights land at j = i0-3 .. i0.
-// Branch-free: the 4 weights are packed into 64 bits and moved to their slots with clamped PTX shifts (shift
-// amounts >= 64, including "negative" ones, yield 0), so independent evaluations can be interleaved by the compiler.
-__device__ __forceinline__ unsigned long long shl64(unsigned long long v, int s) {
-  unsigned long long r;
-  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
-  return r;
-}
-__device__ __forceinline__ unsigned long long shr64(unsigned long long v, int s) {
-  unsigned long long r;
-  asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
-  return r;
-}
-__device__ __forceinline__ uint4 cubic8(float x, float t0, float inv_h, int nintervals, bool valid) {
-  const float u = (x - t0) * inv_h;
-  const bool ok = valid && (u >= 0.0f) && (u < (float)nintervals);    // outside the knot span / NaN: all-zero row
-  const float fi = floorf(u);
-  const float f = u - fi;
-  const int i0 = min(max((int)fi, 0), 15);
-  const float s6 = 1.0f / 6.0f;
-  const float w0 = fmaf(fmaf(fmaf(-s6, f, 0.5f), f, -0.5f), f, s6);
-  const float w1 = fmaf(fmaf(0.5f, f, -1.0f) * f, f, 4.0f * s6);
-  const float w2 = fmaf(fmaf(fmaf(-0.5f, f, 0.5f), f, 0.5f), f, s6);
-  const float w3 = f * f * f * s6;
-  unsigned long long v = (unsigned long long)pack_bf16(w0, w1) | ((unsigned long long)pack_bf16(w2, w3) << 32);
-  v = ok ? v : 0ull;
-  const int sh = 16 * (i0 - 3);
-  const unsigned long long lo = shl64(v, sh) | shr64(v, -sh);
-  const unsigned long long hi = shr64(v, 64 - sh) | shl64(v, sh - 64);
-  return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
-}
+KC_TRACE_DECL(g_trace)
 
 // generic (any family) evaluators are kept out of line so that their local arrays do not inflate the register
 // allocation of the closed-form cubic fast path
@@ -214,6 +169,7 @@ __device__ __forceinline__ float cubic8_dot_grad(float x, float t0, float inv_h,
     acc = fmaf(__uint_as_float(r[2 * p]), __uint_as_float(w[p] << 16), acc);
     acc = fmaf(__uint_as_float(r[2 * p + 1]), __uint_as_float(w[p] & 0xffff0000u), acc);
   }
+  if (tc_nonfinite(x)) acc = __int_as_float(0x7fc00000);               // the reference's autograd yields NaN here
   return acc * inv_h;
 }
 
@@ -363,7 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
         for (int cl = 0; cl < 2; ++cl)
           xv[k][cl] = (offs[k] >= 0 && c0 + cl < cin) ? __ldg(xc + (long long)cl * HW + offs[k]) : 0.0f;
     };
-    Tracer trp(0, tp == 0);
+    KC_TRACER(trp, g_trace, 0, tp == 0);
     if (nb == 8 && g.nsc > 0) fetch8(0, xnext);
     if (MODE == kModeDgrad) {
       // copy chunks: k-core = 8 consecutive output channels of one flat position = one 16-byte vector of the plane-major
@@ -506,7 +462,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       const int nsub = (g.nsub - mw + nmw - 1) / nmw;       // sub-tiles mw, mw + nmw, ... of this issuer
       int stage = 0, buf = 0;
       uint32_t bphase = 0, aphase = 0;
-      Tracer trm(1, lane == 0 && mw == 0);
+      KC_TRACER(trm, g_trace, 1, lane == 0 && mw == 0);
       for (int q = 0; q < nchunks; ++q) {
         const int nk2 = chunk_cols(g, q) >> 1;
         const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);      // 16-byte units per tap image
@@ -551,15 +507,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t bphase = 0;
       const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
-      Tracer trl(2, true);
+      KC_TRACER(trl, g_trace, 2, true);
       for (int q = 0; q < nchunks; ++q) {
         const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
         for (int t = 0; t < T; t += g.tps) {
           mbar_wait(&b_empty[stage], bphase ^ 1);
           trl.stamp();                               // b_empty acquired
-          const uint32_t cbytes = (g_dbg_flag & 1) ? bytes / 2 : bytes;
-          mbar_arrive_expect_tx(&b_full[stage], cbytes);
-          bulk_g2s(bst0 + stage * bstage_bytes, wsrc, cbytes, &b_full[stage]);
+          mbar_arrive_expect_tx(&b_full[stage], bytes);
+          bulk_g2s(bst0 + stage * bstage_bytes, wsrc, bytes, &b_full[stage]);
           wsrc += bytes;
           if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
         }
@@ -571,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     // ================================ epilogue: TMEM -> registers -> z (fp32 NCHW) =====================
     // All 16 producer warps: warp w reads the TMEM lanes of its hardware quarter (w % 4) and every fourth group of 16
     // columns (w / 4); a store instruction writes one output channel of 32 consecutive positions (128 B).
-    Tracer tre(3, threadIdx.x == 0);
+    KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);
     tre.stamp();                                     // producer work done
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -622,7 +577,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     const bool gram = d.basis == KC_BASIS_GRAM && a.dbeta != nullptr;
     const int quarter = warp & 3, cgrp = warp >> 2;
     const int c0 = nt * 16 + cgrp * 4;
-    Tracer tre(3, threadIdx.x == 0);
+    KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);
     tre.stamp();                                     // epilogue entered (producer loop done)
     if (g.fast_cubic && !gram && same_x) {
       // ---- closed-form cubic path (nb == 8): everything stays in registers ----------------------------------------
@@ -747,13 +702,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
         }
       }
       if (gram) {
-        for (int nn = 1; nn <= nb - 2; ++nn) {
-          float v = 0.0f;
+        // deterministic: every epilogue warp writes its own row of the partials buffer (zeros where it had no work);
+        // kc_dbeta_reduce_kernel adds the rows in fixed order
+        const long long row = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16 + warp;
 #pragma unroll
-          for (int j = 0; j < KC_MAX_BASIS; ++j)
-            if (j == nn) v = dbl[j];
-          v = kc_warp_sum(v);
-          if (lane == 0 && v != 0.0f) atomicAdd(&a.dbeta[nn], v);
+        for (int nn = 0; nn < KC_MAX_BASIS; ++nn) {
+          const float v = kc_warp_sum(dbl[nn]);
+          if (lane == nn) a.dbeta[(1 + row) * KC_MAX_BASIS + nn] = (nn >= 1 && nn <= nb - 2) ? v : 0.0f;
         }
       }
     }
@@ -853,7 +808,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     const int r = lane / kPL, pl = lane % kPL;
     const int len = r < d.kh - 1 ? g.SS : g.nrows - (d.kh - 1) * g.SS;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    Tracer trp(0, lane == 0);
+    KC_TRACER(trp, g_trace, 0, lane == 0);
     int buf = 0;
     uint32_t ph = 1;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -892,7 +847,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     if (lane == 0) {
       int stage = 0;
       uint32_t bphase = 1;
-      Tracer trl(2, true);
+      KC_TRACER(trl, g_trace, 2, true);
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nt = (int)(tile % g.n_ntiles);
         const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
@@ -924,7 +879,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     int stage = 0, buf = 0;
     uint32_t bphase = 0, aphase = 0;
     uint32_t it = 0;
-    Tracer trm(1, lane == 0 && mw == 0);
+    KC_TRACER(trm, g_trace, 1, lane == 0 && mw == 0);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
       trm.stamp();                                           // tile start
@@ -1043,7 +998,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       tmem_ld8(taddr, r);
       if (wb > 8) tmem_ld1(taddr + 8u, r + 8); else r[8] = 0u;
     };
-    Tracer tre(3, threadIdx.x == 0);
+    KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);
     float xn[kCh];
     int c0n = 0;
     int offn = nsteps > 0 ? locate(0, c0n) : -1;
@@ -1317,20 +1272,6 @@ __global__ void __launch_bounds__(256) kc_dz_flat_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------------------------------------
 // host-side geometry
 // ---------------------------------------------------------------------------------------------------------
-bool knots_uniform_cubic(const kc_desc* d, float* t0, float* inv_h) {
-  if (d->basis != KC_BASIS_BSPLINE || d->order != 3 || d->nb != 8 || d->nparams != 12) return false;
-  double h = ((double)d->params[11] - (double)d->params[0]) / 11.0;
-  if (!(h > 0)) return false;
-  for (int i = 0; i < 12; ++i) {
-    double e = (double)d->params[0] + h * i - (double)d->params[i];
-    if (e < 0) e = -e;
-    if (e > 1e-5 * h) return false;
-  }
-  *t0 = d->params[0];
-  *inv_h = (float)(1.0 / h);
-  return true;
-}
-
 size_t tc_fixed_smem() { return (size_t)kNumBars * 8 + 16 + sizeof(KcBasisCtx) + 128; }
 
 // Common tail of the forward / dgrad geometry: choose nsub, ring depths and shared-memory carve-up.
@@ -1345,6 +1286,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
   bool found = false;
   double best_cost = 0.0;
   const int nchunks = (kcores + kPL - 1) / kPL;
+  const int sms = kc_sm_count();
   for (int nsub = 4; nsub >= 1; --nsub) {
     if (nsub * g->ntile > 512) continue;
     const int mcta = nsub * kTileM;
@@ -1355,7 +1297,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
     const long long mtiles = (g->L + mcta - 1) / mcta;
     const long long ctas = mtiles * g->n_ntiles;
     // CTAs do not run in lockstep, so wave quantisation only matters while the grid is a wave or two
-    const double waves = ctas < 2 * 148 ? (double)((ctas + 147) / 148) : (double)ctas / 148.0;
+    const double waves = ctas < 2 * sms ? (double)((ctas + sms - 1) / sms) : (double)ctas / (double)sms;
     const double mma_cyc = (double)nchunks * T * 2.0 * (g->ntile / 2 > 48 ? g->ntile / 2 : 48);     // per sub-tile
     const double b_cyc = (double)nchunks * T * (double)btap / 32.0;
     const double cta_cyc = (nsub * mma_cyc > b_cyc ? nsub * mma_cyc : b_cyc) + 8000.0 + nsub * 3000.0;
@@ -1389,7 +1331,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
   g->tmem_cols = 32;
   while (g->tmem_cols < g->nsub * g->ntile) g->tmem_cols *= 2;
   g->wimg_bytes_per_ntile = (long long)T * g->ntile * 16 * kcores;
-  g->fast_cubic = knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
+  g->fast_cubic = kc_knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
   return KC_OK;
 }
 
@@ -1425,7 +1367,7 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
   // Persistent kernel (closed-form cubic basis): N tile = cpt channels x wb columns padded to 128, two sub-tiles per
   // accumulator set, two sets in TMEM (4 x 128 = 512 columns).
   float t0 = 0.0f, inv_h = 0.0f;
-  const bool cubic = knots_uniform_cubic(d, &t0, &inv_h);
+  const bool cubic = kc_knots_uniform_cubic(d, &t0, &inv_h);
   if ((cubic || d->basis == KC_BASIS_RBF || d->basis == KC_BASIS_CHEBY) && d->kh * d->kw <= 64) {
     // channels per N tile: cpt * wb <= 128 columns, <= 4 (8) channels per epilogue warp, and the 8-column TMEM read of the
     // last channel must stay inside the tile ((cpt - 1) * wb + 8 <= 128)
@@ -1505,7 +1447,7 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
       g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = 1; g->na = 3;
       g->bstages = bst; g->mtiles = (g->L + mcta - 1) / mcta; g->smem_bytes = fixed + bst * btap; g->tmem_cols = 512;
       g->wimg_bytes_per_ntile = (long long)T * ntile * 16 * kcores;
-      g->fast_cubic = knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
+      g->fast_cubic = kc_knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
       return KC_OK;
     }
   }
@@ -1627,6 +1569,20 @@ extern "C" size_t kc_tc_bytes(const kc_desc* d, int which) {
   return 0;
 }
 
+// GRAM only: floats of the `dbeta` buffer (KC_MAX_BASIS results + one partial row per thread block / epilogue warp).
+extern "C" size_t kc_dbeta_floats(const kc_desc* d, int tc) {
+  if (kc_validate_desc(d) != KC_OK || d->basis != KC_BASIS_GRAM) return 0;
+  long long rows;
+  if (tc) {
+    TcGeom g;
+    if (tc_dgrad_geometry(d, &g) != KC_OK || g.persistent) return 0;
+    rows = g.mtiles * g.n_ntiles * 16;
+  } else {
+    rows = kc_simt_dgrad_blocks(d);
+  }
+  return (size_t)(1 + rows) * KC_MAX_BASIS;
+}
+
 extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const float* w_basis, void* packed_fwd,
                                   void* packed_dgrad, void* stream) {
   int rc = kc_validate_desc(d);
@@ -1641,7 +1597,8 @@ extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const f
   const int T = d->kh * d->kw;
   long long total = g.wimg_bytes_per_ntile / 16 * g.n_ntiles / T + (long long)kPL * g.ntile * g.n_ntiles;   // one thread per (vector, all taps)
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int max_blocks = kc_sm_count() * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
   if (packed_fwd != nullptr) {
     const int nchunks = g.nsc + (d->act != KC_ACT_NONE ? g.nbc : 0);
     if (d->basis != KC_BASIS_GRAM && T <= kPackMaxT && nchunks <= 65535 && g.n_ntiles <= 65535) {
@@ -1659,7 +1616,7 @@ extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const f
     a.g = gd; a.out = (uint4*)packed_dgrad;
     total = gd.wimg_bytes_per_ntile / 16 * gd.n_ntiles / T + (long long)kPL * gd.ntile * gd.n_ntiles;
     blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
     kc_pack_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
     KC_LAUNCH_CHECK("kc_pack_dgrad_kernel");
   }
@@ -1704,9 +1661,7 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
     if (rc != KC_OK) return rc;
     a.dzf = (const unsigned char*)phi_out;
     a.phi_base_plane0 = splanes;
-    int dev = 0, sms = 148;
-    KC_CUDA_CHECK(cudaGetDevice(&dev));
-    KC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = kc_sm_count();
     const long long ntiles = g.mtiles * g.n_ntiles;
     KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     kc_dgrad_persistent_kernel<2><<<(unsigned)(ntiles < sms ? ntiles : sms), kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
@@ -1753,9 +1708,7 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
   a.dzf = (const unsigned char*)workspace; a.cq = g.Cp; a.dx_base = dx_base; a.dx_basis = dx_basis;
   a.dbeta = (d->basis == KC_BASIS_GRAM) ? dbeta : nullptr;
   if (g.persistent) {
-    int dev = 0, sms = 148;
-    KC_CUDA_CHECK(cudaGetDevice(&dev));
-    KC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = kc_sm_count();
     const long long ntiles = g.mtiles * g.n_ntiles;
     const unsigned nctas = (unsigned)(ntiles < sms ? ntiles : sms);
     if (g.fast_cubic) {
@@ -1772,282 +1725,32 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
   kc_tc_kernel<kModeDgrad><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
   KC_LAUNCH_CHECK("kc_tc_kernel<dgrad>");
+  if (a.dbeta != nullptr) return kc_dbeta_reduce(a.dbeta, (long long)grid.x * grid.y * 16, stream);
   return KC_OK;
 }
 
-// Debug only: raw tcgen05.mma rate from resident smem operands, with knobs that mimic the convolution main loop:
-// nsub accumulators used round-robin, a commit every `commit_every` MMAs (0 = only at the end), and `writers` extra
-// warps streaming 16-byte st.shared into an unrelated smem region while the MMAs run.
-__global__ void __launch_bounds__(576, 1) kc_mma_rate_kernel(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters,
-                                                              int a_rowshift, int nsub, int commit_every, int writers,
-                                                              int mn_major, float* out) {
-  extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar, dummy[8];
-  __shared__ uint32_t tmem_ptr;
-  __shared__ volatile int done;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
-  if (tid == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1000000); done = 0; fence_barrier_init(); }
-  if (warp == 17) tmem_alloc(&tmem_ptr, 512);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tb = tmem_ptr;
-  if (tid == 17 * 32) {
-    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
-    const uint32_t abase = smem_u32(sm) + a_rowshift * 16, bbase = smem_u32(sm) + 96 * 1024;
-    long long t0 = clock64();
-    int cnt = 0;
-    for (int it = 0; it < iters; ++it) {
-      for (int s = 0; s < nsub; ++s) {
-        for (int i = 0; i < 2; ++i) {
-          uint64_t ad = make_smem_desc(abase + (mn_major ? s * 16 + i * 256 : s * 2048 + i * 2 * a_lbo), a_lbo, a_sbo);
-          uint64_t bd = make_smem_desc(bbase + (mn_major ? i * 256 : i * 2 * b_lbo), b_lbo, b_sbo);
-          tc_mma_bf16(tb + s * N, ad, bd, idesc, 1u);
-          if (commit_every > 0 && (++cnt % commit_every) == 0) tc_commit(&dummy[(cnt / commit_every) & 7]);
-        }
-      }
-    }
-    tc_commit(&bar);
-    mbar_wait(&bar, 0);
-    long long t1 = clock64();
-    out[0] = (float)(t1 - t0) / (float)(iters * nsub * 2);
-    done = 1;
-  } else if (warp < writers) {
-    uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + tid;
-    uint4 v = make_uint4(tid, 1, 2, 3);
-    while (!done) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dst[k * 512 % 1024] = v;
-      v.x += 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) tmem_dealloc(tb, 512);
-}
-
-extern "C" int kc_debug_mma_rate(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters, int a_rowshift, int nsub,
-                                 int commit_every, int writers, int mn_major, float* cycles) {
-  float* dev = nullptr;
-  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  kc_mma_rate_kernel<<<1, 576, 160 * 1024>>>(N, a_lbo, a_sbo, b_lbo, b_sbo, iters, a_rowshift, nsub, commit_every, writers, mn_major, dev);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
-  cudaFree(dev);
-  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate: %s", cudaGetErrorString(e));
-  return KC_OK;
-}
-
-// Debug only: tcgen05.mma execution rate with the warp-uniform elect issue path, mimicking one ring step of the conv
-// kernels: nsub accumulators x 2 k-steps per iteration, optional commit per iteration, optional writer warps hammering
-// shared memory with 16-byte stores, optional unaligned A view.
-__global__ void __launch_bounds__(576, 1) kc_mma_rate2_kernel(int N, int mn_major, int iters, int nsub, int commit_each, int writers,
-                                                               int a_shift_rows, float* out) {
-  extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar, dummy[8];
-  __shared__ uint32_t tmem_ptr;
-  __shared__ volatile int done;
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1000000); done = 0; fence_barrier_init(); }
-  if (warp == 17) tmem_alloc(&tmem_ptr, 512);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tb = tmem_ptr;
-  if (warp == 17) {
-    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
-    const uint32_t au = (smem_u32(sm) >> 4) + (uint32_t)a_shift_rows, bu = (smem_u32(sm) + 100 * 1024) >> 4;
-    const uint32_t a_pitch = mn_major ? 1168u : 15456u, b_pitch = mn_major ? 1040u : (uint32_t)N * 16u;
-    const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
-    const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
-    const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
-    long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      if (elect_one_sync()) {
-        for (int s = 0; s < nsub; ++s) {
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + s * 128 + ks * a_step));
-            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + ks * b_step));
-            tc_mma_bf16(tb + s * N, ad, bd, idesc, 1u);
-          }
-        }
-        if (commit_each) tc_commit(&dummy[it & 7]);
-      }
-      __syncwarp();
-    }
-    if (elect_one_sync()) tc_commit(&bar);
-    __syncwarp();
-    mbar_wait(&bar, 0);
-    long long t1 = clock64();
-    if (threadIdx.x == 17 * 32) { out[0] = (float)(t1 - t0) / (float)(iters * nsub * 2); done = 1; }
-  } else if (warp < writers) {
-    uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + threadIdx.x;
-    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
-    while (!done) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dst[(k * 512) & 1023] = v;
-      v.x += 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) tmem_dealloc(tb, 512);
-}
-
-extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, int nsub, int commit_each, int writers, int a_shift_rows, float* cycles) {
-  float* dev = nullptr;
-  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  kc_mma_rate2_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, nsub, commit_each, writers, a_shift_rows, dev);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
-  cudaFree(dev);
-  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate2: %s", cudaGetErrorString(e));
-  return KC_OK;
-}
-
-// Debug only: does the A-operand collector hint relieve the shared-memory bound of narrow MMAs?  Pattern of the weight-
-// gradient kernel: per k-step one A tile feeds three MMAs (three taps = three accumulators, B read from shifted rows).
-__global__ void __launch_bounds__(576, 1) kc_mma_rate3_kernel(int N, int mn_major, int iters, int reuse, int writers, float* out) {
-  extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_ptr;
-  __shared__ volatile int done;
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); done = 0; fence_barrier_init(); }
-  if (warp == 17) tmem_alloc(&tmem_ptr, 512);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tb = tmem_ptr;
-  if (warp == 17) {
-    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
-    const uint32_t au = smem_u32(sm) >> 4, bu = (smem_u32(sm) + 100 * 1024) >> 4;
-    const uint32_t a_pitch = mn_major ? 1168u : 15456u, b_pitch = mn_major ? 1168u : (uint32_t)N * 16u + 64u;
-    const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
-    const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
-    const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
-    long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + (ks & 1) * a_step + (ks >> 1) * 3u));
-          const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + (ks & 1) * b_step));
-          if (reuse) {
-            tc_mma_bf16_keep<1>(tb, ad, bd, idesc, 1u);
-            tc_mma_bf16_keep<2>(tb + N, ad, bd + 1u, idesc, 1u);
-            tc_mma_bf16_keep<3>(tb + 2 * N, ad, bd + 2u, idesc, 1u);
-          } else {
-            tc_mma_bf16(tb, ad, bd, idesc, 1u);
-            tc_mma_bf16(tb + N, ad, bd + 1u, idesc, 1u);
-            tc_mma_bf16(tb + 2 * N, ad, bd + 2u, idesc, 1u);
-          }
-        }
-      }
-      __syncwarp();
-    }
-    if (elect_one_sync()) tc_commit(&bar);
-    __syncwarp();
-    mbar_wait(&bar, 0);
-    long long t1 = clock64();
-    if (threadIdx.x == 17 * 32) { out[0] = (float)(t1 - t0) / (float)(iters * 12); done = 1; }
-  } else if (warp < writers) {
-    uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + threadIdx.x;
-    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
-    while (!done) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dst[(k * 512) & 1023] = v;
-      v.x += 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) tmem_dealloc(tb, 512);
-}
-
-extern "C" int kc_debug_mma_rate3(int N, int mn_major, int iters, int reuse, int writers, float* cycles) {
-  float* dev = nullptr;
-  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  kc_mma_rate3_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, reuse, writers, dev);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
-  cudaFree(dev);
-  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate3: %s", cudaGetErrorString(e));
-  return KC_OK;
-}
-
-// Debug only: latency / throughput of cp.async.bulk global->shared.  Each CTA issues `depth` copies of `bytes` back to back
-// (ring of `depth` buffers), `iters` rounds; same_addr != 0 makes every CTA read the same global range.
-__global__ void __launch_bounds__(32, 1) kc_bulk_bench_kernel(const unsigned char* src, int bytes, int depth, int iters,
-                                                               int same_addr, long long span, float* out) {
-  extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bars[8];
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned char* base = src + (same_addr ? 0 : ((long long)blockIdx.x * (long long)bytes * depth) % span);
-    long long off = 0;
-    long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      for (int k = 0; k < depth; ++k) {
-        mbar_arrive_expect_tx(&bars[k], (uint32_t)bytes);
-        bulk_g2s(sm + (size_t)k * bytes, base + off, (uint32_t)bytes, &bars[k]);
-        off = (off + bytes) % (span / 2);
-      }
-      for (int k = 0; k < depth; ++k) mbar_wait(&bars[k], it & 1);
-    }
-    long long t1 = clock64();
-    if (blockIdx.x == 0) out[0] = (float)(t1 - t0) / (float)iters;
-  }
-}
-
-extern "C" int kc_debug_bulk_bench(const void* src, long long span, int bytes, int depth, int iters, int nctas, int same_addr,
-                                   float* cycles_per_round) {
-  float* dev = nullptr;
-  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_bulk_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes * depth));
-  kc_bulk_bench_kernel<<<nctas, 32, (size_t)bytes * depth>>>((const unsigned char*)src, bytes, depth, iters, same_addr, span, dev);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(cycles_per_round, dev, sizeof(float), cudaMemcpyDeviceToHost);
-  cudaFree(dev);
-  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_bulk_bench: %s", cudaGetErrorString(e));
-  return KC_OK;
-}
-
-// Debug only (not part of include/kanconv.h): enable/disable the timeline trace of kc_fwd_tc_kernel.
-// Debug only: tile geometry chosen for a shape.  which 0 = forward, 1 = dgrad; out = {nsub, ntile, n_ntiles, na, tps, bstages, mtiles, smem}
-extern "C" int kc_debug_tc_geometry(const kc_desc* d, int which, long long* out) {
+// Tile geometry the kernels choose for a shape (introspection for integrators and the CPU tests; no GPU needed).
+// which 0 = forward, 1 = dgrad; out = {nsub, ntile, n_ntiles, na, tps, bstages, mtiles, smem bytes}
+extern "C" int kc_tc_geometry(const kc_desc* d, int which, long long* out) {
+  int rc = kc_validate_desc(d);
+  if (rc != KC_OK) return rc;
+  if (!out) KC_FAIL(KC_ERR_INVALID, "kc_tc_geometry: null pointer");
   TcGeom g;
-  int rc = which == 0 ? tc_forward_geometry(d, &g) : tc_dgrad_geometry(d, &g);
+  rc = which == 0 ? tc_forward_geometry(d, &g) : tc_dgrad_geometry(d, &g);
   if (rc != KC_OK) return rc;
   out[0] = g.nsub; out[1] = g.ntile; out[2] = g.n_ntiles; out[3] = g.na; out[4] = g.tps; out[5] = g.bstages; out[6] = g.mtiles;
   out[7] = (long long)g.smem_bytes;
   return KC_OK;
 }
 
-extern "C" int kc_debug_flag(int v) {
-  KC_CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_flag, &v, sizeof(v)));
-  return KC_OK;
-}
-
+#ifdef KANCONV_DEBUG
+// Debug build only (not part of include/kanconv.h): enable / disable the timeline trace of the kernels in this file.
 extern "C" int kc_debug_trace(void* device_buffer) {
   long long* p = (long long*)device_buffer;
   KC_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
   return KC_OK;
 }
+#endif
 
 extern "C" int kc_tc_selftest(int mode, float* max_abs_err, void* stream) {
   if (!max_abs_err) KC_FAIL(KC_ERR_INVALID, "kc_tc_selftest: null pointer");

@@ -1,8 +1,69 @@
 // kc_tc_basis.cuh - basis evaluation shared by the tensor-core kernels (forward producers, dgrad epilogues, phi pre-pass).
 #pragma once
 #include "kc_common.cuh"
+#include "kc_umma.cuh"
 
 namespace kc {
+
+// ---- optional timeline trace: compiled in only with -DKANCONV_DEBUG (python -m kanconv_b200.build with KANCONV_DEBUG=1).
+// kc_debug_trace*() point the per-TU device pointer at a buffer of 4 x 1024 clock stamps; one CTA records one stamp per
+// pipeline event of representative threads.  In the product build stamp() is an empty inline function.
+#ifdef KANCONV_DEBUG
+#define KC_TRACE_DECL(sym) __device__ long long* sym = nullptr;
+struct Tracer {
+  long long* p; int n;
+  __device__ Tracer(long long* t, int role, bool on) {
+    p = (on && t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? t + role * 1024 : nullptr; n = 0;
+  }
+  __device__ __forceinline__ void stamp() { if (p != nullptr && n < 1024) p[n++] = clock64(); }
+};
+#define KC_TRACER(name, sym, role, on) Tracer name(sym, role, on)
+#else
+#define KC_TRACE_DECL(sym)
+struct Tracer {
+  __device__ __forceinline__ void stamp() {}
+};
+#define KC_TRACER(name, sym, role, on) Tracer name
+#endif
+
+// ---- uniform cubic B-spline, closed form ---------------------------------------------------------
+// The 4 non-zero weights land at j = i0-3 .. i0.  Branch-free: the 4 weights are packed into 64 bits and moved to their
+// slots with clamped PTX shifts (shift amounts >= 64, including "negative" ones, yield 0), so independent evaluations
+// can be interleaved by the compiler.
+__device__ __forceinline__ unsigned long long shl64(unsigned long long v, int s) {
+  unsigned long long r;
+  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
+  return r;
+}
+__device__ __forceinline__ unsigned long long shr64(unsigned long long v, int s) {
+  unsigned long long r;
+  asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
+  return r;
+}
+// true for NaN and +-Inf: the reference's Cox-de Boor recursion turns both into NaN on EVERY basis function
+// ((x - t_i) / d * B with B = 0 gives 0 * Inf; kan_layers.py:212-233)
+__device__ __forceinline__ bool tc_nonfinite(float x) { return !(fabsf(x) <= 3.402823466e38f); }
+
+// 8 basis values of one input as packed bf16.  valid = false (padding position / channel beyond cin): all-zero row.
+__device__ __forceinline__ uint4 cubic8(float x, float t0, float inv_h, int nintervals, bool valid) {
+  const float u = (x - t0) * inv_h;
+  const bool ok = valid && (u >= 0.0f) && (u < (float)nintervals);    // outside the knot span: all-zero row
+  const float fi = floorf(u);
+  const float f = u - fi;
+  const int i0 = min(max((int)fi, 0), 15);
+  const float s6 = 1.0f / 6.0f;
+  const float w0 = fmaf(fmaf(fmaf(-s6, f, 0.5f), f, -0.5f), f, s6);
+  const float w1 = fmaf(fmaf(0.5f, f, -1.0f) * f, f, 4.0f * s6);
+  const float w2 = fmaf(fmaf(fmaf(-0.5f, f, 0.5f), f, 0.5f), f, s6);
+  const float w3 = f * f * f * s6;
+  unsigned long long v = (unsigned long long)pack_bf16(w0, w1) | ((unsigned long long)pack_bf16(w2, w3) << 32);
+  v = ok ? v : 0ull;
+  const int sh = 16 * (i0 - 3);
+  unsigned long long lo = shl64(v, sh) | shr64(v, -sh);
+  unsigned long long hi = shr64(v, 64 - sh) | shl64(v, sh - 64);
+  if (valid && tc_nonfinite(x)) lo = hi = 0x7fc07fc07fc07fc0ull;      // NaN / Inf input: NaN on all eight (see above)
+  return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+}
 
 // Basis value (and optionally derivative) for the tensor-core path: same formulas as kc_eval_basis, evaluated with fast
 // intrinsics (ex2-based exp / tanh / sigmoid, Chebyshev polynomials by recurrence instead of cos(j acos c)); the results
@@ -33,7 +94,8 @@ __device__ inline void tc_eval_basis(const KcBasisCtx& B, float x, float* phi, f
       T0 = T1; T1 = T2; U0 = U1; U1 = U2;
     }
   } else if (B.kind == KC_BASIS_GRAM) {
-    const float t = tc_tanh(x), dt = 1.0f - t * t;
+    const bool pre = kc_gram_presquashed(B);
+    const float t = pre ? x : tc_tanh(x), dt = pre ? 1.0f : 1.0f - t * t;
     float p0 = 1.0f, p1 = t, d0 = 0.0f, d1 = 1.0f;
     for (int i = 0; i < nb; ++i) {
       const float sg = tc_sigmoid(p0);

@@ -64,46 +64,8 @@ struct WgArgs {
 
 __host__ __device__ inline int round_up_w(int a, int b) { return (a + b - 1) / b * b; }
 
-// optional timeline trace (debug), enabled by kc_debug_trace_wgrad(buffer of 4 x 1024 int64)
-__device__ long long* g_trace_w = nullptr;
-struct TracerW {
-  long long* p; int n;
-  __device__ TracerW(int role, bool on) {
-    long long* t = g_trace_w;
-    p = (on && t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? t + role * 1024 : nullptr; n = 0;
-  }
-  __device__ __forceinline__ void stamp() { if (p != nullptr && n < 1024) p[n++] = clock64(); }
-};
+KC_TRACE_DECL(g_trace_w)
 
-__device__ __forceinline__ unsigned long long shl64w(unsigned long long v, int s) {
-  unsigned long long r;
-  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
-  return r;
-}
-__device__ __forceinline__ unsigned long long shr64w(unsigned long long v, int s) {
-  unsigned long long r;
-  asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(s));
-  return r;
-}
-// uniform cubic B-spline, closed form, branch-free (same as the forward kernel's producer)
-__device__ __forceinline__ uint4 cubic8w(float x, float t0, float inv_h, int nintervals, bool valid) {
-  const float u = (x - t0) * inv_h;
-  const bool ok = valid && (u >= 0.0f) && (u < (float)nintervals);
-  const float fi = floorf(u);
-  const float f = u - fi;
-  const int i0 = min(max((int)fi, 0), 15);
-  const float s6 = 1.0f / 6.0f;
-  const float w0 = fmaf(fmaf(fmaf(-s6, f, 0.5f), f, -0.5f), f, s6);
-  const float w1 = fmaf(fmaf(0.5f, f, -1.0f) * f, f, 4.0f * s6);
-  const float w2 = fmaf(fmaf(fmaf(-0.5f, f, 0.5f), f, 0.5f), f, s6);
-  const float w3 = f * f * f * s6;
-  unsigned long long v = (unsigned long long)pack_bf16(w0, w1) | ((unsigned long long)pack_bf16(w2, w3) << 32);
-  v = ok ? v : 0ull;
-  const int sh = 16 * (i0 - 3);
-  const unsigned long long lo = shl64w(v, sh) | shr64w(v, -sh);
-  const unsigned long long hi = shr64w(v, 64 - sh) | shl64w(v, sh - 64);
-  return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
-}
 __device__ __noinline__ uint4 basis8w_generic(const KcBasisCtx& B, float x) {
   float phi[KC_MAX_BASIS];
 #pragma unroll
@@ -165,7 +127,7 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
     for (int pl = 0; pl < 16; ++pl) {
       const bool ok = inside && chunk * g.cps + pl < d.cin;
       uint4 v;
-      if (g.fast_cubic) v = cubic8w(xv[pl], g.t0, g.inv_h, Bs.nparams - 1, ok);
+      if (g.fast_cubic) v = cubic8(xv[pl], g.t0, g.inv_h, Bs.nparams - 1, ok);
       else v = ok ? basis8w_generic(Bs, xv[pl]) : make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(dst + pl * pstride) = v;
     }
@@ -212,7 +174,7 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     bdst[k] = (it < nBitems) ? (uint32_t)(g.a_bytes + bpl * g.bplane_bytes + brow[k] * 16) : 0xffffffffu;
     bplane[k] = bok ? a.dzf + ((long long)(ct * g.bplanes + bpl) * g.L) * 16 : nullptr;
   }
-  TracerW trp(0, tid == 0);
+  KC_TRACER(trp, g_trace_w, 0, tid == 0);
   const int depth = g.prefetch;
   int st = 0, st_done = 0;                        // ring slot being filled / being published (no divisions in the loop)
   uint32_t ph = 1;
@@ -326,7 +288,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     const int kw = d.kw, ntile = g.ntile;
     int st = 0;
     uint32_t ph = 0;
-    TracerW trm(1, lane == 0 && mw == 0);
+    KC_TRACER(trm, g_trace_w, 1, lane == 0 && mw == 0);
     for (int bi = 0; bi < nblocks; ++bi) {
       trm.stamp();
       mbar_wait(&full[st], ph);
@@ -471,20 +433,6 @@ __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_tile_kernel(const __gr
   }
 }
 
-bool knots_uniform_cubic_w(const kc_desc* d, float* t0, float* inv_h) {
-  if (d->basis != KC_BASIS_BSPLINE || d->order != 3 || d->nb != 8 || d->nparams != 12) return false;
-  double h = ((double)d->params[11] - (double)d->params[0]) / 11.0;
-  if (!(h > 0)) return false;
-  for (int i = 0; i < 12; ++i) {
-    double e = (double)d->params[0] + h * i - (double)d->params[i];
-    if (e < 0) e = -e;
-    if (e > 1e-5 * h) return false;
-  }
-  *t0 = d->params[0];
-  *inv_h = (float)(1.0 / h);
-  return true;
-}
-
 int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   if (d->dil_h != 1 || d->dil_w != 1) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs dilation 1");
   if (d->stride_h < 1 || d->stride_w < 1 || d->stride_h > 4 || d->stride_w > 4) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad needs stride <= 4");
@@ -536,7 +484,7 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->tmem_cols = 32;
   while (g->tmem_cols < d->kw * g->ntile) g->tmem_cols *= 2;
   g->nblk = (g->L + g->ks - 1) / g->ks;
-  long long want_split = (3LL * 148 + g->units - 1) / g->units;
+  long long want_split = (3LL * kc_sm_count() + g->units - 1) / g->units;
   const long long minblk = 1024 / g->ks;                            // at least 1024 positions per CTA
   long long max_split = g->nblk / minblk > 0 ? g->nblk / minblk : 1;
   long long ns = want_split < 1 ? 1 : want_split;
@@ -545,17 +493,19 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->nsplit = (int)((g->nblk + g->blk_per_split - 1) / g->blk_per_split);
   g->ws_bytes = (((size_t)g->nsplit * g->units * d->kw * 128 * g->ntile * sizeof(float)) + 255) / 256 * 256;
   g->phi_bytes = (size_t)g->nchunks * 16 * (size_t)g->L * 16;
-  g->fast_cubic = knots_uniform_cubic_w(d, &g->t0, &g->inv_h) ? 1 : 0;
+  g->fast_cubic = kc_knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
   return KC_OK;
 }
 
 }  // namespace
 
-extern "C" int kc_debug_trace_wgrad(void* device_buffer) {
+#ifdef KANCONV_DEBUG
+extern "C" int kc_debug_trace_wgrad(void* device_buffer) {       // debug build only, not part of include/kanconv.h
   long long* p = (long long*)device_buffer;
   KC_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_w, &p, sizeof(p)));
   return KC_OK;
 }
+#endif
 
 // which: 0 = split-K workspace + transient basis buffer, 1 = saved basis rows (phi), 2 = split-K workspace only
 size_t kc_tc_wgrad_ws_bytes(const kc_desc* d, int which) {
@@ -625,11 +575,11 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   KC_LAUNCH_CHECK("kc_wgrad_tc_kernel");
   long long total = (long long)g.units * d->kw * 128 * g.ntile;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > kc_sm_count() * 16) blocks = kc_sm_count() * 16;
   // the tile kernel needs enough (cout tile, chunk) pairs to fill the machine; few-channel layers (many splits, few
   // units) keep the element-parallel kernel
   const long long tile_blocks = (long long)((g.ntile + 31) / 32) * 4 * g.n_ct * g.nchunks;
-  if (d->kh * d->kw <= kRedT && (long long)g.n_ct * g.nchunks <= 65535 && tile_blocks >= 2 * 148) {
+  if (d->kh * d->kw <= kRedT && (long long)g.n_ct * g.nchunks <= 65535 && tile_blocks >= 2 * kc_sm_count()) {
     dim3 rgrid((unsigned)(((g.ntile + 31) / 32) * 4), (unsigned)(g.n_ct * g.nchunks));
     kc_wgrad_tc_reduce_tile_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
   } else {

@@ -1,20 +1,32 @@
 """torch.autograd.Function wrappers around the C ABI of libkanconv.so.
 
-Two differentiable ops make up every KAN convolution layer of the reference:
+Differentiable ops that make up the KAN layers of the reference:
 
-  * ``kan_conv``  - z = conv(act(x_base), W_base) + conv(basis(x_basis), W_basis)   (kan_layers.py:199-241 and siblings)
-  * ``norm_act``  - y = out_act(norm(z))                                           (kan_layers.py:242-243)
+  * ``kan_conv``       - z = conv(act(x_base), W_base) + conv(basis(x_basis), W_basis)   (kan_layers.py:199-241 and siblings)
+  * ``norm_act``       - y = out_act(norm(z)), Instance / Batch norm over [n, c, hw]     (kan_layers.py:242-243)
+  * ``layer_norm_act`` - y = out_act(LayerNorm(z)) over the features of a row            (kan_layers.py:110-112, KANLayer)
+  * ``max_pool2d``     - nn.MaxPool2d between convolution stages                         (models/kan_vgg.py:121)
 
-Both call hand-written CUDA through ctypes (raw device pointers + the current CUDA stream); forward saves only the
-layer INPUT (the basis expansion is recomputed in the backward kernels), so the 8x-expanded tensor and the ~30 autograd
-intermediates of the reference never exist.  CPU tensors are rejected: there is no fallback path.
+All of them call hand-written CUDA through ctypes (raw device pointers + the CUDA stream of the tensors' device).  CPU tensors
+are rejected: there is no fallback path.
+
+What is kept between forward and backward of ``kan_conv``: the layer input ``x`` (fp32, through save_for_backward) and - on the
+tensor-core path, unless ``KANCONV_SAVE_PHI=0`` - ``phi``: the bf16 basis / base-activation rows the forward kernel evaluates
+anyway, 18 B per input element (11 GB over the 13 layers of KAN-VGG16 at batch 64; the reference keeps the fp32 expansion,
+36 B per element, plus ~30 autograd intermediates).  ``phi`` lives on ``ctx`` (not in save_for_backward, so saved-tensor hooks
+do not see it) and is released by the first backward; a second backward through a retained graph re-evaluates the rows in a
+pre-pass and gives the same gradients.  With ``KANCONV_SAVE_PHI=0`` the pre-pass always runs (+6 ms per VGG16 step).
+
+Packed bf16 weight images are cached per parameter and re-packed only when the parameter's version counter changes (once per
+optimizer step in training, never in inference).
 """
 from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -117,8 +129,8 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -126,6 +138,13 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise RuntimeError(f"{what}: kanconv_b200 runs on CUDA tensors only (no CPU fallback); got device {t.device}")
     if t.dtype != torch.float32:
         raise TypeError(f"{what}: expected float32, got {t.dtype}")
+
+
+def _same_device(what: str, dev: torch.device, *tensors) -> None:
+    """The library launches on the CURRENT device with raw pointers: every operand must live on the device the op runs on."""
+    for t in tensors:
+        if t is not None and t.device != dev:
+            raise RuntimeError(f"{what}: all tensors must be on {dev}, got one on {t.device}")
 
 
 def _make_desc(spec: ConvSpec, n, cin_g, h, w, cout_g, x_bs, z_bs) -> L.KcDesc:
@@ -156,6 +175,54 @@ def _use_tc(lib, desc, precision: str) -> bool:
     return ok
 
 
+# ---- packed-weight cache -------------------------------------------------------------------------------------------------
+# key: (id of the root tensor of w_base, id of the root of w_basis, which image, descriptor bytes) -> (versions, packed).
+# "Root" = the Parameter a view was taken from (1-D layers and KANLayer pass views); entries die with their parameter.
+_PACKS: Dict[tuple, tuple] = {}
+_PACK_STATS = {"hits": 0, "misses": 0}
+
+
+def _root(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return t._base if t._base is not None else t
+
+
+def _pack_key(roots, which: int, d) -> tuple:
+    return (tuple(0 if r is None else id(r) for r in roots), which, bytes(d))
+
+
+def _drop_packs(rid: int) -> None:
+    for k in [k for k in _PACKS if rid in k[0]]:
+        _PACKS.pop(k, None)
+
+
+def _packed_weights(lib, d, which: int, wb, ws, roots, versions, stream, kernel_name: str):
+    """bf16 weight image of the forward (which=0) or dgrad (which=1) kernel; re-packed only when a version counter moved."""
+    key = _pack_key(roots, which, d)
+    hit = _PACKS.get(key)
+    if hit is not None and hit[0] == versions and hit[1].device == ws.device:
+        _PACK_STATS["hits"] += 1
+        return hit[1]
+    _PACK_STATS["misses"] += 1
+    nbytes = lib.kc_tc_bytes(ctypes.byref(d), which)
+    packed = hit[1] if (hit is not None and hit[1].numel() == nbytes and hit[1].device == ws.device) else \
+        torch.empty(nbytes, device=ws.device, dtype=torch.uint8)
+    L.check(_timed(kernel_name, 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
+        ctypes.byref(d), _ptr(wb), _ptr(ws), _ptr(packed) if which == 0 else None, _ptr(packed) if which == 1 else None,
+        stream)), "kc_tc_pack_weights")
+    if hit is None:
+        for r in roots:
+            if r is not None:
+                weakref.finalize(r, _drop_packs, id(r))
+    _PACKS[key] = (versions, packed)
+    return packed
+
+
+def pack_cache_stats() -> dict:
+    return dict(_PACK_STATS, entries=len(_PACKS))
+
+
 class _KanConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: ConvSpec, precision: str, x_base, x_basis, beta, *weights):
@@ -165,6 +232,8 @@ class _KanConvFn(torch.autograd.Function):
         xs = xb if alias else x_basis.contiguous()
         _require_cuda(xb, "kan_conv")
         _require_cuda(xs, "kan_conv")
+        dev = xb.device
+        _same_device("kan_conv", dev, xs, beta, *weights)
         G = spec.groups
         n, c_total, h, w = xb.shape
         cg = c_total // G
@@ -172,35 +241,37 @@ class _KanConvFn(torch.autograd.Function):
         w_basis = list(weights[G:2 * G]) if spec.has_base else list(weights[:G])
         og = w_basis[0].shape[0]
         ho, wo = spec.out_hw(h, w)
-        z = torch.empty((n, og * G, ho, wo), device=xb.device, dtype=torch.float32)
-        stream = _stream()
         used_tc = []
         # basis rows saved for the weight gradient (the reference keeps the expanded basis alive for autograd, too)
         want_phi = _SAVE_PHI and _TC_BACKWARD and any(ctx.needs_input_grad[5:])
         phis = []
-        for g in range(G):
-            d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
-            xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
-            wbg = None if w_base[g] is None else w_base[g].contiguous()
-            wsg = w_basis[g].contiguous()
-            tc = _use_tc(lib, d, precision)
-            used_tc.append(tc)
-            if tc:
-                nbytes = lib.kc_tc_bytes(ctypes.byref(d), 0)
-                packed = torch.empty(nbytes, device=xb.device, dtype=torch.uint8)
-                L.check(_timed("kc_pack_fwd_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
-                    ctypes.byref(d), _ptr(wbg), _ptr(wsg), _ptr(packed), None, stream)), "kc_tc_pack_weights")
-                phi = None
-                if (want_phi or lib.kc_tc_fwd_needs_phi(ctypes.byref(d))) and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
-                    phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=xb.device, dtype=torch.uint8)
-                phis.append(phi)
-                L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
-                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), _ptr(phi), stream)), "kc_conv_fwd_tc")
-            else:
-                phis.append(None)
-                L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
-                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream)), "kc_conv_fwd_f32")
-        ctx.spec, ctx.alias, ctx.precision, ctx.used_tc, ctx.phis = spec, alias, precision, used_tc, phis
+        roots = [(_root(w_base[g]), _root(w_basis[g])) for g in range(G)]
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            z = torch.empty((n, og * G, ho, wo), device=dev, dtype=torch.float32)
+            for g in range(G):
+                d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
+                xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
+                wbg = None if w_base[g] is None else w_base[g].contiguous()
+                wsg = w_basis[g].contiguous()
+                tc = _use_tc(lib, d, precision)
+                used_tc.append(tc)
+                if tc:
+                    versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
+                    packed = _packed_weights(lib, d, 0, wbg, wsg, roots[g], versions, stream, "kc_pack_fwd_kernel")
+                    phi = None
+                    if (want_phi or lib.kc_tc_fwd_needs_phi(ctypes.byref(d))) and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
+                        phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=dev, dtype=torch.uint8)
+                    phis.append(phi)
+                    L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
+                        ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), _ptr(phi), stream)),
+                        "kc_conv_fwd_tc")
+                else:
+                    phis.append(None)
+                    L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
+                        ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream)),
+                        "kc_conv_fwd_f32")
+        ctx.spec, ctx.alias, ctx.precision, ctx.used_tc, ctx.phis, ctx.roots = spec, alias, precision, used_tc, phis, roots
         ctx.save_for_backward(xb, xs if not alias else None, beta, *weights)
         return z
 
@@ -214,6 +285,8 @@ class _KanConvFn(torch.autograd.Function):
         alias = ctx.alias
         if alias:
             xs = xb
+        dev = xb.device
+        _same_device("kan_conv backward", dev, dz)
         G = spec.groups
         n, c_total, h, w = xb.shape
         cg = c_total // G
@@ -222,62 +295,68 @@ class _KanConvFn(torch.autograd.Function):
         og = w_basis[0].shape[0]
         ho, wo = spec.out_hw(h, w)
         dz = dz.contiguous()
-        stream = _stream()
         # inputs of forward: (spec, precision, x_base, x_basis, beta, *weights)
         need_dxb, need_dxs, need_dbeta = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         need_w = list(ctx.needs_input_grad[5:])
-        dbeta = torch.zeros_like(beta) if (spec.basis == L.BASIS_GRAM and beta is not None) else None
-        run_dgrad = need_dxb or need_dxs or (dbeta is not None and need_dbeta)
-        dx_base = dx_basis = None
-        if run_dgrad:
-            dx_base = torch.empty_like(xb)
-            dx_basis = dx_base if alias else torch.empty_like(xs)
+        gram = spec.basis == L.BASIS_GRAM and beta is not None
+        run_dgrad = need_dxb or need_dxs or (gram and need_dbeta)
+        dx_base = dx_basis = dbeta = None
         dws: List[Optional[torch.Tensor]] = [None] * len(weights)
-        for g in range(G):
-            d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
-            sl = slice(g * cg, (g + 1) * cg)
-            xbg, xsg, dzg = xb[:, sl], xs[:, sl], dz[:, g * og:(g + 1) * og]
-            wbg = None if w_base[g] is None else w_base[g].contiguous()
-            wsg = w_basis[g].contiguous()
-            tc_bwd = ctx.used_tc[g] and _TC_BACKWARD and lib.kc_tc_bytes(ctypes.byref(d), 1) > 0
-            dzf = None
-            if tc_bwd:
-                dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=xb.device, dtype=torch.uint8)
-                L.check(_timed("kc_dz_flat_kernel", 0.0, 6.0 * dzg.numel(), lambda: lib.kc_tc_dz_flat(
-                    ctypes.byref(d), _ptr(dzg), _ptr(dzf), stream)), "kc_tc_dz_flat")
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
             if run_dgrad:
+                dx_base = torch.empty_like(xb)
+                dx_basis = dx_base if alias else torch.empty_like(xs)
+            for g in range(G):
+                d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
+                sl = slice(g * cg, (g + 1) * cg)
+                xbg, xsg, dzg = xb[:, sl], xs[:, sl], dz[:, g * og:(g + 1) * og]
+                wbg = None if w_base[g] is None else w_base[g].contiguous()
+                wsg = w_basis[g].contiguous()
+                tc_bwd = ctx.used_tc[g] and _TC_BACKWARD and lib.kc_tc_bytes(ctypes.byref(d), 1) > 0
+                dzf = None
                 if tc_bwd:
-                    nbytes = lib.kc_tc_bytes(ctypes.byref(d), 1)
-                    packed_d = torch.empty(nbytes, device=xb.device, dtype=torch.uint8)
-                    L.check(_timed("kc_pack_dgrad_kernel", 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
-                        ctypes.byref(d), _ptr(wbg), _ptr(wsg), None, _ptr(packed_d), stream)), "kc_tc_pack_weights")
-                    L.check(_timed("kc_tc_kernel<dgrad>", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_tc(
-                        ctypes.byref(d), None, _ptr(xbg), _ptr(xsg), _ptr(packed_d), _ptr(beta), _ptr(dx_base[:, sl]),
-                        _ptr(dx_basis[:, sl]), _ptr(dbeta), _ptr(dzf), stream)), "kc_conv_dgrad_tc")
-                else:
-                    L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
-                        ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
-                        _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbeta), stream)), "kc_conv_dgrad_f32")
-            wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
-            if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
-                dwb = torch.empty_like(wbg) if wbg is not None else None
-                dwsg = torch.empty_like(wsg)
-                if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
-                    phi = ctx.phis[g]
-                    ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=xb.device, dtype=torch.uint8)
-                    L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
-                        ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(phi), _ptr(dwb), _ptr(dwsg), _ptr(ws),
-                        stream)), "kc_conv_wgrad_tc")
-                    ctx.phis[g] = None
-                else:
-                    nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
-                    ws = torch.empty(max(nbytes, 16), device=xb.device, dtype=torch.uint8)
-                    L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
-                        ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
-                        "kc_conv_wgrad_f32")
-                if wi_base is not None:
-                    dws[wi_base] = dwb
-                dws[wi_basis] = dwsg
+                    dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
+                    L.check(_timed("kc_dz_flat_kernel", 0.0, 6.0 * dzg.numel(), lambda: lib.kc_tc_dz_flat(
+                        ctypes.byref(d), _ptr(dzg), _ptr(dzf), stream)), "kc_tc_dz_flat")
+                if run_dgrad:
+                    # GRAM: d/d beta_weights of this group (deterministic: per-block partial rows + fixed-order reduction)
+                    dbg = None
+                    if gram and need_dbeta:
+                        dbg = torch.empty(lib.kc_dbeta_floats(ctypes.byref(d), 1 if tc_bwd else 0), device=dev, dtype=torch.float32)
+                    if tc_bwd:
+                        versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
+                        packed_d = _packed_weights(lib, d, 1, wbg, wsg, ctx.roots[g], versions, stream, "kc_pack_dgrad_kernel")
+                        L.check(_timed("kc_tc_kernel<dgrad>", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_tc(
+                            ctypes.byref(d), None, _ptr(xbg), _ptr(xsg), _ptr(packed_d), _ptr(beta), _ptr(dx_base[:, sl]),
+                            _ptr(dx_basis[:, sl]), _ptr(dbg), _ptr(dzf), stream)), "kc_conv_dgrad_tc")
+                    else:
+                        L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
+                            ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
+                            _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbg), stream)), "kc_conv_dgrad_f32")
+                    if dbg is not None:
+                        part = dbg[:beta.numel()]
+                        dbeta = part.clone() if dbeta is None else dbeta + part       # groups are added in order
+                wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
+                if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
+                    dwb = torch.empty_like(wbg) if wbg is not None else None
+                    dwsg = torch.empty_like(wsg)
+                    if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
+                        phi = ctx.phis[g]
+                        ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=dev, dtype=torch.uint8)
+                        L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
+                            ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(phi), _ptr(dwb), _ptr(dwsg), _ptr(ws),
+                            stream)), "kc_conv_wgrad_tc")
+                        ctx.phis[g] = None
+                    else:
+                        nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
+                        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+                        L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
+                            ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
+                            "kc_conv_wgrad_f32")
+                    if wi_base is not None:
+                        dws[wi_base] = dwb
+                    dws[wi_basis] = dwsg
         return (None, None, dx_base if need_dxb else None, (dx_basis if (need_dxs and not alias) else None),
                 dbeta if need_dbeta else None, *dws)
 
@@ -295,6 +374,8 @@ class _NormActFn(torch.autograd.Function):
         lib = L.load()
         z = z.contiguous()
         _require_cuda(z, "norm_act")
+        dev = z.device
+        _same_device("norm_act", dev, given_mean, given_rstd, *params)
         G = spec.groups
         n, c_total, h, w = z.shape
         cg, hw = c_total // G, h * w
@@ -303,25 +384,29 @@ class _NormActFn(torch.autograd.Function):
         bet = [params[2 * g + 1] for g in range(G)] if spec.affine else [None] * G
         off = 2 * G if spec.affine else 0
         alp = [params[off + g] for g in range(G)] if spec.out_act == L.OUT_PRELU else [None] * G
-        y = torch.empty_like(z)
+        given = spec.norm == L.NORM_BATCH and not spec.use_batch_stats
+        if given and (given_mean is None or given_rstd is None):
+            raise ValueError("norm_act: BatchNorm with use_batch_stats=False needs given_mean / given_rstd")
         nstat = {L.NORM_NONE: 1, L.NORM_INSTANCE: n * cg, L.NORM_BATCH: cg}[spec.norm]
-        mean = torch.empty((G, nstat), device=z.device, dtype=torch.float32)
-        rstd = torch.empty((G, nstat), device=z.device, dtype=torch.float32)
-        stream = _stream()
-        for g in range(G):
-            d = L.KcNormDesc()
-            d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
-            d.batch_stride, d.eps = c_total * hw, spec.eps
-            scratch = None
-            if spec.norm == L.NORM_BATCH:
-                if spec.use_batch_stats:
-                    scratch = torch.empty(2 * n * cg, device=z.device, dtype=torch.float32)
-                else:
-                    mean[g].copy_(given_mean[g * cg:(g + 1) * cg])
-                    rstd[g].copy_(given_rstd[g * cg:(g + 1) * cg])
-            L.check(_timed("kc_instnorm_fwd_kernel", 0.0, 8.0 * n * cg * hw, lambda: lib.kc_norm_act_fwd(
-                ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
-                _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream)), "kc_norm_act_fwd")
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            y = torch.empty_like(z)
+            if given:       # eval-mode BatchNorm: the running statistics are inputs of the kernel (scratch = NULL)
+                mean = given_mean.detach().to(torch.float32).reshape(G, cg).contiguous()
+                rstd = given_rstd.detach().to(torch.float32).reshape(G, cg).contiguous()
+            else:
+                mean = torch.empty((G, nstat), device=dev, dtype=torch.float32)
+                rstd = torch.empty((G, nstat), device=dev, dtype=torch.float32)
+            for g in range(G):
+                d = L.KcNormDesc()
+                d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
+                d.batch_stride, d.eps = c_total * hw, spec.eps
+                scratch = None
+                if spec.norm == L.NORM_BATCH and not given:
+                    scratch = torch.empty(2 * n * cg, device=dev, dtype=torch.float32)
+                L.check(_timed("kc_instnorm_fwd_kernel", 0.0, 8.0 * n * cg * hw, lambda: lib.kc_norm_act_fwd(
+                    ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
+                    _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream)), "kc_norm_act_fwd")
         ctx.spec = spec
         ctx.save_for_backward(z, mean, rstd, *params)
         ctx.mark_non_differentiable(mean, rstd)
@@ -333,8 +418,9 @@ class _NormActFn(torch.autograd.Function):
         spec: NormSpec = ctx.spec
         z, mean, rstd = ctx.saved_tensors[:3]
         params = ctx.saved_tensors[3:]
-        if spec.norm == L.NORM_BATCH and not spec.use_batch_stats:
-            raise NotImplementedError("norm_act: backward through BatchNorm in eval mode is not implemented")
+        dev = z.device
+        _same_device("norm_act backward", dev, dy)
+        given = int(spec.norm == L.NORM_BATCH and not spec.use_batch_stats)
         G = spec.groups
         n, c_total, h, w = z.shape
         cg, hw = c_total // G, h * w
@@ -343,25 +429,27 @@ class _NormActFn(torch.autograd.Function):
         off = 2 * G if spec.affine else 0
         alp = [params[off + g] for g in range(G)] if spec.out_act == L.OUT_PRELU else [None] * G
         dy = dy.contiguous()
-        dz = torch.empty_like(z)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
-        stream = _stream()
-        for g in range(G):
-            d = L.KcNormDesc()
-            d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
-            d.batch_stride, d.eps = c_total * hw, spec.eps
-            partials = torch.empty(3 * n * cg + 2 * cg, device=z.device, dtype=torch.float32)
-            dgam = torch.empty_like(gam[g]) if spec.affine else None
-            dbet = torch.empty_like(bet[g]) if spec.affine else None
-            dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
-            sl = slice(g * cg, (g + 1) * cg)
-            L.check(_timed("kc_norm_bwd_kernel", 0.0, 12.0 * n * cg * hw, lambda: lib.kc_norm_act_bwd(
-                ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]), _ptr(bet[g]),
-                _ptr(alp[g]), _ptr(dz[:, sl]), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials), stream)), "kc_norm_act_bwd")
-            if spec.affine:
-                grads[2 * g], grads[2 * g + 1] = dgam, dbet
-            if dalp is not None:
-                grads[off + g] = dalp
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            dz = torch.empty_like(z)
+            for g in range(G):
+                d = L.KcNormDesc()
+                d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
+                d.batch_stride, d.eps = c_total * hw, spec.eps
+                partials = torch.empty(3 * n * cg + 2 * cg, device=dev, dtype=torch.float32)
+                dgam = torch.empty_like(gam[g]) if spec.affine else None
+                dbet = torch.empty_like(bet[g]) if spec.affine else None
+                dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
+                sl = slice(g * cg, (g + 1) * cg)
+                L.check(_timed("kc_norm_bwd_kernel", 0.0, 12.0 * n * cg * hw, lambda: lib.kc_norm_act_bwd(
+                    ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]), _ptr(bet[g]),
+                    _ptr(alp[g]), _ptr(dz[:, sl]), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials), given, stream)),
+                    "kc_norm_act_bwd")
+                if spec.affine:
+                    grads[2 * g], grads[2 * g + 1] = dgam, dbet
+                if dalp is not None:
+                    grads[off + g] = dalp
         return (None, dz, None, None, *grads)
 
 
@@ -378,20 +466,75 @@ def norm_act(spec: NormSpec, z: torch.Tensor, gammas: Sequence[torch.Tensor] = (
     return _NormActFn.apply(spec, z, given_mean, given_rstd, *params)
 
 
+class _LayerNormActFn(torch.autograd.Function):
+    """y = out_act(LayerNorm(z)) over the last axis - the tail of the reference's KANLayer (kan_layers.py:110-112)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, alpha, eps: float, out_act: int):
+        lib = L.load()
+        _require_cuda(z, "layer_norm_act")
+        dev = z.device
+        _same_device("layer_norm_act", dev, gamma, beta, alpha)
+        feat = z.shape[-1]
+        z2 = z.contiguous().reshape(-1, feat)
+        d = L.KcRowNormDesc()
+        d.rows, d.features, d.out_act, d.affine, d.eps = z2.shape[0], feat, out_act, int(gamma is not None), eps
+        with torch.cuda.device(dev):
+            y = torch.empty_like(z2)
+            mean = torch.empty(z2.shape[0], device=dev, dtype=torch.float32)
+            rstd = torch.empty_like(mean)
+            L.check(lib.kc_layernorm_act_fwd(ctypes.byref(d), _ptr(z2), _ptr(gamma), _ptr(beta), _ptr(alpha), _ptr(y), _ptr(mean),
+                                             _ptr(rstd), _stream(dev)), "kc_layernorm_act_fwd")
+        ctx.desc_fields = (z2.shape[0], feat, out_act, int(gamma is not None), eps)
+        ctx.shape = z.shape
+        ctx.save_for_backward(z2, mean, rstd, gamma, beta, alpha)
+        return y.reshape(z.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        z2, mean, rstd, gamma, beta, alpha = ctx.saved_tensors
+        dev = z2.device
+        _same_device("layer_norm_act backward", dev, dy)
+        d = L.KcRowNormDesc()
+        d.rows, d.features, d.out_act, d.affine, d.eps = ctx.desc_fields
+        dy2 = dy.contiguous().reshape(z2.shape)
+        with torch.cuda.device(dev):
+            dz = torch.empty_like(z2)
+            dgam = torch.empty_like(gamma) if gamma is not None else None
+            dbet = torch.empty_like(beta) if beta is not None else None
+            dalp = torch.empty_like(alpha) if alpha is not None else None
+            partials = torch.empty(z2.shape[0], device=dev, dtype=torch.float32)
+            L.check(lib.kc_layernorm_act_bwd(ctypes.byref(d), _ptr(dy2), _ptr(z2), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
+                                             _ptr(alpha), _ptr(dz), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials),
+                                             _stream(dev)), "kc_layernorm_act_bwd")
+        return dz.reshape(ctx.shape), dgam, dbet, dalp, None, None
+
+
+def layer_norm_act(z: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                   alpha: Optional[torch.Tensor], eps: float = 1e-5, out_act: Optional[int] = None) -> torch.Tensor:
+    """out_act(LayerNorm_{last axis}(z)) with per-feature gamma / beta; out_act defaults to PReLU when alpha is given."""
+    if out_act is None:
+        out_act = L.OUT_PRELU if alpha is not None else L.OUT_NONE
+    return _LayerNormActFn.apply(z, gamma, beta, alpha, float(eps), int(out_act))
+
+
 class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k: int, s: int):
         lib = L.load()
         _require_cuda(x, "max_pool2d")
         x = x.contiguous()
+        dev = x.device
         n, c, h, w = x.shape
         if h < k or w < k:
             raise ValueError(f"max_pool2d: input {h}x{w} smaller than the window {k}")
         ho, wo = (h - k) // s + 1, (w - k) // s + 1
-        y = torch.empty((n, c, ho, wo), device=x.device, dtype=torch.float32)
-        idx = torch.empty((n, c, ho, wo), device=x.device, dtype=torch.uint8)
-        L.check(_timed("kc_maxpool_fwd_kernel", 0.0, 4.0 * x.numel() + 5.0 * y.numel(), lambda: lib.kc_maxpool2d_fwd(
-            _ptr(x), _ptr(y), _ptr(idx), n * c, h, w, k, s, ho, wo, _stream())), "kc_maxpool2d_fwd")
+        with torch.cuda.device(dev):
+            y = torch.empty((n, c, ho, wo), device=dev, dtype=torch.float32)
+            idx = torch.empty((n, c, ho, wo), device=dev, dtype=torch.uint8)
+            L.check(_timed("kc_maxpool_fwd_kernel", 0.0, 4.0 * x.numel() + 5.0 * y.numel(), lambda: lib.kc_maxpool2d_fwd(
+                _ptr(x), _ptr(y), _ptr(idx), n * c, h, w, k, s, ho, wo, _stream(dev))), "kc_maxpool2d_fwd")
         ctx.save_for_backward(idx)
         ctx.geom = (n, c, h, w, k, s, ho, wo)
         return y
@@ -401,10 +544,13 @@ class _MaxPoolFn(torch.autograd.Function):
         lib = L.load()
         (idx,) = ctx.saved_tensors
         n, c, h, w, k, s, ho, wo = ctx.geom
+        dev = idx.device
+        _same_device("max_pool2d backward", dev, dy)
         dy = dy.contiguous()
-        dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
-        L.check(_timed("kc_maxpool_bwd_kernel", 0.0, 4.0 * dx.numel() + 5.0 * dy.numel(), lambda: lib.kc_maxpool2d_bwd(
-            _ptr(dy), _ptr(idx), _ptr(dx), n * c, h, w, k, s, ho, wo, _stream())), "kc_maxpool2d_bwd")
+        with torch.cuda.device(dev):
+            dx = torch.empty((n, c, h, w), device=dev, dtype=torch.float32)
+            L.check(_timed("kc_maxpool_bwd_kernel", 0.0, 4.0 * dx.numel() + 5.0 * dy.numel(), lambda: lib.kc_maxpool2d_bwd(
+                _ptr(dy), _ptr(idx), _ptr(dx), n * c, h, w, k, s, ho, wo, _stream(dev))), "kc_maxpool2d_bwd")
         return dx, None, None
 
 

@@ -15,8 +15,9 @@ _CONV = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}
 _DROPOUT = {1: nn.Dropout1d, 2: nn.Dropout2d, 3: nn.Dropout3d}
 
 
-def pair(v, ndim: int) -> Tuple[int, int]:
-    """Conv hyper-parameter -> (h, w) pair; a 1-D layer is run as a 2-D layer of height 1."""
+def pair(v, ndim: int, fill: int = 1) -> Tuple[int, int]:
+    """Conv hyper-parameter -> (h, w) pair.  A 1-D layer is run as a 2-D layer of height 1: ``fill`` is the value of the
+    dummy height axis - 1 for kernel size / stride / dilation, 0 for padding."""
     if isinstance(v, (tuple, list)):
         v = tuple(int(i) for i in v)
         if len(v) == 1:
@@ -24,7 +25,7 @@ def pair(v, ndim: int) -> Tuple[int, int]:
     else:
         v = (int(v),) * ndim
     if ndim == 1:
-        return (1, v[0]) if len(v) == 1 else (1, v[-1])
+        return (fill, v[0]) if len(v) == 1 else (fill, v[-1])
     return (v[0], v[1])
 
 

@@ -31,7 +31,7 @@ class ChebyKANConvNDLayer(KANConvBase):
             nn.init.normal_(m.weight, mean=0.0, std=1 / (input_dim * (degree + 1) * kernel_size ** ndim))
             nn.init.kaiming_normal_(m.weight, mode='fan_in', nonlinearity='relu')
         self._spec = KF.ConvSpec(basis=L.BASIS_CHEBY, act=L.ACT_NONE, nb=degree + 1, order=degree, params=(),
-                                 kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim),
+                                 kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim, fill=0),
                                  dilation=pair(dilation, ndim), groups=groups)
 
     def forward(self, x):

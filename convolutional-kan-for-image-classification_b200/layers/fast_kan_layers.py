@@ -36,7 +36,7 @@ class FastKANConvNDLayer(KANConvBase):
         for m in self.spline_conv:
             nn.init.kaiming_uniform_(m.weight, nonlinearity='linear')
         self._act = act_kind(self.base_activation)
-        self._geom = dict(kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim),
+        self._geom = dict(kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim, fill=0),
                           dilation=pair(dilation, ndim), groups=groups)
 
     def forward(self, x):

@@ -43,15 +43,20 @@ class GRAMKANConvNDLayer(KANConvBase):
         nn.init.normal_(self.beta_weights, mean=0.0,
                         std=1.0 / ((kernel_size ** ndim) * input_dim * (degree + 1.0)))
         self._spec = KF.ConvSpec(basis=L.BASIS_GRAM, act=L.ACT_SILU, nb=degree + 1, order=degree, params=(),
-                                 kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim),
+                                 kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim, fill=0),
                                  dilation=pair(dilation, ndim), groups=groups)
+        self._spec_presquashed = KF.ConvSpec(**dict(self._spec.__dict__, params=(1.0,)))
 
     def forward(self, x):
-        if self.dropout is not None and self.training:
-            raise NotImplementedError("GRAM KAN convolution: dropout on tanh(x) (gram_kan_layers.py:178-179) is not "
-                                      "implemented in the fused kernel; use dropout=0")
         x4 = self._to4d(x)
-        z = KF.kan_conv(self._spec, x4, None, self.beta_weights, [self._w4d(m.weight) for m in self.base_conv],
+        x_basis, spec = None, self._spec
+        if self.dropout is not None and self.training:
+            # gram_kan_layers.py:176-179: Dropout acts on t = tanh(x), spline branch only.  The squashing and the mask are
+            # elementwise torch ops (autograd differentiates them); the kernels then take t as the basis input and skip
+            # their own tanh (ConvSpec.params = (1.0,) = "pre-squashed").
+            x_basis = self._to4d(self.dropout(torch.tanh(x)))
+            spec = self._spec_presquashed
+        z = KF.kan_conv(spec, x4, x_basis, self.beta_weights, [self._w4d(m.weight) for m in self.base_conv],
                         [self._w4d(self.poly_weights[g]) for g in range(self.groups)], self.precision)
         return self._from4d(self._norm_act(z, self.layer_norm, L.OUT_SILU))
 

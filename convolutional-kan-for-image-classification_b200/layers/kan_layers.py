@@ -48,7 +48,7 @@ class KANConvNDLayer(KANConvBase):
             nn.init.kaiming_uniform_(m.weight, nonlinearity='linear')
         self._spec = KF.ConvSpec(basis=L.BASIS_BSPLINE, act=act_kind(self.base_activation), nb=nb, order=spline_order,
                                  params=tuple(float(v) for v in self.grid.tolist()),
-                                 kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim),
+                                 kernel=pair(kernel_size, ndim), stride=pair(stride, ndim), padding=pair(padding, ndim, fill=0),
                                  dilation=pair(dilation, ndim), groups=groups)
 
     def forward(self, x):
@@ -92,9 +92,9 @@ class KANConv1DLayer(KANConvNDLayer):
 class KANLayer(nn.Module):
     """B-spline KAN fully-connected layer - drop-in for the reference's ``KANLayer`` (kan_layers.py:8-114).
 
-    SURVEY 8(f) rank 2 ("next"): the basis expansion + contraction runs through the same CUDA op as the convolution
-    (a 1x1 convolution over a 1x1 map, reusing ``spline_weight [out, in, nb]`` viewed as ``[out, in*nb, 1, 1]``);
-    the LayerNorm + PReLU tail of this <0.01 %-of-FLOPs head uses torch's own ops."""
+    SURVEY 8(f) rank 2: the basis expansion + contraction ``[B, in*nb] x [in*nb, out]`` (+ the base branch) runs through the
+    same CUDA op as the convolution (a 1x1 convolution over a 1x1 map, ``spline_weight [out, in, nb]`` viewed as
+    ``[out, in*nb, 1, 1]``), and the LayerNorm + PReLU tail (kan_layers.py:110-112) through ``kc_layernorm_act_fwd/bwd``."""
 
     def __init__(self, input_features, output_features, grid_size=5, spline_order=3, base_activation=nn.GELU,
                  grid_range=[-1, 1]):
@@ -123,4 +123,4 @@ class KANLayer(nn.Module):
         z = KF.kan_conv(self._spec, x4, None, None, [self.base_weight[:, :, None, None]],
                         [self.spline_weight.reshape(self.output_features, -1, 1, 1)], self.precision)
         z = z.reshape(*lead, self.output_features)
-        return self.prelu(self.layer_norm(z))
+        return KF.layer_norm_act(z, self.layer_norm.weight, self.layer_norm.bias, self.prelu.weight, self.layer_norm.eps)

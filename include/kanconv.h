@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KC_ABI_VERSION 1
+#define KC_ABI_VERSION 2
 #define KC_MAX_BASIS 16   /* max basis width nb  (G+K, D+1 or G)      */
 #define KC_MAX_PARAMS 40  /* knots / rbf grid etc. carried in kc_desc */
 
@@ -99,8 +99,12 @@ int kc_conv_fwd_f32(const kc_desc* d, const float* x_base, const float* x_basis,
                     const float* w_basis, const float* beta, float* z, void* stream);
 
 /* Input gradient.  dx_base/dx_basis receive the base-branch and basis-branch parts; if they are the same pointer
- * the sum is written once.  `dbeta` (GRAM only, [D+1], must be zeroed by the caller) accumulates d/d beta_weights.
+ * the sum is written once.  `dbeta` (GRAM only, may be NULL): a buffer of kc_dbeta_floats(d, tc) floats; on return its
+ * first D+1 floats hold d/d beta_weights of this call (gram_kan_layers.py:150-170).  The kernels write one partial row
+ * per thread block behind them and a fixed-order reduction adds the rows: the result is deterministic, nothing has to be
+ * zeroed, and there are no atomics.
  * Replaces autograd's backward of kan_layers.py:199-239 (the reference has no hand-written backward). */
+size_t kc_dbeta_floats(const kc_desc* d, int tc);      /* tc = 0: kc_conv_dgrad_f32, 1: kc_conv_dgrad_tc; 0 if not GRAM */
 int kc_conv_dgrad_f32(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                       const float* w_base, const float* w_basis, const float* beta, float* dx_base,
                       float* dx_basis, float* dbeta, void* stream);
@@ -127,13 +131,31 @@ int kc_maxpool2d_bwd(const float* dy, const unsigned char* idx, float* dx, long 
  * mean/rstd are [n*c] (instance) or [c] (batch) and are outputs of fwd / inputs of bwd.
  * alpha = PReLU weight (1 element, device).  bwd writes dz and per-plane partials that it then reduces into
  * dgamma[c], dbeta[c], dalpha[1] (any of which may be NULL).  `partials` needs 3*n*c + 2*c floats.
- * fwd `scratch` (2*n*c floats) is only used for KC_NORM_BATCH (per-plane statistics) and may be NULL otherwise.
+ * fwd `scratch` (2*n*c floats) is only used for KC_NORM_BATCH with batch statistics (per-plane sums) and may be NULL
+ * otherwise.  KC_NORM_BATCH with scratch == NULL means "normalise with the GIVEN statistics": mean / rstd are inputs
+ * (nn.BatchNorm in eval mode: running_mean and rsqrt(running_var + eps)) and are not modified.
+ * bwd with `given_stats` != 0 (eval-mode batch norm) treats mean / rstd as constants: dz = rstd * gamma * dy * act'.
  * ------------------------------------------------------------------------------------------------------- */
 int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const float* gamma, const float* beta,
                     const float* alpha, float* y, float* mean, float* rstd, float* scratch, void* stream);
 int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const float* z, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* alpha, float* dz, float* dgamma,
-                    float* dbeta, float* dalpha, float* partials, void* stream);
+                    float* dbeta, float* dalpha, float* partials, int given_stats, void* stream);
+
+/* LayerNorm over the features of each row + output activation: the tail of the fully-connected KANLayer
+ * (layers/kan_layers.py:110-112, nn.LayerNorm(out_features) -> nn.PReLU; models/kans.py:300-327 stacks them).  z, y, dy, dz are
+ * [rows, features] fp32; gamma / beta are per FEATURE (elementwise affine); mean / rstd are [rows]; `partials` = rows floats. */
+typedef struct kc_rownorm_desc {
+  int32_t rows, features;
+  int32_t out_act;     /* kc_out_act_kind */
+  int32_t affine;      /* gamma/beta present */
+  float eps;
+} kc_rownorm_desc;
+int kc_layernorm_act_fwd(const kc_rownorm_desc* d, const float* z, const float* gamma, const float* beta,
+                         const float* alpha, float* y, float* mean, float* rstd, void* stream);
+int kc_layernorm_act_bwd(const kc_rownorm_desc* d, const float* dy, const float* z, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, const float* alpha, float* dz, float* dgamma,
+                         float* dbeta, float* dalpha, float* partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * BF16 tensor-core path (tcgen05.mma, fp32 accumulate in TMEM).  Dilation 1, stride 1..4 (a strided layer runs on the
@@ -171,6 +193,11 @@ int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* x_base, con
 int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base, const float* x_basis,
                      const float* beta, const void* phi, float* dw_base, float* dw_basis, void* workspace,
                      void* stream);
+
+/* Tile geometry the tensor-core kernels choose for a shape (host-side, needs no GPU; for integrators and tests).
+ * which 0 = forward, 1 = dgrad; out[8] = {M sub-tiles per CTA, N tile, number of N tiles, A ring depth, taps per weight
+ * stage, weight ring depth, M tiles, dynamic shared memory in bytes}. */
+int kc_tc_geometry(const kc_desc* d, int which, long long* out);
 
 /* Self-test of the tcgen05 shared-memory descriptor conventions this library relies on: runs a 128xNx64 bf16 GEMM
  * through the same UMMA helpers as the convolution kernels and returns the max abs error against a CUDA-core

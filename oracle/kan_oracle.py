@@ -20,6 +20,9 @@ Reference call sites restated here (paths relative to the reference tree):
   * GRAMKANConvNDLayer.beta/gram_poly/forward_kag  layers/gram_kan_layers.py:150-199
   * FastKANConvNDLayer.forward_fast_kan .......... layers/fast_kan_layers.py:100-120
   * RadialBasisFunction.forward .................. utils/utils.py:19-33
+  * KANLayer.forward (fully-connected layer) ..... layers/kan_layers.py:8-114
+  * KANConv1DLayer (ndim = 1 binding) ............ layers/kan_layers.py:287-297
+  * KAN (MLP of KANLayers) ....................... models/kans.py:300-327
   * VGG.make_layers / forward .................... models/kan_vgg.py:40-188
 
 The third-party arithmetic underneath (conv2d, instance/batch norm, PReLU, GELU/SiLU) lives in
@@ -39,6 +42,7 @@ __all__ = [
     "make_knots", "bspline_basis", "cheby_basis", "gram_basis", "rbf_basis",
     "kan_conv2d", "cheby_conv2d", "gram_conv2d", "fastkan_conv2d",
     "OracleKANConv2D", "OracleChebyKANConv2D", "OracleGRAMKANConv2D", "OracleFastKANConv2D",
+    "OracleKANConv1D", "OracleKANLayer", "OracleKAN", "kan_conv1d", "kan_linear",
     "OracleVGG", "VGG_CFGS", "conv_flops",
 ]
 
@@ -174,6 +178,25 @@ def fastkan_conv2d(x, w_base, w_spline, grid, denominator, act="silu", stride=1,
     u = _norm(x, norm, eps, norm_weight, norm_bias, running, training)
     phi = _expand(rbf_basis(u, grid, denominator))
     return base + F.conv2d(phi, w_spline, None, stride, padding, dilation)
+
+
+def kan_conv1d(x, w_base, w_spline, prelu_weight, knots, spline_order, act="gelu", stride=1, padding=0, dilation=1,
+               eps=1e-5, norm_weight=None, norm_bias=None):
+    """One group of KANConvNDLayer.forward_kan with ndim = 1 (kan_layers.py:197-247 bound by KANConv1DLayer :287-297):
+    x [N, C, L]; nn.Conv1d / InstanceNorm1d underneath."""
+    base = F.conv1d(_act(act)(x), w_base, None, stride, padding, dilation)
+    phi = bspline_basis(x, knots, spline_order).movedim(-1, 2).flatten(1, 2)      # [N, C*nb, L], channel c*nb + j
+    z = base + F.conv1d(phi, w_spline, None, stride, padding, dilation)
+    return F.prelu(F.instance_norm(z, None, None, norm_weight, norm_bias, True, 0.1, eps), prelu_weight)
+
+
+def kan_linear(x, base_weight, spline_weight, ln_weight, ln_bias, prelu_weight, knots, spline_order, act="gelu", eps=1e-5):
+    """KANLayer.forward (kan_layers.py:46-114): x [B, in]; base_weight [out, in]; spline_weight [out, in, nb];
+    LayerNorm over the output features, then PReLU."""
+    base = F.linear(_act(act)(x), base_weight)
+    bases = bspline_basis(x, knots, spline_order)                                   # [B, in, nb]
+    spline = F.linear(bases.reshape(x.shape[0], -1), spline_weight.reshape(spline_weight.shape[0], -1))
+    return F.prelu(F.layer_norm(base + spline, (base_weight.shape[0],), ln_weight, ln_bias, eps), prelu_weight)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -365,6 +388,77 @@ class OracleFastKANConv2D(_OracleBase):
                                        self.rbf.denominator, self.act, self.stride, self.padding, self.dilation,
                                        self.norm_kind, 1e-5, nw, nb, running, self.training))
         return torch.cat(outs, dim=1)
+
+
+class OracleKANConv1D(_OracleBase):
+    """KANConv1DLayer (kan_layers.py:287-297): the N-D layer bound to nn.Conv1d / nn.InstanceNorm1d."""
+
+    def __init__(self, input_dim, output_dim, kernel_size, spline_order=3, groups=1, padding=0, stride=1, dilation=1,
+                 grid_size=5, base_activation="gelu", grid_range=(-1, 1), affine=False):
+        super().__init__()
+        self._check_groups(input_dim, output_dim, groups)
+        k = int(kernel_size)
+        cg, og = input_dim // groups, output_dim // groups
+        self.groups, self.cg, self.og = groups, cg, og
+        self.spline_order, self.act = spline_order, _act_name(base_activation)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.base_conv = nn.ModuleList([_Weight((og, cg, k)) for _ in range(groups)])
+        self.spline_conv = nn.ModuleList([_Weight((og, cg * (grid_size + spline_order), k)) for _ in range(groups)])
+        self.layer_norm = nn.ModuleList([nn.InstanceNorm1d(og, affine=affine) for _ in range(groups)])
+        self.prelus = nn.ModuleList([nn.PReLU() for _ in range(groups)])
+        self.knots = make_knots(grid_size, spline_order, grid_range)
+        for m in list(self.base_conv) + list(self.spline_conv):
+            nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nw, nb = self._nw(self.layer_norm[g])
+            outs.append(kan_conv1d(xg, self.base_conv[g].weight, self.spline_conv[g].weight, self.prelus[g].weight,
+                                   self.knots, self.spline_order, self.act, self.stride, self.padding, self.dilation,
+                                   1e-5, nw, nb))
+        return torch.cat(outs, dim=1)
+
+
+class OracleKANLayer(nn.Module):
+    """KANLayer (kan_layers.py:8-114); state_dict keys base_weight, spline_weight, layer_norm.{weight,bias}, prelu.weight."""
+
+    def __init__(self, input_features, output_features, grid_size=5, spline_order=3, base_activation="gelu",
+                 grid_range=(-1, 1)):
+        super().__init__()
+        self.spline_order, self.act = spline_order, _act_name(base_activation)
+        self.base_weight = nn.Parameter(torch.randn(output_features, input_features))
+        self.spline_weight = nn.Parameter(torch.randn(output_features, input_features, grid_size + spline_order))
+        self.layer_norm = nn.LayerNorm(output_features)
+        self.prelu = nn.PReLU()
+        self.knots = make_knots(grid_size, spline_order, grid_range)
+        nn.init.kaiming_uniform_(self.base_weight, nonlinearity="linear")
+        nn.init.kaiming_uniform_(self.spline_weight, nonlinearity="linear")
+
+    def forward(self, x):
+        return kan_linear(x, self.base_weight, self.spline_weight, self.layer_norm.weight, self.layer_norm.bias,
+                          self.prelu.weight, self.knots, self.spline_order, self.act, self.layer_norm.eps)
+
+
+class OracleKAN(nn.Module):
+    """KAN MLP (models/kans.py:300-327): KANLayers with optional Dropout in between (keys layers.{i}.*)."""
+
+    def __init__(self, layers_hidden, dropout=0.0, grid_size=5, spline_order=3, base_activation="gelu", grid_range=(-1, 1),
+                 first_dropout=True):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        if dropout > 0 and first_dropout:
+            self.layers.append(nn.Dropout(p=dropout))
+        n = len(layers_hidden) - 1
+        for i, (fin, fout) in enumerate(zip(layers_hidden[:-1], layers_hidden[1:])):
+            self.layers.append(OracleKANLayer(fin, fout, grid_size, spline_order, base_activation, grid_range))
+            if dropout > 0 and i != n - 1:
+                self.layers.append(nn.Dropout(p=dropout))
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
 
 
 # ----------------------------------------------------------------------------------------------

@@ -12,10 +12,11 @@ from oracle import kan_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d}
 ORACLE_CTORS = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram": O.OracleGRAMKANConv2D,
-                "fast": O.OracleFastKANConv2D}
+                "fast": O.OracleFastKANConv2D, "kan1d": O.OracleKANConv1D, "kanlayer": O.OracleKANLayer}
 
 
-MODEL_FIXTURES = {"mbv2_fastkan_forward"}      # whole-model fixtures (make_model_golden.py): a different record layout
+# whole-model fixtures (make_model_golden.py): a different record layout
+MODEL_FIXTURES = {"mbv2_fastkan_forward", "vgg16_kansmall_forward", "vgg11_forward", "kan_mlp_forward"}
 
 
 def golden_names():
@@ -62,7 +63,30 @@ def run_fwd_bwd(m, x, g):
 
 
 def rel_err(a, b):
-    """max |a-b| / max |b| (scale-relative max error)."""
+    """max |a-b| / max |b| (scale-relative max error) over the finite elements of the expected tensor ``b``.
+    Non-finite values must sit at exactly the same positions in both (NaN <-> NaN, +-Inf <-> the same Inf); otherwise inf."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    fin = torch.isfinite(b)
+    if not bool(fin.all()):
+        if not torch.equal(torch.isnan(a), torch.isnan(b)):
+            return float("inf")
+        inf = torch.isinf(b)
+        if not torch.equal(torch.isinf(a), inf) or not torch.equal(a[inf], b[inf]):
+            return float("inf")
+        a, b = a[fin], b[fin]
+        if b.numel() == 0:
+            return 0.0
+    elif not bool(torch.isfinite(a).all()):
+        return float("inf")
     denom = float(b.abs().max())
     return float((a - b).abs().max()) / (denom if denom > 0 else 1.0)
+
+
+def tol_violations(a, b, rtol=2e-2, atol=1e-3):
+    """Fraction of elements outside BASELINE north_star's elementwise BF16 tolerance |a-b| <= atol + rtol*|b| (finite part)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    fin = torch.isfinite(b) & torch.isfinite(a)
+    if int(fin.sum()) == 0:
+        return 0.0
+    bad = ((a - b).abs() > atol + rtol * b.abs()) & fin
+    return float(bad.sum()) / float(fin.sum())

@@ -29,7 +29,7 @@ NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d}
 def adversarial_(x, kind):
     """Overwrite a few entries with values at the basis' discontinuities / saturation points."""
     flat = x.view(-1)
-    if kind == "kan":
+    if kind in ("kan", "kan1d", "kanlayer"):
         vals = [-2.2000000477, -1.8000000715, -1.0, -0.6000000238, 0.2000000179, 1.0, 2.2000000477,
                 2.1999998, -2.3, 2.5, 7.0, -9.0, 0.0]
     elif kind == "cheby":
@@ -64,10 +64,25 @@ CASES = [
     ("fast_bn_g5_1x1", "fast", dict(input_dim=6, output_dim=4, kernel_size=1, padding=0, grid_size=5, grid_range=[-1, 1],
                                     norm_layer="batch"), (3, 6, 5, 5)),
     ("fast_groups_s2", "fast", dict(input_dim=4, output_dim=4, kernel_size=3, padding=1, stride=2, groups=2), (2, 4, 8, 8)),
+    # round 2: 1-D convolution layers (kan_layers.py:287-297) and the fully-connected KANLayer (kan_layers.py:8-114)
+    ("kan1d_small", "kan1d", dict(input_dim=4, output_dim=6, kernel_size=3, padding=1, base_activation="gelu"), (2, 4, 11)),
+    ("kan1d_groups_s2", "kan1d", dict(input_dim=4, output_dim=4, kernel_size=3, padding=0, stride=2, groups=2,
+                                    base_activation="silu"), (3, 4, 12)),
+    ("kanlayer_small", "kanlayer", dict(input_features=7, output_features=5, base_activation="gelu"), (6, 7)),
+    ("kanlayer_silu_g3k2", "kanlayer", dict(input_features=12, output_features=9, grid_size=3, spline_order=2,
+                                            grid_range=[-2, 2], base_activation="silu"), (5, 12)),
+    # round 2: non-finite inputs (NaN => NaN, +-Inf => NaN through 0 * Inf in the Cox-de Boor recursion).
+    # One poisoned element per image: the fixture records which outputs / gradients the reference turns into NaN.
+    ("kan_naninf", "kan", dict(input_dim=4, output_dim=6, kernel_size=3, padding=1, base_activation="silu"), (4, 4, 9, 7),
+     {0: float("nan"), 1: float("inf"), 2: float("-inf")}),
+    ("cheby_naninf", "cheby", dict(input_dim=4, output_dim=6, kernel_size=3, padding=1, degree=3), (3, 4, 9, 7),
+     {0: float("nan"), 1: float("inf")}),
+    ("gram_naninf", "gram", dict(input_dim=4, output_dim=6, kernel_size=3, padding=1, degree=3), (3, 4, 9, 7),
+     {0: float("nan"), 1: float("-inf")}),
 ]
 
 CTORS = {"kan": "KANConv2DLayer", "cheby": "ChebyKANConv2DLayer", "gram": "GRAMKANConv2DLayer",
-         "fast": "FastKANConv2DLayer"}
+         "fast": "FastKANConv2DLayer", "kan1d": "KANConv1DLayer", "kanlayer": "KANLayer"}
 
 
 def build(kind, kw):
@@ -96,7 +111,12 @@ def run(module, x, g, dtype):
 
 
 def main():
-    for name, kind, kw, xshape in CASES:
+    only = set(sys.argv[1:])            # optional: names of the cases to (re)generate; default = all + the checksums
+    for case in CASES:
+        name, kind, kw, xshape = case[:4]
+        poison = case[4] if len(case) > 4 else {}
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         m = build(kind, kw)
         m.train()
@@ -109,6 +129,8 @@ def main():
                     p.copy_(0.05 * torch.randn_like(p))
         torch.manual_seed(1)
         x = adversarial_(torch.randn(*xshape) * 1.2, kind)
+        for img, val in poison.items():
+            x[img].view(-1)[(img * 53 + 17) % x[img].numel()] = val
         sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
         with torch.no_grad():
             yshape = m(x).shape
@@ -131,7 +153,9 @@ def main():
             if v is not None:
                 out["grad32/" + k] = v.numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-        print(f"{name}: y{tuple(y64.shape)} |y|={float(y64.norm()):.6f}")
+        print(f"{name}: y{tuple(y64.shape)} |y|={float(torch.nan_to_num(y64).norm()):.6f} nan(y)={int(torch.isnan(y64).sum())}")
+    if only:
+        return
 
     # Known-answer checksums of BASELINE config 1 (SURVEY Appendix E recipe) - regenerated from the live reference.
     ck = {}

@@ -14,19 +14,27 @@ from kanconv_b200 import _lib as L
 from _util import Golden, golden_names
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer}
+CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer,
+         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer}
 
 
 def test_library_exports_every_declared_symbol():
     lib = L.load()
     header = open(os.path.join(ROOT, "include", "kanconv.h")).read()
     declared = set(re.findall(r"\b(kc_[a-z0-9_]+)\s*\(", header))
-    declared -= {"kc_desc", "kc_norm_desc"}
+    declared -= {"kc_desc", "kc_norm_desc", "kc_rownorm_desc"}
     assert declared, "no declarations parsed"
     for name in sorted(declared):
         assert hasattr(lib, name), f"libkanconv.so does not export {name}"
     assert set(L.EXPORTED_SYMBOLS) == declared
-    assert lib.kc_version() == 1
+    assert lib.kc_version() == L.KC_ABI_VERSION == int(re.search(r"#define KC_ABI_VERSION (\d+)", header).group(1))
+    # the product library carries no debug / experiment exports (they exist only in a KANCONV_DEBUG=1 build)
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", L.library_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\b(kc_[a-z0-9_]+)\b", syms))
+    if os.environ.get("KANCONV_DEBUG") != "1":
+        assert not [s_ for s_ in exported if s_.startswith("kc_debug")], exported
+    assert declared <= exported
 
 
 def test_struct_layout_matches_header():
@@ -34,6 +42,7 @@ def test_struct_layout_matches_header():
     assert L.KcDesc.x_batch_stride.offset == 80
     assert ctypes.sizeof(L.KcNormDesc) == 40
     assert L.KcNormDesc.batch_stride.offset == 24
+    assert ctypes.sizeof(L.KcRowNormDesc) == 20 and L.KcRowNormDesc.eps.offset == 16
 
 
 def test_desc_validation_through_abi():

@@ -9,7 +9,7 @@ import kanconv_b200 as K
 from kanconv_b200 import functional as KF
 
 lib = K._lib.load()
-lib.kc_debug_tc_geometry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+lib.kc_tc_geometry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
 FIELDS = ["nsub", "ntile", "n_nt", "na", "tps", "bst", "mtiles", "smem"]
 SMEM_LIMIT = 227 * 1024
 
@@ -23,7 +23,7 @@ def _desc(n, cin, cout, h, w, k=3, pad=1, stride=1, dilation=1):
 
 def _geom(d, which):
     out = (ctypes.c_longlong * 8)()
-    assert lib.kc_debug_tc_geometry(ctypes.byref(d), which, out) == 0, lib.kc_last_error()
+    assert lib.kc_tc_geometry(ctypes.byref(d), which, out) == 0, lib.kc_last_error()
     return dict(zip(FIELDS, list(out)))
 
 

@@ -13,7 +13,8 @@ from oracle import kan_oracle as O
 from _util import Golden, golden_names, rel_err, run_fwd_bwd
 
 pytestmark = pytest.mark.gpu
-CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer}
+CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer,
+         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer}
 FP32_TOL = 1e-5
 BF16_TOL = 2e-2
 

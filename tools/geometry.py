@@ -5,7 +5,7 @@ import torch.nn as nn
 import kanconv_b200 as K
 from kanconv_b200 import functional as KF
 lib = K._lib.load()
-lib.kc_debug_tc_geometry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+lib.kc_tc_geometry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
 shapes = [(32, 64, 128, 112), (32, 128, 128, 112), (64, 3, 64, 224), (64, 64, 64, 224), (64, 64, 128, 112), (64, 128, 128, 112), (64, 128, 256, 56), (64, 256, 256, 56),
           (64, 256, 512, 28), (64, 512, 512, 28), (64, 512, 512, 14), (16, 512, 512, 14), (16, 64, 64, 224)]
 for n, cin, cout, hw in shapes:
@@ -14,7 +14,7 @@ for n, cin, cout, hw in shapes:
     row = []
     for which in (0, 1):
         out = (ctypes.c_longlong * 8)()
-        rc = lib.kc_debug_tc_geometry(ctypes.byref(d), which, out)
+        rc = lib.kc_tc_geometry(ctypes.byref(d), which, out)
         row.append(dict(zip(["nsub", "ntile", "n_nt", "na", "tps", "bst", "mtiles", "smem"], list(out))) if rc == 0 else None)
     for which, r in zip(("fwd  ", "dgrad"), row):
         ctas = r["mtiles"] * r["n_nt"]
