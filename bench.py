@@ -13,8 +13,14 @@ Keys beyond the base contract:
   roofline      - dominant kernel of the step (by summed device time), measured live with CUDA events on the launching
                   stream in a separate instrumented pass of the SAME step: achieved = algorithmic FLOPs per launch
                   (2*N*Ho*Wo*Cout*Cin*(nb+1)*kh*kw) / mean launch duration; peak = MEASURED_PEAKS.json.
-  cpu_baseline  - the oracle port of the reference algorithm (oracle/kan_oracle.py, PyTorch CPU, all host cores) timed on
-                  a bounded sample of the same workload (rank 0, N = 1 only).
+  cpu_baseline  - the reference's own modules when its tree is importable (/root/reference in the dev container, or
+                  baseline/_ref; kind "reference"), else the oracle port of the same algorithm (oracle/kan_oracle.py; kind
+                  "port" - the reference is a Python project and does not travel to the GPU box), PyTorch CPU, all host cores,
+                  timed on a bounded sample of the same workload (rank 0, N = 1 only).
+  gpu_eager_baseline - informational: the same eager-PyTorch modules (reference or port) on THIS GPU, cuDNN/cuBLAS with
+                  TF32 off and on, at the largest power-of-two batch that fits - what a user of the reference runs today.
+  ddp_selfcheck - N > 1 only: max relative deviation of the DDP-averaged gradients of a small sharded batch from the
+                  single-process gradients of the concatenated batch (outside the timed region).
   e2e           - same metric through the public nn.Module API with HOST inputs: every step copies its pinned-host batch
                   to the device and reads the loss back.
 """
@@ -33,6 +39,8 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
+TRAFFIC_FILE = "r2_traffic_b64.json"      # ncu DRAM-traffic capture of this workload (tools/ncu_round.sh + summarize_profiles.py)
+
 WORKLOADS = {
     # name: (arch, H=W, classes, default per-GPU batch, expected_feature_shape, cpu sample batch)
     "kan_vgg16_224": ("VGG16", 224, 1000, 64, (7, 7), 1),
@@ -43,7 +51,7 @@ WORKLOADS = {
 
 def vgg_conv_shapes(arch, hw, cin=3):
     """[(cin, cout, h)] of the KAN conv layers of a KAN-VGG (models/kan_vgg.py:119-130 semantics)."""
-    from oracle.kan_oracle import VGG_CFGS
+    from kanconv_b200.models import cfgs as VGG_CFGS
     out, c, h = [], cin, hw
     for v in VGG_CFGS[arch]:
         if v == "M":
@@ -122,14 +130,41 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup, sample_batch=None):
+def reference_model(workload):
+    """-> (nn.Module on the CPU, kind): the reference's own vggkan() when its tree is importable, else the oracle port."""
+    arch, hw, classes, _, feat, _ = WORKLOADS[workload]
+    for cand in (os.environ.get("KAN_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if not cand or not os.path.isfile(os.path.join(cand, "models", "kan_vgg.py")):
+            continue
+        try:
+            import contextlib
+            import io
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, cand)
+            import models.kan_vgg as ref_vgg
+            if "VGG11" not in ref_vgg.cfgs:       # BASELINE config 3: absent upstream, injected as in the survey
+                ref_vgg.cfgs["VGG11"] = [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512]
+            torch.manual_seed(0)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = ref_vgg.vggkan(3, classes, arch=arch, classifier_type="Linear", expected_feature_shape=feat, spline_order=3,
+                                   grid_size=5)
+            return m, "reference"
+        except Exception as e:      # incomplete tree / missing dependency: fall back to the port, and say so
+            print(f"bench.py: reference at {cand} not usable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        finally:
+            if cand in sys.path:
+                sys.path.remove(cand)
     from oracle import kan_oracle as O
+    torch.manual_seed(0)
+    return O.OracleVGG(3, classes, arch=arch, expected_feature_shape=feat, dropout_linear=0.5), "port"
+
+
+def cpu_reference_run(workload, steps, warmup, sample_batch=None):
     arch, hw, classes, _, feat, cpu_b = WORKLOADS[workload]
     b = sample_batch or cpu_b
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    model = O.OracleVGG(3, classes, arch=arch, expected_feature_shape=feat, dropout_linear=0.5)
+    model, kind = reference_model(workload)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
     lossf = nn.CrossEntropyLoss()
     g = torch.Generator().manual_seed(1234)
@@ -146,9 +181,60 @@ def cpu_reference_run(workload, steps, warmup, sample_batch=None):
         if i >= warmup:
             times.append(dt)
     mean = sum(times) / len(times)
-    return {"value": b / mean, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of batch {b} ({workload}, fp32, torch {torch.__version__} CPU, {torch.get_num_threads()} threads)",
+    return {"value": b / mean, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} step(s) of batch {b} after {warmup} warm-up ({workload}, fp32, torch {torch.__version__} CPU, "
+                      f"{torch.get_num_threads()} threads; min {min(times) * 1e3:.0f} ms, mean {mean * 1e3:.0f} ms per step)",
             "ms_per_step": mean * 1e3, "batch": b}
+
+
+def gpu_eager_baseline(workload, dev):
+    """Informational: the eager-PyTorch modules of the reference (or the port) on this GPU.  TF32 off and on; batch doubled
+    while the measured peak memory says the next size still fits in 70 % of the device."""
+    arch, hw, classes, _, feat, _ = WORKLOADS[workload]
+    out = {"unit": "images/s", "note": "eager PyTorch (cuDNN / cuBLAS) forward + CrossEntropy + backward + AdamW of the reference "
+                                       "modules on the same GPU; materialises the expanded basis tensor"}
+    try:
+        model, kind = reference_model(workload)
+        model = model.to(dev).train()
+        out["kind"] = kind
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        lossf = nn.CrossEntropyLoss()
+        total = torch.cuda.get_device_properties(dev).total_memory
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+        def run(b, tf32, steps=2):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+            g = torch.Generator().manual_seed(1234)
+            x = torch.randn(b, 3, hw, hw, generator=g).to(dev)
+            y = torch.randint(0, classes, (b,), generator=g).to(dev)
+            ts = []
+            for i in range(1 + steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                opt.zero_grad(set_to_none=True)
+                lossf(model(x), y).backward()
+                opt.step()
+                e1.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    ts.append(e0.elapsed_time(e1))
+            return b / (min(ts) * 1e-3)
+
+        try:
+            b, best = 1, {}
+            while True:
+                torch.cuda.reset_peak_memory_stats(dev)
+                best = {"batch": b, "tf32_off": run(b, False), "tf32_on": run(b, True)}
+                peak = torch.cuda.max_memory_allocated(dev)
+                out.update(best, peak_gb=round(peak / 2 ** 30, 1))
+                if b >= 64 or peak * 2.2 > 0.7 * total:
+                    break
+                b *= 2
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    except Exception as e:     # informational leg: never let it take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+    return out
 
 
 def run_reference(args):
@@ -161,7 +247,9 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "arch": arch, "image": [3, hw, hw], "classes": classes,
-                       "per_gpu_batch": batch, "sampled_batch": r["batch"], "impl": "oracle port of the reference (CPU)"},
+                       "per_gpu_batch": batch, "sampled_batch": r["batch"],
+                       "impl": ("the reference's own modules (CPU)" if r["kind"] == "reference"
+                                else "oracle port of the reference (CPU; the Python reference tree is not on this box)")},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -306,18 +394,49 @@ def run_b200(args):
                     "traffic": None, "launches_per_step": st["calls"], "ms_per_launch": st["ms"] / st["calls"],
                     "share_of_library_time": st["ms"] / total_ms, "peak_source": peak_src}
         roof["by_kernel_ms"] = {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        # DRAM bytes per launch of that kernel from the committed ncu capture of this workload (profiles/), if any
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic_b64.json")
+        # DRAM bytes per launch of that kernel from the committed ncu capture of this workload (profiles/).  The capture
+        # records the hash of the CUDA sources it was taken with; a capture of other kernels is refused (traffic = null).
+        tpath = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
         if args.workload == "kan_vgg16_224" and batch == 64 and os.path.exists(tpath):
+            from kanconv_b200 import build as KB
             with open(tpath) as fh:
-                kern = json.load(fh)["kernels"]
-            # template instantiations of one kernel are listed separately in the capture (kc_wgrad_tc_kernel<64>, <128>)
-            hits = [v for k, v in kern.items() if k == name or k.startswith(name + "<")]
-            if hits:
-                nl = sum(v["launches_per_step"] for v in hits)
-                tot = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in hits)
-                roof["traffic"] = int(tot / max(nl, 1e-9))
-                roof["traffic_source"] = "profiles/r1_traffic_b64.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+                cap = json.load(fh)
+            if cap.get("source_hash") != KB.source_hash():
+                roof["traffic_stale"] = (f"profiles/{TRAFFIC_FILE} was captured with other kernel sources "
+                                         f"({str(cap.get('source_hash'))[:12]} != {KB.source_hash()[:12]}); not used")
+            else:
+                kern = cap["kernels"]
+                # template instantiations of one kernel are listed separately in the capture (kc_wgrad_tc_kernel<64>, <128>)
+                hits = [v for k, v in kern.items() if k == name or k.startswith(name + "<")]
+                if hits:
+                    nl = sum(v["launches_per_step"] for v in hits)
+                    tot = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in hits)
+                    roof["traffic"] = int(tot / max(nl, 1e-9))
+                    roof["traffic_source"] = (f"profiles/{TRAFFIC_FILE} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per "
+                                              f"launch; sources {KB.source_hash()[:12]})")
+
+    # ---- N > 1: gradient equality of the sharded step (outside the timed region) -----------------------------------
+    selfcheck = None
+    if world > 1:
+        per, side = 2, 64
+        gs = torch.Generator().manual_seed(4321)
+        xa = torch.randn(per * world, 3, side, side, generator=gs).to(dev)
+        ya = torch.randint(0, classes, (per * world,), generator=gs).to(dev)
+        model.eval()                      # head Dropout off: the two runs must see the same function
+        opt.zero_grad(set_to_none=True)
+        lossf(net(xa[rank * per:(rank + 1) * per]), ya[rank * per:(rank + 1) * per]).backward()      # DDP: all-reduced mean
+        torch.cuda.synchronize()
+        got = [p.grad.detach().clone() for p in model.parameters()]
+        opt.zero_grad(set_to_none=True)
+        lossf(model(xa), ya).backward()                                                             # one process, whole batch
+        worst = 0.0
+        for a_, p in zip(got, model.parameters()):
+            worst = max(worst, float((a_ - p.grad).abs().max() / p.grad.abs().max().clamp_min(1e-30)))
+        worst = max_over_ranks(worst)
+        opt.zero_grad(set_to_none=True)
+        model.train()
+        selfcheck = {"grad_max_rel": worst, "images": per * world, "image": [3, side, side],
+                     "what": "max over parameters and ranks of max|g_ddp - g_single| / max|g_single|"}
 
     if rank != 0:
         if world > 1:
@@ -325,8 +444,15 @@ def run_b200(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(args.workload, 1, 1)
+        cpu = cpu_reference_run(args.workload, 3, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    eager = None
+    if world == 1 and not args.no_gpu_eager_baseline:
+        del net, opt
+        model.to("cpu")
+        KF._PACKS.clear()
+        torch.cuda.empty_cache()
+        eager = gpu_eager_baseline(args.workload, dev)
     gb = batch * world
     flops = step_flops(arch, hw, batch)
     line = {
@@ -341,6 +467,10 @@ def run_b200(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e, "last_loss": last},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+    if selfcheck is not None:
+        line["ddp_selfcheck"] = selfcheck
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -356,6 +486,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "b200" and args.gpus != world:

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "kc_conv_wgrad_tc": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 9),
     "kc_maxpool2d_fwd": (ctypes.c_int, [c_vp] * 3 + [ctypes.c_longlong] + [ctypes.c_int] * 6 + [c_vp]),
     "kc_maxpool2d_bwd": (ctypes.c_int, [c_vp] * 3 + [ctypes.c_longlong] + [ctypes.c_int] * 6 + [c_vp]),
+    "kc_norm_bwd_dz_flat_supported": (ctypes.c_int, [_P(KcDesc), _P(KcNormDesc)]),
+    "kc_norm_bwd_dz_flat": (ctypes.c_int, [_P(KcDesc), _P(KcNormDesc)] + [c_vp] * 9),
     "kc_tc_geometry": (ctypes.c_int, [_P(KcDesc), ctypes.c_int, _P(ctypes.c_longlong)]),
     "kc_tc_selftest": (ctypes.c_int, [ctypes.c_int, _P(ctypes.c_float), c_vp]),
 }

@@ -36,6 +36,11 @@ void kc_count_launch();   // per-process counter of kernels launched by this lib
 int kc_validate_desc(const kc_desc* d);   // common argument checks (kc_api.cu)
 bool kc_knots_uniform_cubic(const kc_desc* d, float* t0, float* inv_h);   // kc_api.cu
 int kc_sm_count();                         // SMs of the current device (kc_api.cu)
+// kc_norm.cu: per-plane partial sums -> dgamma / dbeta / dalpha (any may be NULL), fixed summation order
+int kc_norm_partials_to_params(const kc_norm_desc* d, const float* partials, float* dgamma, float* dbeta, float* dalpha, void* stream);
+// kc_norm_cluster.cu: shared-memory-resident InstanceNorm forward for large planes; KC_ERR_UNSUPPORTED if the shape is not covered
+int kc_instnorm_fwd_cluster(const kc_norm_desc* d, const float* z, const float* gamma, const float* beta, const float* alpha,
+                            float* y, float* mean, float* rstd, void* stream);
 // GRAM d/d beta_weights: fixed-order sum of the `nrows` partial rows behind dbeta[0 .. KC_MAX_BASIS) into it (kc_norm.cu)
 int kc_dbeta_reduce(float* dbeta, long long nrows, void* stream);
 
@@ -73,6 +78,10 @@ __device__ inline void kc_load_basis_ctx(KcBasisCtx* B, const kc_desc& d, const 
   }
   __syncthreads();
 }
+
+// Chebyshev: where clamp(tanh x, -1+1e-7, 1-1e-7) is active autograd MASKS the gradient (clamp backward is a select, not a
+// product), so dx is exactly 0 there even when the incoming gradient is NaN / Inf (cheby_kan_layers.py:93-96).
+__device__ __forceinline__ bool kc_cheby_clamped(float t) { return (t < -1.0f + 1e-7f) || (t > 1.0f - 1e-7f); }
 
 // GRAM with dropout: the binding applies tanh and Dropout to the input itself and sets params[0] = 1 (nparams = 1)
 __device__ __forceinline__ bool kc_gram_presquashed(const KcBasisCtx& B) { return B.nparams > 0 && B.p[0] != 0.0f; }

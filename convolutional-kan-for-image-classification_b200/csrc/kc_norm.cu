@@ -4,6 +4,7 @@
 // (the later passes over the same plane hit L2, the plane is <= 200 KB) and written once; 16-byte accesses,
 // warp-shuffle + shared-memory block reductions.
 #include "kc_common.cuh"
+#include "kc_norm_common.cuh"
 
 namespace {
 
@@ -12,33 +13,6 @@ constexpr int kNTBig = 1024;      // planes of >= 16 K elements: one or two plan
                                   // third pass over a plane hit L2 (8 resident 256-thread CTAs x 200 KB planes overflow it)
 constexpr int kBigPlane = 16384;
 
-
-__device__ __forceinline__ float block_sum(float v, float* sh) {
-  // all threads of the block must call; returns the total to every thread
-  v = kc_warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  __syncthreads();
-  if (lane == 0) sh[wid] = v;
-  __syncthreads();
-  float t = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0f;
-  if (wid == 0) {
-    t = kc_warp_sum(t);
-    if (lane == 0) sh[0] = t;
-  }
-  __syncthreads();
-  return sh[0];
-}
-
-__device__ __forceinline__ float out_act(int kind, float v, float alpha) {
-  if (kind == KC_OUT_PRELU) return v > 0.0f ? v : alpha * v;
-  if (kind == KC_OUT_SILU) return kc_silu(v);
-  return v;
-}
-__device__ __forceinline__ float out_act_grad(int kind, float v, float alpha) {
-  if (kind == KC_OUT_PRELU) return v > 0.0f ? 1.0f : alpha;
-  if (kind == KC_OUT_SILU) return kc_silu_grad(v);
-  return 1.0f;
-}
 
 // ---- generic strided plane iteration helpers (vectorised when aligned) ----------------------------------
 template <typename F>
@@ -421,6 +395,12 @@ extern "C" int kc_layernorm_act_bwd(const kc_rownorm_desc* d, const float* dy, c
   return KC_OK;
 }
 
+int kc_norm_partials_to_params(const kc_norm_desc* d, const float* partials, float* dgamma, float* dbeta, float* dalpha, void* stream) {
+  kc_partials_reduce_kernel<<<d->c + 1, kNT, 0, (cudaStream_t)stream>>>(*d, partials, dgamma, dbeta, dalpha);
+  KC_LAUNCH_CHECK("kc_partials_reduce_kernel");
+  return KC_OK;
+}
+
 int kc_dbeta_reduce(float* dbeta, long long nrows, void* stream) {
   kc_dbeta_reduce_kernel<<<1, KC_MAX_BASIS * 64, 0, (cudaStream_t)stream>>>(dbeta, nrows);
   KC_LAUNCH_CHECK("kc_dbeta_reduce_kernel");
@@ -444,6 +424,10 @@ extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const floa
     KC_LAUNCH_CHECK("kc_plane_stats_kernel");
     kc_batch_stats_combine_kernel<<<(d->c + 7) / 8, 256, 0, st>>>(*d, pmean, pm2, mean, rstd);
     KC_LAUNCH_CHECK("kc_batch_stats_combine_kernel");
+  }
+  if (d->norm == KC_NORM_INSTANCE) {          // large planes: the shared-memory-resident cluster kernel (one HBM read)
+    rc = kc_instnorm_fwd_cluster(d, z, gamma, beta, alpha, y, mean, rstd, stream);
+    if (rc != KC_ERR_UNSUPPORTED) return rc;
   }
   kc_instnorm_fwd_kernel<<<planes, nt, 0, st>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
   KC_LAUNCH_CHECK("kc_instnorm_fwd_kernel");

@@ -232,6 +232,7 @@ kc_dgrad_simt_kernel(const __grid_constant__ kc_desc d, const float* __restrict_
 #pragma unroll
     for (int j = 0; j < KC_MAX_BASIS; ++j)
       if (j < nb) gs = fmaf(acc[j], dphi[j], gs);
+    if (d.basis == KC_BASIS_CHEBY && kc_cheby_clamped(tanhf(xb))) gs = 0.0f;
     float gb = 0.0f;
     if (has_base) {
       float ga = 0.0f;

@@ -197,6 +197,7 @@ __device__ __noinline__ float dgrad_generic(const KcBasisCtx& B, float x, const 
     if (j < B.nb) gs = fmaf(gg[j], dphi[j], gs);
   }
   if (dbl != nullptr) kc_gram_dbeta(B, x, gg, 1, dbl);
+  if (B.kind == KC_BASIS_CHEBY && kc_cheby_clamped(tc_tanh(x))) gs = 0.0f;
   return gs;
 }
 
@@ -721,7 +722,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 
 // d(basis_j)/dx for the RBF and Chebyshev families, j < 8, registers only (every index is a compile-time constant):
 // the epilogue of the persistent dgrad for the layers that have no closed-form cubic basis.
-__device__ __forceinline__ void tc_basis_grad8(const KcBasisCtx& B, float x, float (&dphi)[8]) {
+// Returns true when the gradient is masked to exactly zero (Chebyshev clamp active).
+__device__ __forceinline__ bool tc_basis_grad8(const KcBasisCtx& B, float x, float (&dphi)[8]) {
   const int nb = B.nb;
   if (B.kind == KC_BASIS_RBF) {
     const float inv_den = __fdividef(1.0f, B.p[nb]);
@@ -730,6 +732,7 @@ __device__ __forceinline__ void tc_basis_grad8(const KcBasisCtx& B, float x, flo
       const float q = (x - B.p[j]) * inv_den;
       dphi[j] = j < nb ? __expf(-(q * q)) * (-2.0f * q * inv_den) : 0.0f;
     }
+    return false;
   } else {      // KC_BASIS_CHEBY: d T_j(c) / dx = j U_{j-1}(c) (1 - t^2), c = clamp(tanh x)
     const float lo = -1.0f + 1e-7f, hi = 1.0f - 1e-7f;
     const float t = tc_tanh(x);
@@ -743,6 +746,7 @@ __device__ __forceinline__ void tc_basis_grad8(const KcBasisCtx& B, float x, flo
       const float U2 = 2.0f * c * U1 - U0;
       U0 = U1; U1 = U2;
     }
+    return kc_cheby_clamped(t);
   }
 }
 
@@ -1029,14 +1033,15 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
           ga = __uint_as_float(r[8]);
         } else {
           float dphi[8];
-          tc_basis_grad8(*B, xc[c4], dphi);
+          const bool masked = tc_basis_grad8(*B, xc[c4], dphi);
           gs = 0.0f;
           ga = __uint_as_float(r[8]);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            gs = fmaf(__uint_as_float(r[jj]), dphi[jj], gs);      // dphi is zero for jj >= nb
+            if (jj < nb) gs = fmaf(__uint_as_float(r[jj]), dphi[jj], gs);      // columns >= nb belong to the base branch / next channel
             if (jj == nb) ga = __uint_as_float(r[jj]);
           }
+          if (masked) gs = 0.0f;
         }
         float gb = 0.0f;
         if (has_base) gb = ga * act_grad_fast(act, same_x ? xc[c4] : __ldg(a.x_base + o));
@@ -1567,6 +1572,16 @@ extern "C" size_t kc_tc_bytes(const kc_desc* d, int which) {
   if (which == 4) return kc_tc_wgrad_ws_bytes(d, 1);
   if (which == 5) return kc_tc_wgrad_ws_bytes(d, 2);
   return 0;
+}
+
+// Layout of the bf16 flat dz buffer (kc_tc_dz_flat / kc_norm_bwd_dz_flat): row pitch, positions per image, total positions,
+// channels per position (cout rounded up to 16).
+int kc_tc_flat_layout(const kc_desc* d, int* P, int* IMG, long long* L, int* cq) {
+  TcGeom g;
+  int rc = tc_dgrad_geometry(d, &g);
+  if (rc != KC_OK) return rc;
+  *P = g.P; *IMG = g.IMG; *L = g.L; *cq = g.Cp;
+  return KC_OK;
 }
 
 // GRAM only: floats of the `dbeta` buffer (KC_MAX_BASIS results + one partial row per thread block / epilogue warp).

@@ -67,6 +67,29 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
+// ---- thread-block clusters / distributed shared memory ---------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// split cluster barrier: arrive (release) ... wait (acquire); every thread of every CTA of the cluster executes both
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// read one float from the shared memory of CTA `rank` of this cluster at the address `p` has in this CTA
+__device__ __forceinline__ float dsmem_ld(const float* p, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
 // 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination.  Completion is tracked with
 // commit_group / wait_group, so a producer thread can keep several pipeline stages in flight without holding registers.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {

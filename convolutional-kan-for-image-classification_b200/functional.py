@@ -36,6 +36,8 @@ _TC_BACKWARD = os.environ.get("KANCONV_TC_BACKWARD", "1") != "0"   # debug switc
 # KANCONV_SAVE_PHI=0: do not keep the bf16 basis rows between forward and backward (saves 18 B per input element per
 # layer of activation memory; the weight gradient then re-evaluates them in a pre-pass)
 _SAVE_PHI = os.environ.get("KANCONV_SAVE_PHI", "1") != "0"
+# KANCONV_FUSED_NORM_BWD=0: debug switch, norm backward to fp32 dz + separate conversion to the bf16 flat layout
+_FUSED_NORM_BWD = os.environ.get("KANCONV_FUSED_NORM_BWD", "1") != "0"
 _PRECISION = "auto"      # "auto": tensor cores when the shape is supported, else CUDA-core FP32 | "bf16" | "fp32"
 
 
@@ -223,140 +225,160 @@ def pack_cache_stats() -> dict:
     return dict(_PACK_STATS, entries=len(_PACKS))
 
 
+def _split_weights(spec: ConvSpec, weights):
+    G = spec.groups
+    w_base = list(weights[:G]) if spec.has_base else [None] * G
+    w_basis = list(weights[G:2 * G]) if spec.has_base else list(weights[:G])
+    return w_base, w_basis
+
+
+def _conv_fwd(spec: ConvSpec, precision: str, xb, xs, beta, weights, want_phi: bool):
+    """Forward of all groups.  -> (z, used_tc, phis, roots).  xb / xs contiguous, same device."""
+    lib = L.load()
+    dev = xb.device
+    G = spec.groups
+    n, c_total, h, w = xb.shape
+    cg = c_total // G
+    w_base, w_basis = _split_weights(spec, weights)
+    og = w_basis[0].shape[0]
+    ho, wo = spec.out_hw(h, w)
+    used_tc, phis = [], []
+    roots = [(_root(w_base[g]), _root(w_basis[g])) for g in range(G)]
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        z = torch.empty((n, og * G, ho, wo), device=dev, dtype=torch.float32)
+        for g in range(G):
+            d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
+            xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
+            wbg = None if w_base[g] is None else w_base[g].contiguous()
+            wsg = w_basis[g].contiguous()
+            tc = _use_tc(lib, d, precision)
+            used_tc.append(tc)
+            if tc:
+                versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
+                packed = _packed_weights(lib, d, 0, wbg, wsg, roots[g], versions, stream, "kc_pack_fwd_kernel")
+                phi = None
+                if (want_phi or lib.kc_tc_fwd_needs_phi(ctypes.byref(d))) and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
+                    phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=dev, dtype=torch.uint8)
+                phis.append(phi)
+                L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
+                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), _ptr(phi), stream)),
+                    "kc_conv_fwd_tc")
+            else:
+                phis.append(None)
+                L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
+                    ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream)),
+                    "kc_conv_fwd_f32")
+    return z, used_tc, phis, roots
+
+
+def _conv_bwd(spec: ConvSpec, used_tc, phis, roots, xb, xs, alias: bool, beta, weights, dz, dzf_of_group,
+              need_dx: bool, need_dbeta: bool, need_w):
+    """Backward of all groups.  ``dz`` = fp32 gradient of z, or None when ``dzf_of_group(g, desc)`` supplies the bf16 flat buffer
+    of every tensor-core group (fused norm backward).  -> (dx_base, dx_basis, dbeta, dws)."""
+    lib = L.load()
+    dev = xb.device
+    G = spec.groups
+    n, c_total, h, w = xb.shape
+    cg = c_total // G
+    w_base, w_basis = _split_weights(spec, weights)
+    og = w_basis[0].shape[0]
+    ho, wo = spec.out_hw(h, w)
+    gram = spec.basis == L.BASIS_GRAM and beta is not None
+    run_dgrad = need_dx or (gram and need_dbeta)
+    dx_base = dx_basis = dbeta = None
+    dws: List[Optional[torch.Tensor]] = [None] * len(weights)
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        if run_dgrad:
+            dx_base = torch.empty_like(xb)
+            dx_basis = dx_base if alias else torch.empty_like(xs)
+        for g in range(G):
+            d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
+            sl = slice(g * cg, (g + 1) * cg)
+            xbg, xsg = xb[:, sl], xs[:, sl]
+            dzg = None if dz is None else dz[:, g * og:(g + 1) * og]
+            wbg = None if w_base[g] is None else w_base[g].contiguous()
+            wsg = w_basis[g].contiguous()
+            tc_bwd = used_tc[g] and _TC_BACKWARD and lib.kc_tc_bytes(ctypes.byref(d), 1) > 0
+            dzf = None
+            if tc_bwd:
+                dzf = dzf_of_group(g, d) if dzf_of_group is not None else None
+                if dzf is None:
+                    dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
+                    L.check(_timed("kc_dz_flat_kernel", 0.0, 6.0 * dzg.numel(), lambda: lib.kc_tc_dz_flat(
+                        ctypes.byref(d), _ptr(dzg), _ptr(dzf), stream)), "kc_tc_dz_flat")
+            if run_dgrad:
+                # GRAM: d/d beta_weights of this group (deterministic: per-block partial rows + fixed-order reduction)
+                dbg = None
+                if gram and need_dbeta:
+                    dbg = torch.empty(lib.kc_dbeta_floats(ctypes.byref(d), 1 if tc_bwd else 0), device=dev, dtype=torch.float32)
+                if tc_bwd:
+                    versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
+                    packed_d = _packed_weights(lib, d, 1, wbg, wsg, roots[g], versions, stream, "kc_pack_dgrad_kernel")
+                    L.check(_timed("kc_tc_kernel<dgrad>", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_tc(
+                        ctypes.byref(d), None, _ptr(xbg), _ptr(xsg), _ptr(packed_d), _ptr(beta), _ptr(dx_base[:, sl]),
+                        _ptr(dx_basis[:, sl]), _ptr(dbg), _ptr(dzf), stream)), "kc_conv_dgrad_tc")
+                else:
+                    L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
+                        ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
+                        _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbg), stream)), "kc_conv_dgrad_f32")
+                if dbg is not None:
+                    part = dbg[:beta.numel()]
+                    dbeta = part.clone() if dbeta is None else dbeta + part       # groups are added in order
+            wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
+            if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
+                dwb = torch.empty_like(wbg) if wbg is not None else None
+                dwsg = torch.empty_like(wsg)
+                if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
+                    phi = phis[g]
+                    ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=dev, dtype=torch.uint8)
+                    L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
+                        ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(phi), _ptr(dwb), _ptr(dwsg), _ptr(ws),
+                        stream)), "kc_conv_wgrad_tc")
+                    phis[g] = None
+                else:
+                    nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
+                    ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+                    L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
+                        ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
+                        "kc_conv_wgrad_f32")
+                if wi_base is not None:
+                    dws[wi_base] = dwb
+                dws[wi_basis] = dwsg
+    return dx_base, dx_basis, dbeta, dws
+
+
 class _KanConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: ConvSpec, precision: str, x_base, x_basis, beta, *weights):
-        lib = L.load()
         alias = x_basis is None
         xb = x_base.contiguous()
         xs = xb if alias else x_basis.contiguous()
         _require_cuda(xb, "kan_conv")
         _require_cuda(xs, "kan_conv")
-        dev = xb.device
-        _same_device("kan_conv", dev, xs, beta, *weights)
-        G = spec.groups
-        n, c_total, h, w = xb.shape
-        cg = c_total // G
-        w_base = list(weights[:G]) if spec.has_base else [None] * G
-        w_basis = list(weights[G:2 * G]) if spec.has_base else list(weights[:G])
-        og = w_basis[0].shape[0]
-        ho, wo = spec.out_hw(h, w)
-        used_tc = []
+        _same_device("kan_conv", xb.device, xs, beta, *weights)
         # basis rows saved for the weight gradient (the reference keeps the expanded basis alive for autograd, too)
         want_phi = _SAVE_PHI and _TC_BACKWARD and any(ctx.needs_input_grad[5:])
-        phis = []
-        roots = [(_root(w_base[g]), _root(w_basis[g])) for g in range(G)]
-        with torch.cuda.device(dev):
-            stream = _stream(dev)
-            z = torch.empty((n, og * G, ho, wo), device=dev, dtype=torch.float32)
-            for g in range(G):
-                d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
-                xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
-                wbg = None if w_base[g] is None else w_base[g].contiguous()
-                wsg = w_basis[g].contiguous()
-                tc = _use_tc(lib, d, precision)
-                used_tc.append(tc)
-                if tc:
-                    versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
-                    packed = _packed_weights(lib, d, 0, wbg, wsg, roots[g], versions, stream, "kc_pack_fwd_kernel")
-                    phi = None
-                    if (want_phi or lib.kc_tc_fwd_needs_phi(ctypes.byref(d))) and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
-                        phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=dev, dtype=torch.uint8)
-                    phis.append(phi)
-                    L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
-                        ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), _ptr(phi), stream)),
-                        "kc_conv_fwd_tc")
-                else:
-                    phis.append(None)
-                    L.check(_timed("kc_fwd_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_f32(
-                        ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta), _ptr(zg), stream)),
-                        "kc_conv_fwd_f32")
-        ctx.spec, ctx.alias, ctx.precision, ctx.used_tc, ctx.phis, ctx.roots = spec, alias, precision, used_tc, phis, roots
+        z, used_tc, phis, roots = _conv_fwd(spec, precision, xb, xs, beta, weights, want_phi)
+        ctx.spec, ctx.alias, ctx.used_tc, ctx.phis, ctx.roots = spec, alias, used_tc, phis, roots
         ctx.save_for_backward(xb, xs if not alias else None, beta, *weights)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        lib = L.load()
-        spec: ConvSpec = ctx.spec
         saved = ctx.saved_tensors
         xb, xs, beta = saved[0], saved[1], saved[2]
         weights = saved[3:]
         alias = ctx.alias
         if alias:
             xs = xb
-        dev = xb.device
-        _same_device("kan_conv backward", dev, dz)
-        G = spec.groups
-        n, c_total, h, w = xb.shape
-        cg = c_total // G
-        w_base = list(weights[:G]) if spec.has_base else [None] * G
-        w_basis = list(weights[G:2 * G]) if spec.has_base else list(weights[:G])
-        og = w_basis[0].shape[0]
-        ho, wo = spec.out_hw(h, w)
-        dz = dz.contiguous()
+        _same_device("kan_conv backward", xb.device, dz)
         # inputs of forward: (spec, precision, x_base, x_basis, beta, *weights)
         need_dxb, need_dxs, need_dbeta = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
-        need_w = list(ctx.needs_input_grad[5:])
-        gram = spec.basis == L.BASIS_GRAM and beta is not None
-        run_dgrad = need_dxb or need_dxs or (gram and need_dbeta)
-        dx_base = dx_basis = dbeta = None
-        dws: List[Optional[torch.Tensor]] = [None] * len(weights)
-        with torch.cuda.device(dev):
-            stream = _stream(dev)
-            if run_dgrad:
-                dx_base = torch.empty_like(xb)
-                dx_basis = dx_base if alias else torch.empty_like(xs)
-            for g in range(G):
-                d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
-                sl = slice(g * cg, (g + 1) * cg)
-                xbg, xsg, dzg = xb[:, sl], xs[:, sl], dz[:, g * og:(g + 1) * og]
-                wbg = None if w_base[g] is None else w_base[g].contiguous()
-                wsg = w_basis[g].contiguous()
-                tc_bwd = ctx.used_tc[g] and _TC_BACKWARD and lib.kc_tc_bytes(ctypes.byref(d), 1) > 0
-                dzf = None
-                if tc_bwd:
-                    dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
-                    L.check(_timed("kc_dz_flat_kernel", 0.0, 6.0 * dzg.numel(), lambda: lib.kc_tc_dz_flat(
-                        ctypes.byref(d), _ptr(dzg), _ptr(dzf), stream)), "kc_tc_dz_flat")
-                if run_dgrad:
-                    # GRAM: d/d beta_weights of this group (deterministic: per-block partial rows + fixed-order reduction)
-                    dbg = None
-                    if gram and need_dbeta:
-                        dbg = torch.empty(lib.kc_dbeta_floats(ctypes.byref(d), 1 if tc_bwd else 0), device=dev, dtype=torch.float32)
-                    if tc_bwd:
-                        versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
-                        packed_d = _packed_weights(lib, d, 1, wbg, wsg, ctx.roots[g], versions, stream, "kc_pack_dgrad_kernel")
-                        L.check(_timed("kc_tc_kernel<dgrad>", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_tc(
-                            ctypes.byref(d), None, _ptr(xbg), _ptr(xsg), _ptr(packed_d), _ptr(beta), _ptr(dx_base[:, sl]),
-                            _ptr(dx_basis[:, sl]), _ptr(dbg), _ptr(dzf), stream)), "kc_conv_dgrad_tc")
-                    else:
-                        L.check(_timed("kc_dgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_dgrad_f32(
-                            ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(wbg), _ptr(wsg), _ptr(beta),
-                            _ptr(dx_base[:, sl]), _ptr(dx_basis[:, sl]), _ptr(dbg), stream)), "kc_conv_dgrad_f32")
-                    if dbg is not None:
-                        part = dbg[:beta.numel()]
-                        dbeta = part.clone() if dbeta is None else dbeta + part       # groups are added in order
-                wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
-                if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
-                    dwb = torch.empty_like(wbg) if wbg is not None else None
-                    dwsg = torch.empty_like(wsg)
-                    if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
-                        phi = ctx.phis[g]
-                        ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=dev, dtype=torch.uint8)
-                        L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
-                            ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(phi), _ptr(dwb), _ptr(dwsg), _ptr(ws),
-                            stream)), "kc_conv_wgrad_tc")
-                        ctx.phis[g] = None
-                    else:
-                        nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
-                        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
-                        L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
-                            ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
-                            "kc_conv_wgrad_f32")
-                    if wi_base is not None:
-                        dws[wi_base] = dwb
-                    dws[wi_basis] = dwsg
+        dx_base, dx_basis, dbeta, dws = _conv_bwd(ctx.spec, ctx.used_tc, ctx.phis, ctx.roots, xb, xs, alias, beta, weights,
+                                                  dz.contiguous(), None, need_dxb or need_dxs, need_dbeta,
+                                                  list(ctx.needs_input_grad[5:]))
         return (None, None, dx_base if need_dxb else None, (dx_basis if (need_dxs and not alias) else None),
                 dbeta if need_dbeta else None, *dws)
 
@@ -368,45 +390,93 @@ def kan_conv(spec: ConvSpec, x_base: torch.Tensor, x_basis: Optional[torch.Tenso
     return _KanConvFn.apply(spec, precision or _PRECISION, x_base, x_basis, beta, *weights)
 
 
+def _norm_params(spec: NormSpec, params):
+    G = spec.groups
+    # params layout: [gamma_0, beta_0, ..., gamma_{G-1}, beta_{G-1}] if affine, then [alpha_0..alpha_{G-1}] if PReLU
+    gam = [params[2 * g] for g in range(G)] if spec.affine else [None] * G
+    bet = [params[2 * g + 1] for g in range(G)] if spec.affine else [None] * G
+    off = 2 * G if spec.affine else 0
+    alp = [params[off + g] for g in range(G)] if spec.out_act == L.OUT_PRELU else [None] * G
+    return gam, bet, alp, off
+
+
+def _norm_desc(spec: NormSpec, n, cg, hw, c_total) -> L.KcNormDesc:
+    d = L.KcNormDesc()
+    d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
+    d.batch_stride, d.eps = c_total * hw, spec.eps
+    return d
+
+
+def _norm_fwd(spec: NormSpec, z, given_mean, given_rstd, params):
+    """-> (y, mean, rstd); z contiguous."""
+    lib = L.load()
+    dev = z.device
+    G = spec.groups
+    n, c_total, h, w = z.shape
+    cg, hw = c_total // G, h * w
+    gam, bet, alp, _ = _norm_params(spec, params)
+    given = spec.norm == L.NORM_BATCH and not spec.use_batch_stats
+    if given and (given_mean is None or given_rstd is None):
+        raise ValueError("norm_act: BatchNorm with use_batch_stats=False needs given_mean / given_rstd")
+    nstat = {L.NORM_NONE: 1, L.NORM_INSTANCE: n * cg, L.NORM_BATCH: cg}[spec.norm]
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        y = torch.empty_like(z)
+        if given:       # eval-mode BatchNorm: the running statistics are inputs of the kernel (scratch = NULL)
+            mean = given_mean.detach().to(torch.float32).reshape(G, cg).contiguous()
+            rstd = given_rstd.detach().to(torch.float32).reshape(G, cg).contiguous()
+        else:
+            mean = torch.empty((G, nstat), device=dev, dtype=torch.float32)
+            rstd = torch.empty((G, nstat), device=dev, dtype=torch.float32)
+        for g in range(G):
+            d = _norm_desc(spec, n, cg, hw, c_total)
+            scratch = None
+            if spec.norm == L.NORM_BATCH and not given:
+                scratch = torch.empty(2 * n * cg, device=dev, dtype=torch.float32)
+            L.check(_timed("kc_instnorm_fwd_kernel", 0.0, 8.0 * n * cg * hw, lambda: lib.kc_norm_act_fwd(
+                ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
+                _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream)), "kc_norm_act_fwd")
+    return y, mean, rstd
+
+
+def _norm_bwd(spec: NormSpec, z, mean, rstd, params, dy):
+    """-> (dz fp32, grads of params); dy contiguous."""
+    lib = L.load()
+    dev = z.device
+    given = int(spec.norm == L.NORM_BATCH and not spec.use_batch_stats)
+    G = spec.groups
+    n, c_total, h, w = z.shape
+    cg, hw = c_total // G, h * w
+    gam, bet, alp, off = _norm_params(spec, params)
+    grads: List[Optional[torch.Tensor]] = [None] * len(params)
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        dz = torch.empty_like(z)
+        for g in range(G):
+            d = _norm_desc(spec, n, cg, hw, c_total)
+            partials = torch.empty(3 * n * cg + 2 * cg, device=dev, dtype=torch.float32)
+            dgam = torch.empty_like(gam[g]) if spec.affine else None
+            dbet = torch.empty_like(bet[g]) if spec.affine else None
+            dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
+            sl = slice(g * cg, (g + 1) * cg)
+            L.check(_timed("kc_norm_bwd_kernel", 0.0, 12.0 * n * cg * hw, lambda: lib.kc_norm_act_bwd(
+                ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]), _ptr(bet[g]),
+                _ptr(alp[g]), _ptr(dz[:, sl]), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials), given, stream)),
+                "kc_norm_act_bwd")
+            if spec.affine:
+                grads[2 * g], grads[2 * g + 1] = dgam, dbet
+            if dalp is not None:
+                grads[off + g] = dalp
+    return dz, grads
+
+
 class _NormActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: NormSpec, z, given_mean, given_rstd, *params):
-        lib = L.load()
         z = z.contiguous()
         _require_cuda(z, "norm_act")
-        dev = z.device
-        _same_device("norm_act", dev, given_mean, given_rstd, *params)
-        G = spec.groups
-        n, c_total, h, w = z.shape
-        cg, hw = c_total // G, h * w
-        # params layout: [gamma_0, beta_0, ..., gamma_{G-1}, beta_{G-1}] if affine, then [alpha_0..alpha_{G-1}] if PReLU
-        gam = [params[2 * g] for g in range(G)] if spec.affine else [None] * G
-        bet = [params[2 * g + 1] for g in range(G)] if spec.affine else [None] * G
-        off = 2 * G if spec.affine else 0
-        alp = [params[off + g] for g in range(G)] if spec.out_act == L.OUT_PRELU else [None] * G
-        given = spec.norm == L.NORM_BATCH and not spec.use_batch_stats
-        if given and (given_mean is None or given_rstd is None):
-            raise ValueError("norm_act: BatchNorm with use_batch_stats=False needs given_mean / given_rstd")
-        nstat = {L.NORM_NONE: 1, L.NORM_INSTANCE: n * cg, L.NORM_BATCH: cg}[spec.norm]
-        with torch.cuda.device(dev):
-            stream = _stream(dev)
-            y = torch.empty_like(z)
-            if given:       # eval-mode BatchNorm: the running statistics are inputs of the kernel (scratch = NULL)
-                mean = given_mean.detach().to(torch.float32).reshape(G, cg).contiguous()
-                rstd = given_rstd.detach().to(torch.float32).reshape(G, cg).contiguous()
-            else:
-                mean = torch.empty((G, nstat), device=dev, dtype=torch.float32)
-                rstd = torch.empty((G, nstat), device=dev, dtype=torch.float32)
-            for g in range(G):
-                d = L.KcNormDesc()
-                d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
-                d.batch_stride, d.eps = c_total * hw, spec.eps
-                scratch = None
-                if spec.norm == L.NORM_BATCH and not given:
-                    scratch = torch.empty(2 * n * cg, device=dev, dtype=torch.float32)
-                L.check(_timed("kc_instnorm_fwd_kernel", 0.0, 8.0 * n * cg * hw, lambda: lib.kc_norm_act_fwd(
-                    ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
-                    _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream)), "kc_norm_act_fwd")
+        _same_device("norm_act", z.device, given_mean, given_rstd, *params)
+        y, mean, rstd = _norm_fwd(spec, z, given_mean, given_rstd, params)
         ctx.spec = spec
         ctx.save_for_backward(z, mean, rstd, *params)
         ctx.mark_non_differentiable(mean, rstd)
@@ -414,42 +484,10 @@ class _NormActFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dmean, _drstd):
-        lib = L.load()
-        spec: NormSpec = ctx.spec
         z, mean, rstd = ctx.saved_tensors[:3]
         params = ctx.saved_tensors[3:]
-        dev = z.device
-        _same_device("norm_act backward", dev, dy)
-        given = int(spec.norm == L.NORM_BATCH and not spec.use_batch_stats)
-        G = spec.groups
-        n, c_total, h, w = z.shape
-        cg, hw = c_total // G, h * w
-        gam = [params[2 * g] for g in range(G)] if spec.affine else [None] * G
-        bet = [params[2 * g + 1] for g in range(G)] if spec.affine else [None] * G
-        off = 2 * G if spec.affine else 0
-        alp = [params[off + g] for g in range(G)] if spec.out_act == L.OUT_PRELU else [None] * G
-        dy = dy.contiguous()
-        grads: List[Optional[torch.Tensor]] = [None] * len(params)
-        with torch.cuda.device(dev):
-            stream = _stream(dev)
-            dz = torch.empty_like(z)
-            for g in range(G):
-                d = L.KcNormDesc()
-                d.norm, d.out_act, d.n, d.c, d.hw, d.affine = spec.norm, spec.out_act, n, cg, hw, int(spec.affine)
-                d.batch_stride, d.eps = c_total * hw, spec.eps
-                partials = torch.empty(3 * n * cg + 2 * cg, device=dev, dtype=torch.float32)
-                dgam = torch.empty_like(gam[g]) if spec.affine else None
-                dbet = torch.empty_like(bet[g]) if spec.affine else None
-                dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
-                sl = slice(g * cg, (g + 1) * cg)
-                L.check(_timed("kc_norm_bwd_kernel", 0.0, 12.0 * n * cg * hw, lambda: lib.kc_norm_act_bwd(
-                    ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]), _ptr(bet[g]),
-                    _ptr(alp[g]), _ptr(dz[:, sl]), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials), given, stream)),
-                    "kc_norm_act_bwd")
-                if spec.affine:
-                    grads[2 * g], grads[2 * g + 1] = dgam, dbet
-                if dalp is not None:
-                    grads[off + g] = dalp
+        _same_device("norm_act backward", z.device, dy)
+        dz, grads = _norm_bwd(ctx.spec, z, mean, rstd, params, dy.contiguous())
         return (None, dz, None, None, *grads)
 
 
@@ -464,6 +502,94 @@ def norm_act(spec: NormSpec, z: torch.Tensor, gammas: Sequence[torch.Tensor] = (
     if spec.out_act == L.OUT_PRELU:
         params += list(alphas)
     return _NormActFn.apply(spec, z, given_mean, given_rstd, *params)
+
+
+class _KanLayerFn(torch.autograd.Function):
+    """conv -> norm -> output activation of one KAN convolution layer as ONE autograd node (kan_layers.py:199-243).
+
+    Same kernels as ``kan_conv`` followed by ``norm_act`` in the forward.  The point is the backward: on the tensor-core path
+    the norm backward writes dz directly in the bf16 flat operand layout of the dgrad / wgrad kernels
+    (``kc_norm_bwd_dz_flat``), so the fp32 dz tensor and the separate conversion pass never exist."""
+
+    @staticmethod
+    def forward(ctx, spec: ConvSpec, nspec: NormSpec, precision: str, x, beta, given_mean, given_rstd, n_weights: int, *params):
+        weights, nparams = params[:n_weights], params[n_weights:]
+        xb = x.contiguous()
+        _require_cuda(xb, "kan_layer")
+        _same_device("kan_layer", xb.device, beta, given_mean, given_rstd, *params)
+        want_phi = _SAVE_PHI and _TC_BACKWARD and any(ctx.needs_input_grad[8:8 + n_weights])
+        z, used_tc, phis, roots = _conv_fwd(spec, precision, xb, xb, beta, weights, want_phi)
+        y, mean, rstd = _norm_fwd(nspec, z, given_mean, given_rstd, nparams)
+        ctx.spec, ctx.nspec, ctx.used_tc, ctx.phis, ctx.roots, ctx.n_weights = spec, nspec, used_tc, phis, roots, n_weights
+        ctx.save_for_backward(xb, beta, z, mean, rstd, *params)
+        ctx.mark_non_differentiable(mean, rstd)
+        return y, mean, rstd
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _drstd):
+        lib = L.load()
+        spec, nspec, nw = ctx.spec, ctx.nspec, ctx.n_weights
+        xb, beta, z, mean, rstd = ctx.saved_tensors[:5]
+        params = ctx.saved_tensors[5:]
+        weights, nparams = params[:nw], params[nw:]
+        dev = xb.device
+        _same_device("kan_layer backward", dev, dy)
+        dy = dy.contiguous()
+        G = nspec.groups
+        n, c_total, ho, wo = z.shape
+        cg, hw = c_total // G, ho * wo
+        _, _, alp, off = _norm_params(nspec, nparams)
+        ngrads: List[Optional[torch.Tensor]] = [None] * len(nparams)
+        fused = [False] * G
+
+        def dzf_of_group(g, d):
+            """bf16 flat dz of group g straight from (dy, z): the fused norm backward, when the shape allows it."""
+            nd = _norm_desc(nspec, n, cg, hw, c_total)
+            if not lib.kc_norm_bwd_dz_flat_supported(ctypes.byref(d), ctypes.byref(nd)):
+                return None
+            sl = slice(g * cg, (g + 1) * cg)
+            dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
+            partials = torch.empty(3 * n * cg, device=dev, dtype=torch.float32)
+            dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
+            L.check(_timed("kc_norm_bwd_flat_kernel", 0.0, 10.0 * n * cg * hw, lambda: lib.kc_norm_bwd_dz_flat(
+                ctypes.byref(d), ctypes.byref(nd), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(alp[g]),
+                _ptr(dzf), _ptr(dalp), _ptr(partials), _stream(dev))), "kc_norm_bwd_dz_flat")
+            if dalp is not None:
+                ngrads[off + g] = dalp
+            fused[g] = True
+            return dzf
+
+        # which groups take the fused path is decided by the same predicates _conv_bwd uses
+        n_in, cin_total, h, w = xb.shape
+        d0 = _make_desc(spec, n_in, cin_total // spec.groups, h, w, cg, cin_total * h * w, c_total * hw)
+        nd0 = _norm_desc(nspec, n, cg, hw, c_total)
+        all_fused = _TC_BACKWARD and _FUSED_NORM_BWD and all(ctx.used_tc) and lib.kc_tc_bytes(ctypes.byref(d0), 1) > 0 and \
+            lib.kc_tc_bytes(ctypes.byref(d0), 3) > 0 and \
+            bool(lib.kc_norm_bwd_dz_flat_supported(ctypes.byref(d0), ctypes.byref(nd0)))
+        dz = None
+        with torch.cuda.device(dev):
+            if not all_fused:
+                dz, ngrads_full = _norm_bwd(nspec, z, mean, rstd, nparams, dy)
+                ngrads = list(ngrads_full)
+            need = ctx.needs_input_grad
+            dx, _, dbeta, dws = _conv_bwd(spec, ctx.used_tc, ctx.phis, ctx.roots, xb, xb, True, beta, weights, dz,
+                                          dzf_of_group if all_fused else None, need[3], need[4], list(need[8:8 + nw]))
+        return (None, None, None, dx if need[3] else None, dbeta if need[4] else None, None, None, None, *dws, *ngrads)
+
+
+def kan_layer(spec: ConvSpec, nspec: NormSpec, x: torch.Tensor, beta: Optional[torch.Tensor], w_base: Sequence[torch.Tensor],
+              w_basis: Sequence[torch.Tensor], gammas: Sequence[torch.Tensor] = (), betas: Sequence[torch.Tensor] = (),
+              alphas: Sequence[torch.Tensor] = (), given_mean: Optional[torch.Tensor] = None,
+              given_rstd: Optional[torch.Tensor] = None, precision: Optional[str] = None):
+    """out_act(norm(kan_conv(x))) as one differentiable op; returns (y, mean, rstd) like ``norm_act``."""
+    weights = (list(w_base) if spec.has_base else []) + list(w_basis)
+    nparams: List[torch.Tensor] = []
+    if nspec.affine:
+        for ga, be in zip(gammas, betas):
+            nparams += [ga, be]
+    if nspec.out_act == L.OUT_PRELU:
+        nparams += list(alphas)
+    return _KanLayerFn.apply(spec, nspec, precision or _PRECISION, x, beta, given_mean, given_rstd, len(weights), *weights, *nparams)
 
 
 class _LayerNormActFn(torch.autograd.Function):

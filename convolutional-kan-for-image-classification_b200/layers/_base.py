@@ -123,6 +123,15 @@ class KANConvBase(nn.Module):
             m.running_mean.mul_(1 - mom).add_(mean[g], alpha=mom)
             m.running_var.mul_(1 - mom).add_(var, alpha=mom)
 
+    def _conv_norm_act(self, spec, x4: torch.Tensor, beta, w_base, w_basis, norms, out_act: int, alphas=()):
+        """out_act(norm(kan_conv(x))) as one autograd node (functional.kan_layer): same forward kernels as kan_conv + norm_act,
+        and a backward in which the norm kernel emits dz directly in the operand layout of the tensor-core dgrad / wgrad."""
+        nspec, gammas, betas, gm, gr = self._norm_spec(norms, out_act, self.training)
+        y, mean, rstd = KF.kan_layer(spec, nspec, x4, beta, w_base, w_basis, gammas, betas, alphas, gm, gr, self.precision)
+        if nspec.norm == L.NORM_BATCH and self.training:
+            self._update_running_stats(norms, mean, rstd, y.shape[0] * y.shape[2] * y.shape[3])
+        return y
+
     def _norm_act(self, z: torch.Tensor, norms, out_act: int, alphas=()):
         spec, gammas, betas, gm, gr = self._norm_spec(norms, out_act, self.training)
         y, mean, rstd = KF.norm_act(spec, z, gammas, betas, alphas, gm, gr)

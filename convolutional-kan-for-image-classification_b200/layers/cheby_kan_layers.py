@@ -36,8 +36,8 @@ class ChebyKANConvNDLayer(KANConvBase):
 
     def forward(self, x):
         x4 = self._to4d(x)
-        z = KF.kan_conv(self._spec, x4, None, None, [], [self._w4d(m.weight) for m in self.poly_conv], self.precision)
-        y = self._from4d(self._norm_act(z, self.layer_norm, L.OUT_NONE))
+        y = self._from4d(self._conv_norm_act(self._spec, x4, None, [], [self._w4d(m.weight) for m in self.poly_conv],
+                                             self.layer_norm, L.OUT_NONE))
         if self.dropout is not None:
             y = self.dropout(y)
         return y

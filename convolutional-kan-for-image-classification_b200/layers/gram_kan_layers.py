@@ -56,8 +56,11 @@ class GRAMKANConvNDLayer(KANConvBase):
             # their own tanh (ConvSpec.params = (1.0,) = "pre-squashed").
             x_basis = self._to4d(self.dropout(torch.tanh(x)))
             spec = self._spec_presquashed
-        z = KF.kan_conv(spec, x4, x_basis, self.beta_weights, [self._w4d(m.weight) for m in self.base_conv],
-                        [self._w4d(self.poly_weights[g]) for g in range(self.groups)], self.precision)
+        w_base = [self._w4d(m.weight) for m in self.base_conv]
+        w_poly = [self._w4d(self.poly_weights[g]) for g in range(self.groups)]
+        if x_basis is None:
+            return self._from4d(self._conv_norm_act(spec, x4, self.beta_weights, w_base, w_poly, self.layer_norm, L.OUT_SILU))
+        z = KF.kan_conv(spec, x4, x_basis, self.beta_weights, w_base, w_poly, self.precision)
         return self._from4d(self._norm_act(z, self.layer_norm, L.OUT_SILU))
 
 

@@ -53,9 +53,9 @@ class KANConvNDLayer(KANConvBase):
 
     def forward(self, x):
         x4 = self._to4d(x)
-        z = KF.kan_conv(self._spec, x4, None, None, [self._w4d(m.weight) for m in self.base_conv],
-                        [self._w4d(m.weight) for m in self.spline_conv], self.precision)
-        y = self._norm_act(z, self.layer_norm, L.OUT_PRELU, [m.weight for m in self.prelus])
+        y = self._conv_norm_act(self._spec, x4, None, [self._w4d(m.weight) for m in self.base_conv],
+                                [self._w4d(m.weight) for m in self.spline_conv], self.layer_norm, L.OUT_PRELU,
+                                [m.weight for m in self.prelus])
         y = self._from4d(y)
         if self.dropout is not None:
             y = self.dropout(y)

@@ -199,6 +199,16 @@ int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const float* x_base,
  * stage, weight ring depth, M tiles, dynamic shared memory in bytes}. */
 int kc_tc_geometry(const kc_desc* d, int which, long long* out);
 
+/* Backward of (InstanceNorm -> output activation) fused with the conversion of dz to the bf16 flat operand layout:
+ * equivalent to kc_norm_act_bwd followed by kc_tc_dz_flat, without the fp32 dz round trip through HBM (reads dy and z once,
+ * writes 2 bytes per element).  `conv` = descriptor of the convolution that produced z (its geometry fixes the flat layout),
+ * `dz_flat` = kc_tc_bytes(conv, 2) bytes, `partials` = 3*n*c floats, `dalpha` (1 float) may be NULL.  Covers instance norm
+ * without affine parameters on stride-1 layers; kc_norm_bwd_dz_flat_supported() == 0 means "use the two-step path".
+ * [backward of kan_layers.py:241-243, gram:187, cheby:98] */
+int kc_norm_bwd_dz_flat_supported(const kc_desc* conv, const kc_norm_desc* d);
+int kc_norm_bwd_dz_flat(const kc_desc* conv, const kc_norm_desc* d, const float* dy, const float* z, const float* mean,
+                        const float* rstd, const float* alpha, void* dz_flat, float* dalpha, float* partials, void* stream);
+
 /* Self-test of the tcgen05 shared-memory descriptor conventions this library relies on: runs a 128xNx64 bf16 GEMM
  * through the same UMMA helpers as the convolution kernels and returns the max abs error against a CUDA-core
  * evaluation of the same product (expected < 1e-2).  mode 0 = K-major A/B, 1 = MN-major A/B. */

@@ -142,12 +142,13 @@ def _expand(basis: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 def kan_conv2d(x, w_base, w_spline, prelu_weight, knots, spline_order, act="gelu",
                stride: IntOr2 = 1, padding: IntOr2 = 0, dilation: IntOr2 = 1,
-               norm="instance", eps=1e-5, norm_weight=None, norm_bias=None):
-    """One group of KANConvNDLayer.forward_kan (kan_layers.py:197-247), ndim = 2, no dropout."""
+               norm="instance", eps=1e-5, norm_weight=None, norm_bias=None, running=None, training=True):
+    """One group of KANConvNDLayer.forward_kan (kan_layers.py:197-247), ndim = 2, no dropout.
+    ``running`` = (running_mean, running_var) of a BatchNorm2d norm layer (updated in training, used in eval)."""
     base = F.conv2d(_act(act)(x), w_base, None, stride, padding, dilation)
     phi = _expand(bspline_basis(x, knots, spline_order))
     z = base + F.conv2d(phi, w_spline, None, stride, padding, dilation)
-    return F.prelu(_norm(z, norm, eps, norm_weight, norm_bias), prelu_weight)
+    return F.prelu(_norm(z, norm, eps, norm_weight, norm_bias, running, training), prelu_weight)
 
 
 def cheby_conv2d(x, w_poly, degree, stride=1, padding=0, dilation=1,
@@ -158,10 +159,15 @@ def cheby_conv2d(x, w_poly, degree, stride=1, padding=0, dilation=1,
 
 
 def gram_conv2d(x, w_base, w_poly, beta_weights, degree, stride=1, padding=0, dilation=1,
-                norm="instance", eps=1e-5, norm_weight=None, norm_bias=None):
-    """One group of GRAMKANConvNDLayer.forward_kag (gram_kan_layers.py:172-189); SiLU everywhere."""
+                norm="instance", eps=1e-5, norm_weight=None, norm_bias=None, tanh_scale=None):
+    """One group of GRAMKANConvNDLayer.forward_kag (gram_kan_layers.py:172-189); SiLU everywhere.
+    ``tanh_scale`` ([N, C, 1, 1], entries 0 or 1/(1-p)) stands for the Dropout2d the reference applies to tanh(x)
+    (:178-179) with a mask chosen by the caller."""
     base = F.conv2d(F.silu(x), w_base, None, stride, padding, dilation)
-    polys = gram_basis(torch.tanh(x), degree, beta_weights)
+    t = torch.tanh(x)
+    if tanh_scale is not None:
+        t = t * tanh_scale
+    polys = gram_basis(t, degree, beta_weights)
     phi = F.silu(torch.cat(polys, dim=1))               # degree-major: channel d*C + c
     z = F.conv2d(phi, w_poly, None, stride, padding, dilation) + base
     return F.silu(_norm(z, norm, eps, norm_weight, norm_bias))
@@ -287,11 +293,13 @@ class OracleKANConv2D(_OracleBase):
     def forward(self, x):
         outs = []
         for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
-            nw, nb = self._nw(self.layer_norm[g])
+            nm = self.layer_norm[g]
+            nw, nb = self._nw(nm)
+            running = (nm.running_mean, nm.running_var) if isinstance(nm, nn.BatchNorm2d) else None
             outs.append(kan_conv2d(xg, self.base_conv[g].weight, self.spline_conv[g].weight,
                                    self.prelus[g].weight, self.knots, self.spline_order, self.act,
                                    self.stride, self.padding, self.dilation, self.norm_kind,
-                                   1e-5, nw, nb))
+                                   1e-5, nw, nb, running, self.training))
         return torch.cat(outs, dim=1)
 
 
@@ -340,13 +348,14 @@ class OracleGRAMKANConv2D(_OracleBase):
         nn.init.kaiming_uniform_(self.poly_weights, nonlinearity="linear")
         nn.init.normal_(self.beta_weights, 0.0, 1.0 / (kh * kw * input_dim * (degree + 1.0)))
 
-    def forward(self, x):
+    def forward(self, x, tanh_scale=None):
         outs = []
+        scales = [None] * self.groups if tanh_scale is None else torch.split(tanh_scale, self.cg, dim=1)
         for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
             nw, nb = self._nw(self.layer_norm[g])
             outs.append(gram_conv2d(xg, self.base_conv[g].weight, self.poly_weights[g], self.beta_weights,
                                     self.degree, self.stride, self.padding, self.dilation, self.norm_kind,
-                                    1e-5, nw, nb))
+                                    1e-5, nw, nb, scales[g]))
         return torch.cat(outs, dim=1)
 
 

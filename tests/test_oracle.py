@@ -116,3 +116,60 @@ def test_oracle_vgg_shapes():
     y = m(torch.randn(2, 3, 32, 32))
     assert y.shape == (2, 10)
     y.sum().backward()
+
+
+# ---- round 2: the oracle at model level against fixtures computed by the REFERENCE models (make_model_golden.py) ----------
+def _load_model_fixture(name):
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return z, json.loads(bytes(z["gradsum"]).decode()) if "gradsum" in z.files else None
+
+
+@pytest.mark.parametrize("arch,fixture", [("VGG16_kansmall", "vgg16_kansmall_forward"), ("VGG11", "vgg11_forward")])
+def test_oracle_vgg_matches_reference_model(arch, fixture):
+    """OracleVGG (the CPU baseline of bench.py and the checker of the GPU model tests) against the reference's own vggkan():
+    same seed -> same weights (the oracle modules consume the RNG like the reference ctor), fp64 logits, loss and EVERY
+    parameter gradient (sum and L2 norm for all, full tensors for a few)."""
+    z, gsum = _load_model_fixture(fixture)
+    torch.manual_seed(0)
+    m = O.OracleVGG(3, 10, arch=arch, dropout_linear=0.0).double().train()
+    x, t = torch.from_numpy(z["x"]).double(), torch.from_numpy(z["t"])
+    y = m(x)
+    loss = torch.nn.functional.cross_entropy(y, t)
+    loss.backward()
+    assert rel_err(y, torch.from_numpy(z["y"])) < 1e-10
+    assert abs(float(loss) - float(z["loss"])) < 1e-10
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    assert set(grads) == set(gsum)
+    for k, (s, nrm) in gsum.items():
+        assert abs(float(grads[k].norm()) - nrm) <= 1e-8 * max(nrm, 1e-12), k
+        assert abs(float(grads[k].sum()) - s) <= 1e-8 * max(nrm, 1e-12), k
+    for k in z.files:
+        if k.startswith("grad/"):
+            assert rel_err(grads[k[5:]], torch.from_numpy(z[k])) < 1e-9, k
+
+
+def test_oracle_kan_mlp_matches_reference_model():
+    """OracleKAN against MLP_KAN_FACTORY['KAN']([20, 16, 10]) of the reference (models/kans.py:300-327)."""
+    z, _ = _load_model_fixture("kan_mlp_forward")
+    m = O.OracleKAN([20, 16, 10], dropout=0.0)
+    m.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")})
+    m = m.double().train()
+    y, dx, grads = run_fwd_bwd(m, torch.from_numpy(z["x"]).double(), torch.from_numpy(z["g"]).double())
+    assert rel_err(y, torch.from_numpy(z["y"])) < 1e-6          # the fixture stores the weights in fp32
+    assert rel_err(dx, torch.from_numpy(z["dx"])) < 1e-6
+    for k in z.files:
+        if k.startswith("grad/"):
+            assert rel_err(grads[k[5:]], torch.from_numpy(z[k])) < 1e-6, k
+
+
+def test_nonfinite_inputs_propagate_like_the_reference():
+    """NaN and +-Inf turn every B-spline basis function into NaN; the fixtures record where NaN ends up."""
+    knots = O.make_knots(5, 3, (-1, 1))
+    b = O.bspline_basis(torch.tensor([float("inf"), float("-inf"), float("nan")]), knots, 3)
+    assert torch.isnan(b).all()
+    for name, bad_images in [("kan_naninf", [0, 1, 2]), ("cheby_naninf", [0]), ("gram_naninf", [0, 1])]:
+        gd = Golden(name)
+        nan_img = torch.isnan(gd.y64).flatten(1).all(1)
+        assert nan_img.nonzero().flatten().tolist() == bad_images, name
+        assert not torch.isnan(gd.y64[~nan_img]).any()
