@@ -13,6 +13,10 @@ constexpr int kNTBig = 1024;      // planes of >= 16 K elements: one or two plan
                                   // third pass over a plane hit L2 (8 resident 256-thread CTAs x 200 KB planes overflow it)
 constexpr int kBigPlane = 16384;
 
+// Threads per plane CTA.  Small planes get small CTAs so that up to 32 of them are resident per SM: a 14x14 plane is 49
+// float4 - with 256 threads per plane most of the block idles through three latency-bound passes (measured 0.64 TB/s).
+inline int plane_threads(int hw) { return hw >= kBigPlane ? kNTBig : hw > 1024 ? kNT : hw > 256 ? 128 : 64; }
+
 
 // ---- generic strided plane iteration helpers (vectorised when aligned) ----------------------------------
 template <typename F>
@@ -416,7 +420,7 @@ extern "C" int kc_norm_act_fwd(const kc_norm_desc* d, const float* z, const floa
   if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_fwd: PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
   const int planes = d->n * d->c;
-  const int nt = d->hw >= kBigPlane ? kNTBig : kNT;
+  const int nt = plane_threads(d->hw);
   if (d->norm == KC_NORM_BATCH && scratch != nullptr) {      // scratch == NULL: mean / rstd are given (eval mode)
     float* pmean = scratch;
     float* pm2 = scratch + planes;
@@ -444,7 +448,7 @@ extern "C" int kc_norm_act_bwd(const kc_norm_desc* d, const float* dy, const flo
   if (d->norm != KC_NORM_NONE && (!mean || !rstd)) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: mean/rstd required");
   if (d->out_act == KC_OUT_PRELU && !alpha) KC_FAIL(KC_ERR_INVALID, "kc_norm_act_bwd: PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nt = d->hw >= kBigPlane ? kNTBig : kNT;
+  const int nt = plane_threads(d->hw);
   const int planes = d->n * d->c;
   if (d->norm == KC_NORM_BATCH && given_stats) {
     // eval-mode batch norm: the statistics are constants, so dz = rstd * gamma * dy * act'(v) - the NONE formula with the

@@ -11,6 +11,8 @@
 // The bulk loads are TMA-engine copies (cp.async.bulk, SASS UBLKCP) of whole contiguous plane chunks: no registers, the
 // whole chunk is in flight at once.  Replaces native_batch_norm(_backward) + prelu / silu (+ backward) of
 // kan_layers.py:241-243, gram_kan_layers.py:187, cheby_kan_layers.py:98.
+#include <stdlib.h>
+
 #include "kc_common.cuh"
 #include "kc_norm_common.cuh"
 #include "kc_umma.cuh"
@@ -22,7 +24,8 @@ namespace {
 using namespace kc;
 
 constexpr int kFwdThreads = 256;
-constexpr int kBwdThreads = 512;
+constexpr int kBwdThreadsBig = 1024, kBwdThreadsSmall = 256;  // one CTA per SM (chunk up to 200 KB) / four CTAs per SM (<= 52 KB)
+constexpr int kBwdThreadsTiny = 64;                           // chunks of <= 64 float4 columns per channel (14x14 planes)
 constexpr uint32_t kBulkPiece = 32 * 1024;       // bytes per cp.async.bulk request
 constexpr size_t kSmemMax = 200 * 1024 + 1024;   // largest resident chunk (8 channels x 28 rows x 224 floats = 200 704 B)
 
@@ -129,72 +132,101 @@ struct NbfArgs {
   float* partials;
 };
 
-__global__ void __launch_bounds__(kBwdThreads)
+// Both phases are written for <= 64 registers per thread so that 32 warps are resident per SM (1024 threads with the 200 KB
+// chunk of the 224x224 planes, 4 x 256 threads otherwise): an elementwise kernel at this bandwidth is ISSUE-bound unless the
+// instruction count per element is small (a 512-thread / 128-register version ran at 2.7 TB/s; a version with the activation
+// kind as a run-time switch and scalar dy loads executed 63 instructions per element - profiles/r2_ncu_summary.md).  Hence:
+// activation kind and "all eight channels present" are template parameters, every global / shared access is 16 bytes wide.
+template <int KIND>
+__device__ __forceinline__ float act_grad_t(float v, float alpha) {
+  if (KIND == KC_OUT_PRELU) return v > 0.0f ? 1.0f : alpha;
+  if (KIND == KC_OUT_SILU) return kc_silu_grad(v);
+  return 1.0f;
+}
+
+// CH = channels per CTA: 8 (one CTA writes whole 16-byte vectors of the flat buffer) or 4 (two CTAs each write one 8-byte half;
+// used for the 224x224 planes so that the resident chunk is 100 KB and TWO CTAs share an SM - with one CTA per SM the bulk
+// load, the two phases and the cluster barriers of a chunk run back to back and the SM idles in between).
+template <int kBwdThreads, int CH, int KIND, bool FULL>
+__global__ void __launch_bounds__(kBwdThreads, kBwdThreads >= 1024 ? 1 : kBwdThreads >= 256 ? 4 : 16)
 kc_norm_bwd_flat_cluster_kernel(const __grid_constant__ NbfArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* zbuf = reinterpret_cast<float*>(smem_raw);           // [8][cap] zhat of this CTA's rows
-  __shared__ float red[kBwdThreads / 32][24];
-  __shared__ float part[24];         // this CTA's sums, read by the peers through DSMEM
-  __shared__ float tot[24];          // cluster totals
-  __shared__ __align__(8) uint64_t bar;
+  float* zbuf = reinterpret_cast<float*>(smem_raw);           // [CH][cap] zhat of this CTA's rows
+  __shared__ float red[kBwdThreads / 32][3 * CH];
+  __shared__ float part[3 * CH];     // this CTA's sums, read by the peers through DSMEM
+  __shared__ float4 coef[CH];        // phase 2: {rstd, rstd * mean(dv), rstd * mean(dv * zhat), 0} per channel
+  __shared__ float stat[2 * CH];     // mean[CH], rstd[CH]
+  __shared__ __align__(8) uint64_t bar[CH];     // one per channel: phase 1 starts on channel 0 while the others are in flight
+  constexpr int kParts = 8 / CH;     // CTAs (clusters) that share one 8-channel group of the flat buffer
   const kc_norm_desc& d = a.d;
   const uint32_t cs = cluster_nctarank(), rank = cluster_ctarank();
-  const int cl = blockIdx.x / cs, n = cl / a.groups8, g8 = cl % a.groups8;
-  const int c0 = g8 * 8, nch = max(0, min(8, d.c - c0));
+  const int cl = blockIdx.x / cs, half = cl % kParts, n = (cl / kParts) / a.groups8, g8 = (cl / kParts) % a.groups8;
+  const int c0 = g8 * 8 + half * CH, nch = FULL ? CH : max(0, min(CH, d.c - c0));
   const int r0 = (int)rank * a.rows, r1 = min(a.ho, r0 + a.rows);
   const int cnt = max(0, r1 - r0) * a.wo, cap = a.rows * a.wo, hw = a.ho * a.wo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long base = (long long)n * d.batch_stride + (long long)c0 * hw + (long long)r0 * a.wo;      // channel c: + c * hw
-  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < CH) mbar_init(&bar[tid], 1);
+  if (tid == 0) fence_barrier_init();
+  if (tid < 2 * CH) {
+    const int c = tid % CH;
+    stat[tid] = c < nch ? (tid < CH ? a.mean : a.rstd)[n * d.c + c0 + c] : 0.0f;
+  }
   __syncthreads();
-  if (tid == 0 && cnt > 0 && nch > 0) {
-    mbar_arrive_expect_tx(&bar, (uint32_t)(cnt * 4 * nch));
-    for (int c = 0; c < nch; ++c) bulk_load_chunk(zbuf + (size_t)c * cap, a.z + base + (long long)c * hw, (uint32_t)cnt * 4u, &bar);
-  }
-  const int kind = d.out_act;
-  const float alpha = (kind == KC_OUT_PRELU) ? a.alpha[0] : 0.0f;
-  float mean[8], rstd[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const bool ok = c < nch;
-    mean[c] = ok ? a.mean[n * d.c + c0 + c] : 0.0f;
-    rstd[c] = ok ? a.rstd[n * d.c + c0 + c] : 0.0f;
-  }
-  if (cnt > 0 && nch > 0) mbar_wait(&bar, 0);
-  // ---- phase 1: sums over this CTA's rows; zhat replaces z in shared memory -------------------------------------
-  float acc[24];
-#pragma unroll
-  for (int i = 0; i < 24; ++i) acc[i] = 0.0f;
-  const int n4 = cnt >> 2;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (c < nch) {
+  if (tid == 0 && cnt > 0)
+    for (int c = 0; c < nch; ++c) {
+      mbar_arrive_expect_tx(&bar[c], (uint32_t)cnt * 4u);
+      bulk_load_chunk(zbuf + (size_t)c * cap, a.z + base + (long long)c * hw, (uint32_t)cnt * 4u, &bar[c]);
+    }
+  const float alpha = (KIND == KC_OUT_PRELU) ? a.alpha[0] : 0.0f;
+  // ---- phase 1: per-channel sums over this CTA's rows; zhat replaces z in shared memory ---------------------------
+  // A thread owns at most two float4 columns of a channel (host: n4 <= 2 * threads).  The dy vectors of channel c + 1 are
+  // requested before channel c is processed, and those of channel 0 before the wait for the bulk copy of z.  (A generic
+  // prefetch queue over any number of columns executed 30 % more instructions and was slower.)
+  const int n4 = cnt >> 2, hw4 = hw >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(a.dy + base);
+  const int i0 = tid, i1 = tid + kBwdThreads;
+  const bool has0 = i0 < n4, has1 = i1 < n4;
+  const float4 zero_f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ga = (has0 && nch > 0) ? ldg4_early(g4 + i0) : zero_f4;
+  float4 gb = (has1 && nch > 0) ? ldg4_early(g4 + i1) : zero_f4;
+#pragma unroll 1
+  for (int c = 0; c < CH; ++c) {
+    float s_dvz = 0.0f, s_dv = 0.0f, s_da = 0.0f;
+    if (c < nch) {                                   // warp-uniform
+      const float4 ca = ga, cb = gb;
+      if (c + 1 < nch) {
+        const float4* gn = g4 + (c + 1) * hw4;
+        if (has0) ga = ldg4_early(gn + i0);
+        if (has1) gb = ldg4_early(gn + i1);
+      }
+      const float mean = stat[c], rstd = stat[CH + c];
       float4* zb = reinterpret_cast<float4*>(zbuf + (size_t)c * cap);
-      const float4* g4 = reinterpret_cast<const float4*>(a.dy + base + (long long)c * hw);
-      for (int i = tid; i < n4; i += kBwdThreads) {
-        float4 zv = zb[i];
-        const float4 gv = __ldg(g4 + i);
-        zv.x = (zv.x - mean[c]) * rstd[c]; zv.y = (zv.y - mean[c]) * rstd[c];
-        zv.z = (zv.z - mean[c]) * rstd[c]; zv.w = (zv.w - mean[c]) * rstd[c];
-        zb[i] = zv;
-        const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      if (cnt > 0) mbar_wait(&bar[c], 0);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float dv = gg[e] * out_act_grad(kind, zz[e], alpha);
-          acc[c] = fmaf(dv, zz[e], acc[c]);
-          acc[8 + c] += dv;
-          if (kind == KC_OUT_PRELU && !(zz[e] > 0.0f)) acc[16 + c] = fmaf(gg[e], zz[e], acc[16 + c]);
+      for (int h = 0; h < 2; ++h) {
+        if (h == 0 ? has0 : has1) {
+          const float4 g = h == 0 ? ca : cb;
+          float4 zv = zb[h == 0 ? i0 : i1];
+          zv.x = (zv.x - mean) * rstd; zv.y = (zv.y - mean) * rstd; zv.z = (zv.z - mean) * rstd; zv.w = (zv.w - mean) * rstd;
+          zb[h == 0 ? i0 : i1] = zv;
+          const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float dv = gg[e] * act_grad_t<KIND>(zz[e], alpha);
+            s_dvz = fmaf(dv, zz[e], s_dvz);
+            s_dv += dv;
+            if (KIND == KC_OUT_PRELU && !(zz[e] > 0.0f)) s_da = fmaf(gg[e], zz[e], s_da);
+          }
         }
       }
     }
-  }
-#pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const float v = kc_warp_sum(acc[i]);
-    if (lane == 0) red[warp][i] = v;
+    s_dvz = kc_warp_sum(s_dvz); s_dv = kc_warp_sum(s_dv);
+    if (KIND == KC_OUT_PRELU) s_da = kc_warp_sum(s_da);
+    if (lane == 0) { red[warp][c] = s_dvz; red[warp][CH + c] = s_dv; red[warp][2 * CH + c] = s_da; }
   }
   __syncthreads();
-  if (tid < 24) {
+  if (tid < 3 * CH) {
     float v = 0.0f;
     for (int w = 0; w < kBwdThreads / 32; ++w) v += red[w][tid];
     part[tid] = v;
@@ -202,45 +234,75 @@ kc_norm_bwd_flat_cluster_kernel(const __grid_constant__ NbfArgs a) {
   __syncthreads();
   cluster_arrive();
   cluster_wait();
-  if (tid < 24) {
+  if (tid < 3 * CH) {
     float v = 0.0f;
     for (uint32_t r = 0; r < cs; ++r) v += dsmem_ld(&part[tid], r);       // rank order: deterministic
-    tot[tid] = v;
-    const int c = tid & 7, which = tid >> 3;
+    red[0][tid] = v;
+    const int c = tid % CH, which = tid / CH;
     if (rank == 0 && c < nch) a.partials[(long long)which * d.n * d.c + n * d.c + c0 + c] = v;
   }
   __syncthreads();
-  cluster_arrive();                  // done with the peers' shared memory
-  // ---- phase 2: dz of 8 channels per position -> one 16-byte bf16 vector of the flat buffer -----------------------
-  float m1[8], m2[8];
-  const float inv_hw = 1.0f / (float)hw;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) { m2[c] = tot[c] * inv_hw; m1[c] = tot[8 + c] * inv_hw; }
-  unsigned char* outp = a.dzf + ((long long)g8 * a.L + (long long)n * a.IMG) * 16;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-  const float* gbase = a.dy + base;
-  for (int p = tid; p < cnt; p += kBwdThreads) {
-    const int yl = p / a.wo, x = p - yl * a.wo;
-    float f[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float v = 0.0f;
-      if (c < nch) {
-        const float zh = zbuf[(size_t)c * cap + p];
-        const float dv = __ldg(gbase + (long long)c * hw + p) * out_act_grad(kind, zh, alpha);
-        v = rstd[c] * (dv - m1[c] - zh * m2[c]);
-      }
-      f[c] = v;
-    }
-    uint4* dst = reinterpret_cast<uint4*>(outp + ((long long)(r0 + yl) * a.P + x) * 16);
-    *dst = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-    if (x == a.wo - 1)
-      for (int gx = 1; gx <= a.P - a.wo; ++gx) dst[gx] = zero4;             // gap column(s) of this row
+  if (tid < CH) {
+    const float inv_hw = 1.0f / (float)hw, rs = stat[CH + tid];
+    coef[tid] = make_float4(rs, rs * red[0][CH + tid] * inv_hw, rs * red[0][tid] * inv_hw, 0.0f);
   }
-  if (r1 == a.ho && r0 < a.ho) {     // the CTA that owns the last row also zero-fills the gap rows of the image
-    const int q0 = a.ho * a.P, q1 = a.IMG;
+  __syncthreads();
+  cluster_arrive();                  // done with the peers' shared memory
+  // ---- phase 2: four consecutive positions x CH channels per thread -> four (half) vectors of the flat buffer --------
+  //   dz = rstd * (dv - mean(dv) - zhat * mean(dv * zhat)) = coef.x * dv - (coef.y + zhat * coef.z)
+  // dy is read again (L2 hits: this CTA streamed the same bytes in phase 1).  Channels are taken two at a time and packed
+  // straight into the output words (bf16x2 = channels 2k, 2k+1); the dy vectors of the next channel pair are requested
+  // before the current pair is evaluated.
+  unsigned char* outp = a.dzf + ((long long)g8 * a.L + (long long)n * a.IMG) * 16 + half * (2 * CH);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < n4; i += kBwdThreads) {
+    uint32_t o[4][CH / 2];
+    float4 ga = (FULL || 0 < nch) ? ldg4_early(g4 + i) : zero_f4;
+    float4 gb = (FULL || 1 < nch) ? ldg4_early(g4 + hw4 + i) : zero_f4;
+#pragma unroll
+    for (int k = 0; k < CH / 2; ++k) {
+      const float4 gpair[2] = {ga, gb};
+      if (k + 1 < CH / 2) {
+        ga = (FULL || 2 * k + 2 < nch) ? ldg4_early(g4 + (2 * k + 2) * hw4 + i) : zero_f4;
+        gb = (FULL || 2 * k + 3 < nch) ? ldg4_early(g4 + (2 * k + 3) * hw4 + i) : zero_f4;
+      }
+      float f[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = 2 * k + q;
+        if (FULL || c < nch) {
+          const float4 g = gpair[q];
+          const float4 zv = *(reinterpret_cast<const float4*>(zbuf + (size_t)c * cap) + i);
+          const float4 kf = coef[c];
+          const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[q][e] = fmaf(kf.x, gg[e] * act_grad_t<KIND>(zz[e], alpha), -fmaf(zz[e], kf.z, kf.y));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[q][e] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e][k] = pack_bf16(f[0][e], f[1][e]);
+    }
+    const int p = i * 4;
+    int yl = p / a.wo, x = p - yl * a.wo;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      unsigned char* dst = outp + ((long long)(r0 + yl) * a.P + x) * 16;
+      if (CH == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(o[e][0], o[e][1], o[e][2 % (CH / 2)], o[e][3 % (CH / 2)]);
+      else *reinterpret_cast<uint2*>(dst) = make_uint2(o[e][0], o[e][1]);
+      if (++x == a.wo) {
+        if (half == 0)
+          for (int gx = 1; gx <= a.P - a.wo; ++gx) *reinterpret_cast<uint4*>(dst + gx * 16 - half * (2 * CH)) = zero4;   // gap column(s)
+        x = 0; ++yl;
+      }
+    }
+  }
+  if (half == 0 && r1 == a.ho && r0 < a.ho) {     // the CTA that owns the last row also zero-fills the gap rows of the image
+    const int q0r = a.ho * a.P, q1r = a.IMG;
     uint4* dst = reinterpret_cast<uint4*>(outp);
-    for (int q = q0 + tid; q < q1; q += kBwdThreads) dst[q] = zero4;
+    for (int q = q0r + tid; q < q1r; q += kBwdThreads) dst[q] = zero4;
   }
   cluster_wait();
 }
@@ -274,6 +336,45 @@ cudaError_t launch_cluster(Kernel kernel, unsigned grid, unsigned threads, size_
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+template <int T, int CH, int KIND>
+cudaError_t launch_nbf(const NbfArgs& a, unsigned grid, size_t smem, int cs, bool full, cudaStream_t st) {
+  cudaError_t e;
+  if (full) {
+    e = cudaFuncSetAttribute(kc_norm_bwd_flat_cluster_kernel<T, CH, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_cluster(kc_norm_bwd_flat_cluster_kernel<T, CH, KIND, true>, grid, T, smem, cs, st, a);
+  }
+  e = cudaFuncSetAttribute(kc_norm_bwd_flat_cluster_kernel<T, CH, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return launch_cluster(kc_norm_bwd_flat_cluster_kernel<T, CH, KIND, false>, grid, T, smem, cs, st, a);
+}
+
+template <int T, int CH>
+cudaError_t launch_nbf_kind(const NbfArgs& a, unsigned grid, size_t smem, int cs, bool full, cudaStream_t st) {
+  if (a.d.out_act == KC_OUT_PRELU) return launch_nbf<T, CH, KC_OUT_PRELU>(a, grid, smem, cs, full, st);
+  if (a.d.out_act == KC_OUT_SILU) return launch_nbf<T, CH, KC_OUT_SILU>(a, grid, smem, cs, full, st);
+  return launch_nbf<T, CH, KC_OUT_NONE>(a, grid, smem, cs, full, st);
+}
+
+// Launch shape of the fused backward: cluster size, rows per CTA, threads.  The resident chunk (8 channels x rows x wo floats) is
+// kept <= 52 KB when a cluster of <= 8 CTAs allows it (four 256-thread CTAs per SM; 64-thread CTAs for the 14x14 planes), else
+// <= 200 KB with one 1024-thread CTA per SM (the 224x224 planes).  A thread owns at most two float4 columns per channel.
+// (Splitting the 8 channels over two CTAs - 100 KB chunks, two CTAs per SM, 8-byte half-vector stores - measured 6 % slower.)
+struct NbfPlan { int ch, cs, rows, threads; size_t smem; };
+bool plan_nbf(int ho, int wo, NbfPlan* pl) {
+  for (int pass = 0; pass < 2; ++pass)
+    for (int cs = 1; cs <= 8; cs *= 2) {
+      const int rows = (ho + cs - 1) / cs;
+      const size_t smem = (size_t)rows * wo * 32;
+      if (smem > (pass == 0 ? (size_t)52 * 1024 : kSmemMax)) continue;
+      const int threads = pass == 1 ? kBwdThreadsBig : rows * wo <= 4 * kBwdThreadsTiny ? kBwdThreadsTiny : kBwdThreadsSmall;
+      if (rows * wo > 8 * threads) continue;
+      *pl = {8, cs, rows, threads, smem};
+      return true;
+    }
+  return false;
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -282,6 +383,8 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 // the error string semantics of the caller) when it does not: kc_norm_act_fwd then runs the generic two-pass kernel.
 int kc_instnorm_fwd_cluster(const kc_norm_desc* d, const float* z, const float* gamma, const float* beta, const float* alpha,
                             float* y, float* mean, float* rstd, void* stream) {
+  const char* env = getenv("KANCONV_NORM_CLUSTER");          // debug switch: 0 = always the generic two-pass kernel
+  if (env != nullptr && env[0] == '0') return KC_ERR_UNSUPPORTED;
   if (d->norm != KC_NORM_INSTANCE || d->hw < 3136 || (d->hw & 3) || (d->batch_stride & 3) || !aligned16(z) || !aligned16(y))
     return KC_ERR_UNSUPPORTED;
   int chunk4 = 0;
@@ -310,10 +413,9 @@ extern "C" int kc_norm_bwd_dz_flat_supported(const kc_desc* conv, const kc_norm_
   if (conv->wo > P || conv->ho * P > IMG) return 0;
   const int hw = d->hw;
   if ((hw & 3) || (d->batch_stride & 3)) return 0;
-  int rows = 0;
-  const int cs = pick_cluster(conv->ho, (size_t)conv->wo * 32, 52 * 1024, kSmemMax, &rows);
-  if (cs == 0) return 0;
-  if (cs > 1 && ((rows * conv->wo) & 3)) return 0;          // every CTA's chunk must start 16-byte aligned
+  NbfPlan pl;
+  if (!plan_nbf(conv->ho, conv->wo, &pl)) return 0;
+  if (pl.cs > 1 && ((pl.rows * conv->wo) & 3)) return 0;    // every CTA's chunk must start 16-byte aligned
   return 1;
 }
 
@@ -330,13 +432,16 @@ extern "C" int kc_norm_bwd_dz_flat(const kc_desc* conv, const kc_norm_desc* d, c
   int rc = kc_tc_flat_layout(conv, &a.P, &a.IMG, &a.L, &cq);
   if (rc != KC_OK) return rc;
   a.groups8 = cq / 8;
-  const int cs = pick_cluster(conv->ho, (size_t)conv->wo * 32, 52 * 1024, kSmemMax, &a.rows);
+  NbfPlan pl;
+  plan_nbf(conv->ho, conv->wo, &pl);
+  a.rows = pl.rows;
   a.dy = dy; a.z = z; a.mean = mean; a.rstd = rstd; a.alpha = alpha; a.dzf = (unsigned char*)dz_flat; a.partials = partials;
-  const size_t smem = (size_t)a.rows * a.wo * 32;
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_norm_bwd_flat_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long grid = (long long)d->n * a.groups8 * cs;
+  const long long grid = (long long)d->n * a.groups8 * (8 / pl.ch) * pl.cs;
   if (grid > 0x7fffffffLL) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_norm_bwd_dz_flat: grid too large");
-  cudaError_t e = launch_cluster(kc_norm_bwd_flat_cluster_kernel, (unsigned)grid, kBwdThreads, smem, cs, (cudaStream_t)stream, a);
+  const bool full = (d->c % 8) == 0 && a.groups8 * 8 == d->c;          // every 8-channel group of the flat buffer is complete
+  cudaError_t e = pl.threads == kBwdThreadsBig ? launch_nbf_kind<kBwdThreadsBig, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream)
+                  : pl.threads == kBwdThreadsTiny ? launch_nbf_kind<kBwdThreadsTiny, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream)
+                                                  : launch_nbf_kind<kBwdThreadsSmall, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream);
   kc_count_launch();
   if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "launch of kc_norm_bwd_flat_cluster_kernel failed: %s", cudaGetErrorString(e));
   if (dalpha != nullptr) return kc_norm_partials_to_params(d, partials, nullptr, nullptr, dalpha, stream);

@@ -181,6 +181,12 @@ __device__ __forceinline__ float ldg_early(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ float4 ldg4_early(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE, sm_100 version field = 1 (cute::UMMA::SmemDescriptor bit layout).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -16,7 +16,7 @@ ORACLE_CTORS = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram
 
 
 # whole-model fixtures (make_model_golden.py): a different record layout
-MODEL_FIXTURES = {"mbv2_fastkan_forward", "vgg16_kansmall_forward", "vgg11_forward", "kan_mlp_forward"}
+MODEL_FIXTURES = {"mbv2_fastkan_forward", "vgg16_kansmall_forward", "vgg16_kansmall_128_forward", "vgg11_forward", "kan_mlp_forward"}
 
 
 def golden_names():

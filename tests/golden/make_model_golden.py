@@ -80,13 +80,13 @@ from models.kans import MLP_KAN_FACTORY as REF_MLP  # noqa: E402
 ref_vgg.cfgs["VGG11"] = [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512]
 
 
-def run_vgg(arch, dtype, batch):
+def run_vgg(arch, dtype, batch, size=32):
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         m = vggkan(3, 10, arch=arch, classifier_type="Linear", dropout_linear=0.0)
     m = m.to(dtype).train()
     torch.manual_seed(1)
-    x = torch.randn(batch, 3, 32, 32)
+    x = torch.randn(batch, 3, size, size)
     t = torch.arange(batch) % 10
     y = m(x.to(dtype))
     loss = nn.functional.cross_entropy(y, t)
@@ -94,14 +94,17 @@ def run_vgg(arch, dtype, batch):
     return x, t, y.detach(), float(loss.detach()), {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
 
 
-def vgg_fixture(arch, fname, batch, full_keys):
-    x, t, y64, l64, g64 = run_vgg(arch, torch.float64, batch)
-    _, _, y32, l32, g32 = run_vgg(arch, torch.float32, batch)
+def vgg_fixture(arch, fname, batch, full_keys, size=32):
+    x, t, y64, l64, g64 = run_vgg(arch, torch.float64, batch, size)
+    _, _, y32, l32, g32 = run_vgg(arch, torch.float32, batch, size)
     summ = {k: [float(v.sum()), float(v.norm())] for k, v in g64.items()}
     summ32 = {k: [float(v.double().sum()), float(v.double().norm())] for k, v in g32.items()}
+    # the reference's own fp32-vs-fp64 deviation of every gradient, max|a-b| / max|b|: the yardstick for an fp32 implementation
+    noise = {k: float((g32[k].double() - v).abs().max() / v.abs().max().clamp_min(1e-300)) for k, v in g64.items()}
     np.savez_compressed(os.path.join(HERE, fname), x=x.numpy(), t=t.numpy(), y=y64.numpy(), loss=l64, y32=y32.numpy(), loss32=l32,
                         gradsum=np.frombuffer(json.dumps(summ).encode(), dtype=np.uint8),
                         gradsum32=np.frombuffer(json.dumps(summ32).encode(), dtype=np.uint8),
+                        gradnoise32=np.frombuffer(json.dumps(noise).encode(), dtype=np.uint8),
                         **{"grad/" + k: g64[k].numpy() for k in full_keys}, **{"grad32/" + k: g32[k].numpy() for k in full_keys})
     print(fname, "y", tuple(y64.shape), "loss", l64, "ref fp32 self-noise y", float((y32.double() - y64).abs().max() / y64.abs().max()),
           "params", len(g64))
@@ -115,6 +118,12 @@ if not sys.argv[1:] or "vgg" in sys.argv[1:]:
     vgg_fixture("VGG11", "vgg11_forward.npz", 2,
                 ["features.0.spline_conv.0.weight", "features.0.base_conv.0.weight", "features.11.prelus.0.weight",
                  "classifier.1.weight", "classifier.1.bias"])
+    # the same KAN-VGG16_kansmall at 128x128 (tail maps 8x8 instead of 2x2): InstanceNorm over 4 values makes the 32x32 case
+    # ill-conditioned (rounding is amplified ~700x from input to logits); this one is the model-level
+    # yardstick of the BF16 tensor-core path
+    vgg_fixture("VGG16_kansmall", "vgg16_kansmall_128_forward.npz", 2,
+                ["features.0.spline_conv.0.weight", "features.16.base_conv.0.weight", "classifier.1.weight", "classifier.1.bias"],
+                size=128)
 
 # KAN MLP head (models/kans.py:300-327 through MLP_KAN_FACTORY['KAN']): [20, 16, 10], no dropout
 if not sys.argv[1:] or "mlp" in sys.argv[1:]:

@@ -649,3 +649,79 @@ def test_packed_weights_are_cached_per_parameter_version():
     with torch.no_grad():
         assert torch.equal(ref(x), y3)                           # the cached image was refreshed, not reused stale
     del m, ref
+
+
+@pytest.mark.parametrize("n,c,h,w", [(3, 8, 224, 224), (2, 24, 112, 112), (2, 40, 56, 56), (2, 16, 64, 100), (1, 8, 300, 200)])
+def test_cluster_resident_instance_norm_forward(n, c, h, w):
+    """kc_instnorm_fwd_cluster_kernel (plane chunks resident in shared memory, statistics combined across the thread-block
+    cluster through DSMEM) against torch's instance_norm + prelu, FP32 tolerance; statistics are returned too."""
+    import torch.nn.functional as F
+    from kanconv_b200 import functional as KF
+    torch.manual_seed(0)
+    z = (torch.randn(n, c, h, w, device="cuda") * 3.0 + 1.5)
+    alpha = torch.tensor([0.25], device="cuda")
+    spec = KF.NormSpec(L.NORM_INSTANCE, L.OUT_PRELU, 1, False, 1e-5)
+    y, mean, rstd = KF.norm_act(spec, z, alphas=[alpha])
+    ref = F.prelu(F.instance_norm(z.double(), eps=1e-5), alpha.double())
+    assert rel_err(y, ref) < FP32_TOL
+    assert rel_err(mean.flatten(), z.double().mean((2, 3)).flatten()) < FP32_TOL
+    assert rel_err(rstd.flatten(), (z.double().var((2, 3), unbiased=False) + 1e-5).rsqrt().flatten()) < FP32_TOL
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,pad,kind", [(2, 16, 16, 224, 224, 1, "kan"), (2, 16, 24, 112, 112, 1, "kan"),
+                                                   (2, 32, 40, 56, 56, 1, "kan"), (3, 16, 20, 28, 28, 1, "kan"),
+                                                   (2, 16, 16, 14, 14, 1, "kan"), (2, 8, 12, 30, 44, 0, "kan"),
+                                                   (2, 16, 24, 20, 28, 1, "cheby"), (2, 16, 24, 20, 28, 1, "gram")])
+def test_fused_norm_backward_matches_two_step_path(n, cin, cout, h, w, pad, kind):
+    """kc_norm_bwd_dz_flat (norm backward writing the bf16 flat dz of the tensor-core kernels directly; planes split over a
+    cluster, zhat resident in shared memory) against kc_norm_act_bwd + kc_tc_dz_flat: same dX / dW / d alpha up to the bf16
+    rounding of dz (the two paths sum the plane statistics in a different order, so dz can differ by one bf16 ulp)."""
+    from kanconv_b200 import functional as KF
+    torch.manual_seed(0)
+    if kind == "kan":
+        m = K.KANConv2DLayer(cin, cout, 3, padding=pad, base_activation=nn.SiLU).cuda()
+    elif kind == "cheby":
+        m = K.ChebyKANConv2DLayer(cin, cout, 3, padding=pad).cuda()
+    else:
+        m = K.GRAMKANConv2DLayer(cin, cout, 3, padding=pad).cuda()
+    m.precision = "bf16"
+    x = torch.randn(n, cin, h, w, device="cuda")
+    ho, wo = h + 2 * pad - 2, w + 2 * pad - 2
+    g = torch.randn(n, cout, ho, wo, device="cuda")
+    res = {}
+    for fused in (True, False):
+        KF._FUSED_NORM_BWD = fused
+        try:
+            KF.profile_begin()
+            res[fused] = run_fwd_bwd(m, x, g)
+            names = set(KF.profile_end())
+        finally:
+            KF._FUSED_NORM_BWD = True
+        assert ("kc_norm_bwd_flat_kernel" in names) == fused and ("kc_dz_flat_kernel" in names) == (not fused), names
+    (y1, dx1, g1), (y0, dx0, g0) = res[True], res[False]
+    assert torch.equal(y1, y0)
+    errs = {"dx": rel_err(dx1, dx0)}
+    for k in g0:
+        errs[k] = rel_err(g1[k], g0[k])
+    print(kind, (n, cin, cout, h, w), {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 4e-3, errs
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 64, 64, 8, 8), (2, 512, 512, 2, 2), (2, 32, 48, 16, 16), (2, 256, 512, 4, 4), (3, 20, 12, 9, 7)])
+def test_fp32_path_at_model_channel_counts(n, cin, cout, h, w):
+    """The FP32 CUDA-core kernels at the channel counts of the models (the reference-generated goldens have <= 8 channels):
+    whole layer y / dX / every gradient against the fp64 oracle, 1e-5."""
+    ora, mod = _oracle_and_module("kan", dict(input_dim=cin, output_dim=cout, kernel_size=3, padding=1, base_activation="silu"),
+                                  dict(input_dim=cin, output_dim=cout, kernel_size=3, padding=1, base_activation=nn.SiLU))
+    mod.precision = "fp32"
+    torch.manual_seed(11)
+    x = torch.randn(n, cin, h, w)
+    g = torch.randn(n, cout, h, w)
+    yo, dxo, go = run_fwd_bwd(ora, x.double(), g.double())
+    y, dx, gr = run_fwd_bwd(mod, x.cuda(), g.cuda())
+    errs = {"y": rel_err(y, yo), "dx": rel_err(dx, dxo)}
+    for k in go:
+        errs[k] = rel_err(gr[k], go[k])
+    print((n, cin, cout, h, w), {k: f"{v:.2e}" for k, v in errs.items()})
+    # 2x2 maps: InstanceNorm over four values amplifies the fp32 rounding of z (K = 41 472 products per output) several times
+    assert max(errs.values()) < (2e-5 if h * w <= 4 else FP32_TOL), errs

@@ -125,7 +125,8 @@ def _load_model_fixture(name):
     return z, json.loads(bytes(z["gradsum"]).decode()) if "gradsum" in z.files else None
 
 
-@pytest.mark.parametrize("arch,fixture", [("VGG16_kansmall", "vgg16_kansmall_forward"), ("VGG11", "vgg11_forward")])
+@pytest.mark.parametrize("arch,fixture", [("VGG16_kansmall", "vgg16_kansmall_forward"), ("VGG11", "vgg11_forward"),
+                                          ("VGG16_kansmall", "vgg16_kansmall_128_forward")])
 def test_oracle_vgg_matches_reference_model(arch, fixture):
     """OracleVGG (the CPU baseline of bench.py and the checker of the GPU model tests) against the reference's own vggkan():
     same seed -> same weights (the oracle modules consume the RNG like the reference ctor), fp64 logits, loss and EVERY
@@ -173,3 +174,30 @@ def test_nonfinite_inputs_propagate_like_the_reference():
         nan_img = torch.isnan(gd.y64).flatten(1).all(1)
         assert nan_img.nonzero().flatten().tolist() == bad_images, name
         assert not torch.isnan(gd.y64[~nan_img]).any()
+
+
+def test_model_gradients_are_discontinuous_at_fp32_resolution():
+    """Why the model-level GPU tests cannot gate gradients in max-norm: KAN-VGG is PReLU + MaxPool, its loss is only piecewise
+    smooth, and at fp32 resolution one forward pass lands on the other side of a kink or pooling tie about once.  Here the
+    reference's own arithmetic (the oracle, pinned to the reference at 1e-10) is run in fp32 on an input moved by 1e-6
+    (relative): single gradient tensors jump by more than 1e-2 relative to the fp64 gradient, although the UNperturbed fp32 run
+    is within ~1e-4 of it and the logits move by ~1e-5 only."""
+    z, _ = _load_model_fixture("vgg16_kansmall_128_forward")
+    x, t = torch.from_numpy(z["x"]), torch.from_numpy(z["t"])
+
+    def grads(dtype, xin):
+        torch.manual_seed(0)
+        m = O.OracleVGG(3, 10, arch="VGG16_kansmall", dropout_linear=0.0).to(dtype).train()
+        y = m(xin.to(dtype))
+        torch.nn.functional.cross_entropy(y, t).backward()
+        return y.detach().double(), {k: p.grad.double() for k, p in m.named_parameters() if p.grad.numel() > 1}
+
+    y64, g64 = grads(torch.float64, x)
+    worst = 0.0
+    for seed in (101, 102):
+        torch.manual_seed(seed)
+        y32, g32 = grads(torch.float32, x * (1 + 1e-6 * torch.randn_like(x)))
+        assert rel_err(y32, y64) < 1e-3                                  # the forward pass is stable ...
+        worst = max(worst, max(rel_err(g32[k], g64[k]) for k in g64))
+    print(f"worst max-norm gradient deviation of a perturbed fp32 run: {worst:.2e}")
+    assert worst > 1e-2                                                  # ... individual gradient entries are not

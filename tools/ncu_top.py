@@ -12,7 +12,11 @@ rows = list(csv.reader(out.splitlines()))
 import os
 his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 which = int(os.environ.get("KERNEL_INDEX", "0"))
+if os.environ.get("KERNEL_NAME"):      # first section whose "Kernel Name" line contains the substring
+    want = os.environ["KERNEL_NAME"]
+    which = next(k for k, i in enumerate(his) if i > 0 and rows[i - 1] and rows[i - 1][0] == "Kernel Name" and want in rows[i - 1][1])
 hi = his[which]
+print("kernel:", rows[hi - 1][1][:100] if hi > 0 else "?")
 end = his[which + 1] if which + 1 < len(his) else len(rows)
 hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}

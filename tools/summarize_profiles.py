@@ -1,8 +1,12 @@
-"""Turn the raw ncu outputs of tools/ncu_round.sh (gpurun_out/) into the committed summaries under profiles/:
-r1_ncu_launches_b16.csv (copied), r1_traffic_b64.json and the tables of r1_ncu_summary.md (printed to stdout as markdown)."""
+"""Turn the raw ncu outputs of tools/ncu_round.sh (gpurun_out/<round>/) into the committed summaries under profiles/:
+<round>_ncu_launches_b16.csv (copied), <round>_traffic_b64.json (with the hash of the CUDA sources the capture was taken with; bench.py
+refuses a capture of other kernels) and the tables of <round>_ncu_summary.md (printed to stdout as markdown).
+usage: python tools/summarize_profiles.py [round tag, default r2]"""
 import collections, csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+sys.path.insert(0, ROOT)
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
+OUT, PROF = os.path.join(ROOT, "gpurun_out", TAG), os.path.join(ROOT, "profiles")
 
 
 def rows_of(path):
@@ -17,8 +21,8 @@ def short(n):
     return n.replace("kc_tc_kernel<0>", "kc_tc_kernel<fwd>").replace("kc_tc_kernel<1>", "kc_tc_kernel<dgrad>")[:80]
 
 
-shutil.copy(os.path.join(OUT, "r1_launches.csv"), os.path.join(PROF, "r1_ncu_launches_b16.csv"))
-hdr, col, data = rows_of(os.path.join(PROF, "r1_ncu_launches_b16.csv"))
+shutil.copy(os.path.join(OUT, "launches.csv"), os.path.join(PROF, TAG + "_ncu_launches_b16.csv"))
+hdr, col, data = rows_of(os.path.join(PROF, TAG + "_ncu_launches_b16.csv"))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in data:
     v = float(r[col["Metric Value"]].replace(",", "")); u = r[col["Metric Unit"]]
@@ -33,7 +37,7 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {100 * v[1] / tot:.1f} % | {v[0]} | {v[1] / v[0]:.1f} | `{k}` |")
 print(f"\nkernels of this library: {100 * mine / tot:.1f} % of device time\n")
 
-hdr, col, data = rows_of(os.path.join(OUT, "r1_traffic_b64.csv"))
+hdr, col, data = rows_of(os.path.join(OUT, "traffic_b64.csv"))
 launch = collections.OrderedDict()
 scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 for r in data:
@@ -52,20 +56,23 @@ for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
               "dram_bytes_per_launch": round((a["rd"] + a["wr"]) / a["n"])}
     o = out[n]
     print(f"| `{n}` | {o['launches_per_step']:.0f} | {o['ms_per_step_under_ncu']:.2f} | {o['dram_read_bytes_per_step'] / 1e9:.2f} | {o['dram_write_bytes_per_step'] / 1e9:.2f} |")
-json.dump({"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:kc_, "
+from kanconv_b200 import build as KB
+srchash = open(os.path.join(OUT, "source_hash.txt")).read().strip() if os.path.exists(os.path.join(OUT, "source_hash.txt")) else KB.source_hash()
+json.dump({"source_hash": srchash, "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:kc_, "
            "python bench.py --steps 1 --warmup 3 --no-cpu-baseline (KAN-VGG16 @224, batch 64)", "steps_captured": nsteps, "kernels": out},
-          open(os.path.join(PROF, "r1_traffic_b64.json"), "w"), indent=1)
+          open(os.path.join(PROF, TAG + "_traffic_b64.json"), "w"), indent=1)
 
-rep = os.path.join(OUT, "r1_tc_kernels.ncu-rep")
-if os.path.exists(rep):
+for rep in sorted(p_ for p_ in os.listdir(OUT) if p_.endswith(".ncu-rep")):
+    title = rep[:-8]
+    rep = os.path.join(OUT, rep)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
     want = ["gpu__time_duration.sum", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
             "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
     names = [short(r[hdr.index("Kernel Name")]) for r in rows[2:]]
-    print("\n## ncu --set full, KANConv2D 256->256, 32x56x56\n\n| metric | " + " | ".join(names) + " |\n|---|" + "---|" * len(names))
+    print(f"\n## ncu --set full, {title}\n\n| metric | " + " | ".join(names) + " |\n|---|" + "---|" * len(names))
     for w in want:
         if w in hdr:
             i = hdr.index(w)
