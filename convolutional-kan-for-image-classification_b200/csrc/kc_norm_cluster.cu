@@ -307,6 +307,232 @@ kc_norm_bwd_flat_cluster_kernel(const __grid_constant__ NbfArgs a) {
   cluster_wait();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small planes (hw <= 1024: the 32x32 .. 2x2 maps of KAN-VGG on CIFAR-sized inputs and the 28x28 / 14x14 tail of VGG16 @224):
+// ONE WARP PER PLANE, the plane lives in registers (<= 8 float4 per lane), statistics by warp shuffles - no shared-memory
+// passes, no block barriers.  A block-per-plane kernel spends its time in three latency-bound passes and two block reductions
+// for a few hundred bytes (measured 0.6-2 TB/s).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWarpPlaneMax4 = 8;        // float4 per lane (instantiated for 2 and 8: the 14x14 / 16x16 planes need two)
+
+template <int VPL>
+__global__ void __launch_bounds__(256, VPL <= 2 ? 8 : 4)
+kc_instnorm_fwd_warp_kernel(const __grid_constant__ kc_norm_desc d, const float* __restrict__ z, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, const float* __restrict__ alpha_p, float* __restrict__ y,
+                            float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long plane = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (plane >= (long long)d.n * d.c) return;
+  const int n = (int)(plane / d.c), ch = (int)(plane % d.c), n4 = d.hw >> 2;
+  const long long off = (long long)n * d.batch_stride + (long long)ch * d.hw;
+  const float4* z4 = reinterpret_cast<const float4*>(z + off);
+  float4 v[VPL];
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < n4 ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mean = kc_warp_sum(s) / (float)d.hw;
+  float m2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    if (lane + 32 * k < n4) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+      m2 = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(e, e, m2))));
+    }
+  }
+  const float rstd = rsqrtf(kc_warp_sum(m2) / (float)d.hw + d.eps);
+  if (lane == 0) { mean_out[plane] = mean; rstd_out[plane] = rstd; }
+  const float g = (d.affine && gamma) ? gamma[ch] : 1.0f;
+  const float b = (d.affine && beta) ? beta[ch] : 0.0f;
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  const float sc = rstd * g, sh0 = b - mean * rstd * g;
+  const int kind = d.out_act;
+  float4* y4 = reinterpret_cast<float4*>(y + off);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < n4) {
+      float4 o;
+      o.x = out_act(kind, fmaf(v[k].x, sc, sh0), alpha); o.y = out_act(kind, fmaf(v[k].y, sc, sh0), alpha);
+      o.z = out_act(kind, fmaf(v[k].z, sc, sh0), alpha); o.w = out_act(kind, fmaf(v[k].w, sc, sh0), alpha);
+      y4[i] = o;
+    }
+  }
+}
+
+// Backward + bf16 flat dz for small planes: one CTA per (image, 8-channel group), warp w = channel w.  dz of the eight
+// channels meets in a shared-memory tile [position][8 x bf16] and leaves as coalesced 16-byte vectors (gap columns / rows
+// zero-filled).  Same sums and the same partials layout as the cluster kernel.
+template <int KIND, int VPL>
+__global__ void __launch_bounds__(256, VPL <= 2 ? 4 : 2)
+kc_norm_bwd_flat_warp_kernel(const __grid_constant__ NbfArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* tile = reinterpret_cast<uint16_t*>(smem_raw);        // [hw][8] bf16
+  const kc_norm_desc& d = a.d;
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  const int n = blockIdx.x / a.groups8, g8 = blockIdx.x % a.groups8;
+  const int ch = g8 * 8 + c, hw = a.ho * a.wo, n4 = hw >> 2;
+  const bool live = ch < d.c;
+  const float alpha = (KIND == KC_OUT_PRELU) ? a.alpha[0] : 0.0f;
+  float4 zv[VPL], gv[VPL];
+  float s_dvz = 0.0f, s_dv = 0.0f, s_da = 0.0f, rstd = 0.0f;
+  if (live) {
+    const long long off = (long long)n * d.batch_stride + (long long)ch * hw;
+    const float4* z4 = reinterpret_cast<const float4*>(a.z + off);
+    const float4* g4 = reinterpret_cast<const float4*>(a.dy + off);
+    const float mean = a.mean[n * d.c + ch];
+    rstd = a.rstd[n * d.c + ch];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      zv[k] = i < n4 ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gv[k] = i < n4 ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (lane + 32 * k < n4) {
+        float zz[4] = {(zv[k].x - mean) * rstd, (zv[k].y - mean) * rstd, (zv[k].z - mean) * rstd, (zv[k].w - mean) * rstd};
+        float gg[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float dv = gg[e] * act_grad_t<KIND>(zz[e], alpha);
+          s_dvz = fmaf(dv, zz[e], s_dvz);
+          s_dv += dv;
+          if (KIND == KC_OUT_PRELU && !(zz[e] > 0.0f)) s_da = fmaf(gg[e], zz[e], s_da);
+          gg[e] = dv;
+        }
+        zv[k] = make_float4(zz[0], zz[1], zz[2], zz[3]);       // zhat
+        gv[k] = make_float4(gg[0], gg[1], gg[2], gg[3]);       // dv
+      }
+    }
+    s_dvz = kc_warp_sum(s_dvz); s_dv = kc_warp_sum(s_dv);
+    if (KIND == KC_OUT_PRELU) s_da = kc_warp_sum(s_da);
+    if (lane == 0) {
+      const long long NP = (long long)d.n * d.c, pl = (long long)n * d.c + ch;
+      a.partials[pl] = s_dvz; a.partials[NP + pl] = s_dv; a.partials[2 * NP + pl] = s_da;
+    }
+  }
+  const float m1 = s_dv / (float)hw, m2 = s_dvz / (float)hw;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < n4) {
+      const float zz[4] = {zv[k].x, zv[k].y, zv[k].z, zv[k].w}, dv[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float dz = live ? rstd * (dv[e] - m1 - zz[e] * m2) : 0.0f;
+        tile[(size_t)(4 * i + e) * 8 + c] = __bfloat16_as_ushort(__float2bfloat16_rn(dz));
+      }
+    }
+  }
+  __syncthreads();
+  unsigned char* outp = a.dzf + ((long long)g8 * a.L + (long long)n * a.IMG) * 16;
+  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int q = threadIdx.x; q < a.IMG; q += 256) {               // every flat position of the image, gaps included
+    const int yy = q / a.P, x = q - yy * a.P;
+    reinterpret_cast<uint4*>(outp)[q] = (yy < a.ho && x < a.wo) ? t4[yy * a.wo + x] : zero4;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Micro planes (hw <= 128: the 8x8 .. 2x2 maps at the tail of KAN-VGG on 32x32 inputs): a plane needs only LPP = 1 .. 32 lanes
+// (one float4 each), so a warp carries 32 / LPP planes (consecutive images of one channel) and the reductions are segmented
+// shuffles.  With a warp (or a block) per 2x2 plane the step of BASELINE config 3 spent 3 of 11 ms in launch-bound norm kernels.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float seg_sum(float v, int lpp) {
+  for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+kc_instnorm_fwd_micro_kernel(const __grid_constant__ kc_norm_desc d, int lpp, const float* __restrict__ z, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, const float* __restrict__ alpha_p, float* __restrict__ y,
+                             float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  // plane index p = n * c + ch; a warp takes 32 / lpp consecutive planes
+  const int lane = threadIdx.x & 31, per_warp = 32 / lpp, i = lane % lpp, n4 = d.hw >> 2;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long plane = warp * per_warp + lane / lpp;
+  const bool live = plane < (long long)d.n * d.c && i < n4;
+  const int n = live ? (int)(plane / d.c) : 0, ch = live ? (int)(plane % d.c) : 0;
+  const long long off = (long long)n * d.batch_stride + (long long)ch * d.hw;
+  const float4 v = live ? __ldg(reinterpret_cast<const float4*>(z + off) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float mean = seg_sum((v.x + v.y) + (v.z + v.w), lpp) / (float)d.hw;
+  const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+  const float rstd = rsqrtf(seg_sum(live ? fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, a3 * a3))) : 0.0f, lpp) / (float)d.hw + d.eps);
+  if (!live) return;
+  if (i == 0) { mean_out[plane] = mean; rstd_out[plane] = rstd; }
+  const float g = (d.affine && gamma) ? gamma[ch] : 1.0f;
+  const float b = (d.affine && beta) ? beta[ch] : 0.0f;
+  const float alpha = (d.out_act == KC_OUT_PRELU) ? alpha_p[0] : 0.0f;
+  const float sc = rstd * g, sh0 = b - mean * rstd * g;
+  const int kind = d.out_act;
+  float4 o;
+  o.x = out_act(kind, fmaf(v.x, sc, sh0), alpha); o.y = out_act(kind, fmaf(v.y, sc, sh0), alpha);
+  o.z = out_act(kind, fmaf(v.z, sc, sh0), alpha); o.w = out_act(kind, fmaf(v.w, sc, sh0), alpha);
+  reinterpret_cast<float4*>(y + off)[i] = o;
+}
+
+// Backward + flat dz for micro planes: CTA = 8 warps = the 8 channels of a group; warp c carries channel c of 32 / lpp
+// consecutive images.  The dz tile [image][position][8 x bf16] is assembled in shared memory and written out as whole images
+// of the flat buffer (gap columns / rows zero-filled).
+template <int KIND>
+__global__ void __launch_bounds__(256)
+kc_norm_bwd_flat_micro_kernel(const __grid_constant__ NbfArgs a, int lpp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* tile = reinterpret_cast<uint16_t*>(smem_raw);        // [images per CTA][hw][8] bf16
+  const kc_norm_desc& d = a.d;
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5, ipc = 32 / lpp, i = lane % lpp, il = lane / lpp;
+  const int nblk = (d.n + ipc - 1) / ipc;                        // image blocks per channel group
+  const int g8 = blockIdx.x / nblk, n0 = (blockIdx.x % nblk) * ipc, n = n0 + il;
+  const int ch = g8 * 8 + c, hw = a.ho * a.wo, n4 = hw >> 2;
+  const bool live = ch < d.c && n < d.n && i < n4;
+  const float alpha = (KIND == KC_OUT_PRELU) ? a.alpha[0] : 0.0f;
+  float zz[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+  float s_dvz = 0.0f, s_dv = 0.0f, s_da = 0.0f, rstd = 0.0f;
+  if (live) {
+    const long long off = (long long)n * d.batch_stride + (long long)ch * hw;
+    const float4 zv = __ldg(reinterpret_cast<const float4*>(a.z + off) + i);
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(a.dy + off) + i);
+    const float mean = a.mean[n * d.c + ch];
+    rstd = a.rstd[n * d.c + ch];
+    zz[0] = (zv.x - mean) * rstd; zz[1] = (zv.y - mean) * rstd; zz[2] = (zv.z - mean) * rstd; zz[3] = (zv.w - mean) * rstd;
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      dv[e] = gg[e] * act_grad_t<KIND>(zz[e], alpha);
+      s_dvz = fmaf(dv[e], zz[e], s_dvz);
+      s_dv += dv[e];
+      if (KIND == KC_OUT_PRELU && !(zz[e] > 0.0f)) s_da = fmaf(gg[e], zz[e], s_da);
+    }
+  }
+  s_dvz = seg_sum(s_dvz, lpp); s_dv = seg_sum(s_dv, lpp); s_da = seg_sum(s_da, lpp);
+  if (live && i == 0) {
+    const long long NP = (long long)d.n * d.c, pl = (long long)n * d.c + ch;
+    a.partials[pl] = s_dvz; a.partials[NP + pl] = s_dv; a.partials[2 * NP + pl] = s_da;
+  }
+  const float m1 = s_dv / (float)hw, m2 = s_dvz / (float)hw;
+  if (i < n4 && n < d.n) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float dz = live ? rstd * (dv[e] - m1 - zz[e] * m2) : 0.0f;
+      tile[((size_t)il * hw + 4 * i + e) * 8 + c] = __bfloat16_as_ushort(__float2bfloat16_rn(dz));
+    }
+  }
+  __syncthreads();
+  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  const int nimg = min(ipc, d.n - n0);
+  uint4* outp = reinterpret_cast<uint4*>(a.dzf + ((long long)g8 * a.L + (long long)n0 * a.IMG) * 16);
+  for (int q = threadIdx.x; q < nimg * a.IMG; q += 256) {        // consecutive images are consecutive in the flat buffer
+    const int im = q / a.IMG, r = q - im * a.IMG, yy = r / a.P, x = r - yy * a.P;
+    outp[q] = (yy < a.ho && x < a.wo) ? t4[(size_t)im * hw + yy * a.wo + x] : zero4;
+  }
+}
+
 int pick_cluster(int units, size_t bytes_per_unit, size_t want, size_t limit, int* per_cta) {
   // smallest cluster size cs in {1, 2, 4, 8} whose per-CTA share of `units` needs <= want bytes; else the smallest that fits limit
   for (int pass = 0; pass < 2; ++pass) {
@@ -385,6 +611,23 @@ int kc_instnorm_fwd_cluster(const kc_norm_desc* d, const float* z, const float* 
                             float* y, float* mean, float* rstd, void* stream) {
   const char* env = getenv("KANCONV_NORM_CLUSTER");          // debug switch: 0 = always the generic two-pass kernel
   if (env != nullptr && env[0] == '0') return KC_ERR_UNSUPPORTED;
+  if (d->norm == KC_NORM_INSTANCE && d->hw <= 128 * kWarpPlaneMax4 && (d->hw & 3) == 0 && (d->batch_stride & 3) == 0 && aligned16(z) &&
+      aligned16(y)) {              // small planes: one warp per plane
+    const long long planes = (long long)d->n * d->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->hw <= 128) {            // micro planes: several planes per warp
+      int lpp = 1;
+      while (lpp * 4 < d->hw) lpp *= 2;
+      const long long warps = (planes + 32 / lpp - 1) / (32 / lpp);
+      kc_instnorm_fwd_micro_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(*d, lpp, z, gamma, beta, alpha, y, mean, rstd);
+    } else if (d->hw <= 256) {
+      kc_instnorm_fwd_warp_kernel<2><<<(unsigned)((planes + 7) / 8), 256, 0, st>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
+    } else {
+      kc_instnorm_fwd_warp_kernel<8><<<(unsigned)((planes + 7) / 8), 256, 0, st>>>(*d, z, gamma, beta, alpha, y, mean, rstd);
+    }
+    KC_LAUNCH_CHECK("kc_instnorm_fwd_warp_kernel");
+    return KC_OK;
+  }
   if (d->norm != KC_NORM_INSTANCE || d->hw < 3136 || (d->hw & 3) || (d->batch_stride & 3) || !aligned16(z) || !aligned16(y))
     return KC_ERR_UNSUPPORTED;
   int chunk4 = 0;
@@ -436,6 +679,29 @@ extern "C" int kc_norm_bwd_dz_flat(const kc_desc* conv, const kc_norm_desc* d, c
   plan_nbf(conv->ho, conv->wo, &pl);
   a.rows = pl.rows;
   a.dy = dy; a.z = z; a.mean = mean; a.rstd = rstd; a.alpha = alpha; a.dzf = (unsigned char*)dz_flat; a.partials = partials;
+  if (d->hw <= 128 * kWarpPlaneMax4) {       // small planes: one warp per channel plane, eight channels per CTA
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->hw <= 128) {            // micro planes: 32 / lpp images per warp
+      int lpp = 1;
+      while (lpp * 4 < d->hw) lpp *= 2;
+      const int ipc = 32 / lpp;
+      const size_t tile = (size_t)ipc * d->hw * 16;
+      const unsigned blocks = (unsigned)((long long)((d->n + ipc - 1) / ipc) * a.groups8);
+      if (d->out_act == KC_OUT_PRELU) kc_norm_bwd_flat_micro_kernel<KC_OUT_PRELU><<<blocks, 256, tile, st>>>(a, lpp);
+      else if (d->out_act == KC_OUT_SILU) kc_norm_bwd_flat_micro_kernel<KC_OUT_SILU><<<blocks, 256, tile, st>>>(a, lpp);
+      else kc_norm_bwd_flat_micro_kernel<KC_OUT_NONE><<<blocks, 256, tile, st>>>(a, lpp);
+    } else {
+      const size_t tile = (size_t)d->hw * 16;
+      const unsigned blocks = (unsigned)((long long)d->n * a.groups8);
+      const bool v2 = d->hw <= 256;
+      if (d->out_act == KC_OUT_PRELU) { if (v2) kc_norm_bwd_flat_warp_kernel<KC_OUT_PRELU, 2><<<blocks, 256, tile, st>>>(a); else kc_norm_bwd_flat_warp_kernel<KC_OUT_PRELU, 8><<<blocks, 256, tile, st>>>(a); }
+      else if (d->out_act == KC_OUT_SILU) { if (v2) kc_norm_bwd_flat_warp_kernel<KC_OUT_SILU, 2><<<blocks, 256, tile, st>>>(a); else kc_norm_bwd_flat_warp_kernel<KC_OUT_SILU, 8><<<blocks, 256, tile, st>>>(a); }
+      else { if (v2) kc_norm_bwd_flat_warp_kernel<KC_OUT_NONE, 2><<<blocks, 256, tile, st>>>(a); else kc_norm_bwd_flat_warp_kernel<KC_OUT_NONE, 8><<<blocks, 256, tile, st>>>(a); }
+    }
+    KC_LAUNCH_CHECK("kc_norm_bwd_flat_warp_kernel");
+    if (dalpha != nullptr) return kc_norm_partials_to_params(d, partials, nullptr, nullptr, dalpha, stream);
+    return KC_OK;
+  }
   const long long grid = (long long)d->n * a.groups8 * (8 / pl.ch) * pl.cs;
   if (grid > 0x7fffffffLL) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_norm_bwd_dz_flat: grid too large");
   const bool full = (d->c % 8) == 0 && a.groups8 * 8 == d->c;          // every 8-channel group of the flat buffer is complete

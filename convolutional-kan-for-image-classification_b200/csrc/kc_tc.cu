@@ -750,6 +750,45 @@ __device__ __forceinline__ bool tc_basis_grad8(const KcBasisCtx& B, float x, flo
   }
 }
 
+// GRAM (gram_kan_layers.py:150-181), registers only: d SiLU(p_j(t)) / dx for j < 8 and, for the d/d beta_weights reduction, the
+// sums over j of g_j * SiLU'(p_j) * dp_j/d beta(n, n+1) for n = 1 .. nb-2 (accumulated into dbl[n - 1] with the coefficient
+// of kc_gram_coef applied).  p_0 = 1, p_1 = t, p_i = t p_{i-1} - beta_{i-1} p_{i-2};  q^n_i = dp_i/d beta_n obeys
+// q_i = t q_{i-1} - [i-1 == n] p_{i-2} - beta_{i-1} q_{i-2}.  Every index is a compile-time constant after unrolling.
+__device__ __forceinline__ void tc_gram_grad8(const KcBasisCtx& B, float x, const uint32_t* r, float (&dphi)[8], float (&dbl)[6],
+                                              bool want_dbeta) {
+  const int nb = B.nb;
+  const bool pre = kc_gram_presquashed(B);
+  const float t = pre ? x : tc_tanh(x), dt = pre ? 1.0f : 1.0f - t * t;
+  float p[8], sgp[8];                      // p_j and SiLU'(p_j)
+  float p0 = 1.0f, p1 = t, d0 = 0.0f, d1 = 1.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sg = tc_sigmoid(p0);
+    p[j] = p0;
+    sgp[j] = sg * fmaf(p0, 1.0f - sg, 1.0f);
+    dphi[j] = j < nb ? sgp[j] * d0 * dt : 0.0f;
+    const float b = B.gbeta[j + 1 < KC_MAX_BASIS ? j + 1 : 0];
+    const float p2 = t * p1 - b * p0, d2 = p1 + t * d1 - b * d0;
+    p0 = p1; p1 = p2; d0 = d1; d1 = d2;
+  }
+  if (!want_dbeta) return;
+#pragma unroll
+  for (int n = 1; n <= 6; ++n) {
+    if (n <= nb - 2) {
+      float q0 = 0.0f, q1 = 0.0f, s = 0.0f;        // q_0 = q_1 = 0
+#pragma unroll
+      for (int i = 2; i < 8; ++i) {
+        if (i < nb) {
+          const float q2 = t * q1 - ((i - 1 == n) ? p[i - 2] : 0.0f) - B.gbeta[i - 1] * q0;
+          s = fmaf(__uint_as_float(r[i]) * sgp[i], q2, s);
+          q0 = q1; q1 = q2;
+        }
+      }
+      dbl[n - 1] = fmaf(s, kc_gram_coef(n), dbl[n - 1]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Persistent GEMM kernel with both operands fed by the TMA engine: one CTA per SM walks a list of (256-position tile, N tile)
 // pairs.  The TMEM holds TWO accumulator sets (2 sub-tiles x <= 128 columns each), so the 16 epilogue warps drain tile t
@@ -757,6 +796,7 @@ __device__ __forceinline__ bool tc_basis_grad8(const KcBasisCtx& B, float x, flo
 //   warps 0-15 epilogue | 16 A loader (strips of a plane-major flat buffer) | 17 weight loader | 18-19 MMA issuers
 // FAM 1: dgrad, closed-form cubic basis   (A = dz_flat, N tile = cpt channels x (nb + base) columns padded to 128)
 // FAM 0: dgrad, RBF / Chebyshev basis
+// FAM 3: dgrad, Gram basis (adds the deterministic d/d beta_weights partial rows: one row per CTA and epilogue warp)
 // FAM 2: forward of a 1x1 convolution from the saved basis rows (A = phi, N tile = output channels): pointwise layers have one
 //        tap of MMA work per K chunk, so evaluating the basis inside the GEMM kernel leaves the tensor cores idle; the basis is
 //        written once by the pre-pass (it is needed for the weight gradient anyway) and this kernel streams it back.
@@ -766,7 +806,7 @@ constexpr int kDgBars = 2 * kMaxA + 2 * kMaxBStages + 4;
 
 template <int FAM>
 __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(const __grid_constant__ TcFwdArgs a) {
-  constexpr bool CUBIC = FAM == 1, FWD = FAM == 2;
+  constexpr bool CUBIC = FAM == 1, FWD = FAM == 2, GRAMF = FAM == 3;
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
@@ -791,7 +831,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   const int wb = d.nb + (has_base ? 1 : 0);
   const int nchunks = FWD ? g.nsc + (has_base ? g.nbc : 0) : g.nbc;
   const long long ntiles = g.mtiles * g.n_ntiles;
-  if (FAM == 0) kc_load_basis_ctx(B, d, a.beta);
+  if (FAM == 0 || GRAMF) kc_load_basis_ctx(B, d, a.beta);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
@@ -1003,6 +1043,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       if (wb > 8) tmem_ld1(taddr + 8u, r + 8); else r[8] = 0u;
     };
     KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);
+    float dbl[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};          // GRAM: this thread's d/d beta(n, n+1) sums, n = 1 .. 6
     float xn[kCh];
     int c0n = 0;
     int offn = nsteps > 0 ? locate(0, c0n) : -1;
@@ -1033,7 +1074,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
           ga = __uint_as_float(r[8]);
         } else {
           float dphi[8];
-          const bool masked = tc_basis_grad8(*B, xc[c4], dphi);
+          bool masked = false;
+          if (GRAMF) tc_gram_grad8(*B, xc[c4], r, dphi, dbl, a.dbeta != nullptr);
+          else masked = tc_basis_grad8(*B, xc[c4], dphi);
           gs = 0.0f;
           ga = __uint_as_float(r[8]);
 #pragma unroll
@@ -1069,6 +1112,15 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      }
+    }
+    if (GRAMF && a.dbeta != nullptr) {
+      // deterministic d/d beta_weights: one partial row per (CTA, epilogue warp); kc_dbeta_reduce_kernel adds them in order
+      const long long row = (long long)blockIdx.x * kDgEpiWarps + warp;
+#pragma unroll
+      for (int nn = 0; nn < KC_MAX_BASIS; ++nn) {
+        const float v = (nn >= 1 && nn <= 6) ? kc_warp_sum(dbl[nn >= 1 && nn <= 6 ? nn - 1 : 0]) : 0.0f;
+        if (lane == nn) a.dbeta[(1 + row) * KC_MAX_BASIS + nn] = (nn >= 1 && nn <= nb - 2) ? v : 0.0f;
       }
     }
     }
@@ -1373,7 +1425,7 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
   // accumulator set, two sets in TMEM (4 x 128 = 512 columns).
   float t0 = 0.0f, inv_h = 0.0f;
   const bool cubic = kc_knots_uniform_cubic(d, &t0, &inv_h);
-  if ((cubic || d->basis == KC_BASIS_RBF || d->basis == KC_BASIS_CHEBY) && d->kh * d->kw <= 64) {
+  if ((cubic || d->basis == KC_BASIS_RBF || d->basis == KC_BASIS_CHEBY || d->basis == KC_BASIS_GRAM) && d->kh * d->kw <= 64) {
     // channels per N tile: cpt * wb <= 128 columns, <= 4 (8) channels per epilogue warp, and the 8-column TMEM read of the
     // last channel must stay inside the tile ((cpt - 1) * wb + 8 <= 128)
     int cpt = 128 / wb;
@@ -1590,8 +1642,13 @@ extern "C" size_t kc_dbeta_floats(const kc_desc* d, int tc) {
   long long rows;
   if (tc) {
     TcGeom g;
-    if (tc_dgrad_geometry(d, &g) != KC_OK || g.persistent) return 0;
-    rows = g.mtiles * g.n_ntiles * 16;
+    if (tc_dgrad_geometry(d, &g) != KC_OK) return 0;
+    if (g.persistent) {           // one row per (CTA, epilogue warp) of the persistent grid
+      const long long ntiles = g.mtiles * g.n_ntiles, sms = kc_sm_count();
+      rows = (ntiles < sms ? ntiles : sms) * kDgEpiWarps;
+    } else {
+      rows = g.mtiles * g.n_ntiles * 16;
+    }
   } else {
     rows = kc_simt_dgrad_blocks(d);
   }
@@ -1729,6 +1786,12 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
     if (g.fast_cubic) {
       KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
       kc_dgrad_persistent_kernel<1><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    } else if (d->basis == KC_BASIS_GRAM) {
+      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      kc_dgrad_persistent_kernel<3><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+      KC_LAUNCH_CHECK("kc_dgrad_persistent_kernel");
+      if (a.dbeta != nullptr) return kc_dbeta_reduce(a.dbeta, (long long)nctas * kDgEpiWarps, stream);
+      return KC_OK;
     } else {
       KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
       kc_dgrad_persistent_kernel<0><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);

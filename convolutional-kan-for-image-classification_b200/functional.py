@@ -127,6 +127,20 @@ def _conv_flops(d) -> float:
     return 2.0 * d.n * d.ho * d.wo * d.cout * d.cin * wb * d.kh * d.kw
 
 
+# Every buffer the binding hands to the library is allocated through these two functions.  tests/test_redzones_gpu.py swaps
+# _ALLOC for an allocator that surrounds each buffer with poisoned guard bands and checks them after the kernels ran
+# (compute-sanitizer is closed on the GPU pool this repo is developed on, so out-of-bounds writes are hunted this way).
+_ALLOC = torch.empty
+
+
+def _empty(*shape, dtype, device):
+    return _ALLOC(*shape, dtype=dtype, device=device)
+
+
+def _empty_like(t: torch.Tensor):
+    return _ALLOC(tuple(t.shape), dtype=t.dtype, device=t.device)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -209,7 +223,7 @@ def _packed_weights(lib, d, which: int, wb, ws, roots, versions, stream, kernel_
     _PACK_STATS["misses"] += 1
     nbytes = lib.kc_tc_bytes(ctypes.byref(d), which)
     packed = hit[1] if (hit is not None and hit[1].numel() == nbytes and hit[1].device == ws.device) else \
-        torch.empty(nbytes, device=ws.device, dtype=torch.uint8)
+        _empty(nbytes, device=ws.device, dtype=torch.uint8)
     L.check(_timed(kernel_name, 0.0, 1.5 * nbytes, lambda: lib.kc_tc_pack_weights(
         ctypes.byref(d), _ptr(wb), _ptr(ws), _ptr(packed) if which == 0 else None, _ptr(packed) if which == 1 else None,
         stream)), "kc_tc_pack_weights")
@@ -223,6 +237,11 @@ def _packed_weights(lib, d, which: int, wb, ws, roots, versions, stream, kernel_
 
 def pack_cache_stats() -> dict:
     return dict(_PACK_STATS, entries=len(_PACKS))
+
+
+def clear_pack_cache() -> None:
+    """Drop every cached weight image (needed only after writing weights through ``.data``, which bypasses version counters)."""
+    _PACKS.clear()
 
 
 def _split_weights(spec: ConvSpec, weights):
@@ -246,7 +265,7 @@ def _conv_fwd(spec: ConvSpec, precision: str, xb, xs, beta, weights, want_phi: b
     roots = [(_root(w_base[g]), _root(w_basis[g])) for g in range(G)]
     with torch.cuda.device(dev):
         stream = _stream(dev)
-        z = torch.empty((n, og * G, ho, wo), device=dev, dtype=torch.float32)
+        z = _empty((n, og * G, ho, wo), device=dev, dtype=torch.float32)
         for g in range(G):
             d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
             xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
@@ -259,7 +278,7 @@ def _conv_fwd(spec: ConvSpec, precision: str, xb, xs, beta, weights, want_phi: b
                 packed = _packed_weights(lib, d, 0, wbg, wsg, roots[g], versions, stream, "kc_pack_fwd_kernel")
                 phi = None
                 if (want_phi or lib.kc_tc_fwd_needs_phi(ctypes.byref(d))) and lib.kc_tc_bytes(ctypes.byref(d), 4) > 0:
-                    phi = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=dev, dtype=torch.uint8)
+                    phi = _empty(lib.kc_tc_bytes(ctypes.byref(d), 4), device=dev, dtype=torch.uint8)
                 phis.append(phi)
                 L.check(_timed("kc_tc_kernel<fwd>", _conv_flops(d), 0.0, lambda: lib.kc_conv_fwd_tc(
                     ctypes.byref(d), _ptr(xbg), _ptr(xsg), _ptr(packed), _ptr(beta), _ptr(zg), _ptr(phi), stream)),
@@ -291,8 +310,8 @@ def _conv_bwd(spec: ConvSpec, used_tc, phis, roots, xb, xs, alias: bool, beta, w
     with torch.cuda.device(dev):
         stream = _stream(dev)
         if run_dgrad:
-            dx_base = torch.empty_like(xb)
-            dx_basis = dx_base if alias else torch.empty_like(xs)
+            dx_base = _empty_like(xb)
+            dx_basis = dx_base if alias else _empty_like(xs)
         for g in range(G):
             d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
             sl = slice(g * cg, (g + 1) * cg)
@@ -305,14 +324,14 @@ def _conv_bwd(spec: ConvSpec, used_tc, phis, roots, xb, xs, alias: bool, beta, w
             if tc_bwd:
                 dzf = dzf_of_group(g, d) if dzf_of_group is not None else None
                 if dzf is None:
-                    dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
+                    dzf = _empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
                     L.check(_timed("kc_dz_flat_kernel", 0.0, 6.0 * dzg.numel(), lambda: lib.kc_tc_dz_flat(
                         ctypes.byref(d), _ptr(dzg), _ptr(dzf), stream)), "kc_tc_dz_flat")
             if run_dgrad:
                 # GRAM: d/d beta_weights of this group (deterministic: per-block partial rows + fixed-order reduction)
                 dbg = None
                 if gram and need_dbeta:
-                    dbg = torch.empty(lib.kc_dbeta_floats(ctypes.byref(d), 1 if tc_bwd else 0), device=dev, dtype=torch.float32)
+                    dbg = _empty(lib.kc_dbeta_floats(ctypes.byref(d), 1 if tc_bwd else 0), device=dev, dtype=torch.float32)
                 if tc_bwd:
                     versions = (None if w_base[g] is None else w_base[g]._version, w_basis[g]._version)
                     packed_d = _packed_weights(lib, d, 1, wbg, wsg, roots[g], versions, stream, "kc_pack_dgrad_kernel")
@@ -328,18 +347,18 @@ def _conv_bwd(spec: ConvSpec, used_tc, phis, roots, xb, xs, alias: bool, beta, w
                     dbeta = part.clone() if dbeta is None else dbeta + part       # groups are added in order
             wi_base, wi_basis = (g, G + g) if spec.has_base else (None, g)
             if (wi_base is not None and need_w[wi_base]) or need_w[wi_basis]:
-                dwb = torch.empty_like(wbg) if wbg is not None else None
-                dwsg = torch.empty_like(wsg)
+                dwb = _empty_like(wbg) if wbg is not None else None
+                dwsg = _empty_like(wsg)
                 if tc_bwd and lib.kc_tc_bytes(ctypes.byref(d), 3) > 0:
                     phi = phis[g]
-                    ws = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=dev, dtype=torch.uint8)
+                    ws = _empty(lib.kc_tc_bytes(ctypes.byref(d), 5 if phi is not None else 3), device=dev, dtype=torch.uint8)
                     L.check(_timed("kc_wgrad_tc_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_tc(
                         ctypes.byref(d), _ptr(dzf), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(phi), _ptr(dwb), _ptr(dwsg), _ptr(ws),
                         stream)), "kc_conv_wgrad_tc")
                     phis[g] = None
                 else:
                     nbytes = lib.kc_wgrad_workspace_bytes(ctypes.byref(d))
-                    ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+                    ws = _empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
                     L.check(_timed("kc_wgrad_simt_kernel", _conv_flops(d), 0.0, lambda: lib.kc_conv_wgrad_f32(
                         ctypes.byref(d), _ptr(dzg), _ptr(xbg), _ptr(xsg), _ptr(beta), _ptr(dwb), _ptr(dwsg), _ptr(ws), stream)),
                         "kc_conv_wgrad_f32")
@@ -421,18 +440,18 @@ def _norm_fwd(spec: NormSpec, z, given_mean, given_rstd, params):
     nstat = {L.NORM_NONE: 1, L.NORM_INSTANCE: n * cg, L.NORM_BATCH: cg}[spec.norm]
     with torch.cuda.device(dev):
         stream = _stream(dev)
-        y = torch.empty_like(z)
+        y = _empty_like(z)
         if given:       # eval-mode BatchNorm: the running statistics are inputs of the kernel (scratch = NULL)
             mean = given_mean.detach().to(torch.float32).reshape(G, cg).contiguous()
             rstd = given_rstd.detach().to(torch.float32).reshape(G, cg).contiguous()
         else:
-            mean = torch.empty((G, nstat), device=dev, dtype=torch.float32)
-            rstd = torch.empty((G, nstat), device=dev, dtype=torch.float32)
+            mean = _empty((G, nstat), device=dev, dtype=torch.float32)
+            rstd = _empty((G, nstat), device=dev, dtype=torch.float32)
         for g in range(G):
             d = _norm_desc(spec, n, cg, hw, c_total)
             scratch = None
             if spec.norm == L.NORM_BATCH and not given:
-                scratch = torch.empty(2 * n * cg, device=dev, dtype=torch.float32)
+                scratch = _empty(2 * n * cg, device=dev, dtype=torch.float32)
             L.check(_timed("kc_instnorm_fwd_kernel", 0.0, 8.0 * n * cg * hw, lambda: lib.kc_norm_act_fwd(
                 ctypes.byref(d), _ptr(z[:, g * cg:(g + 1) * cg]), _ptr(gam[g]), _ptr(bet[g]), _ptr(alp[g]),
                 _ptr(y[:, g * cg:(g + 1) * cg]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(scratch), stream)), "kc_norm_act_fwd")
@@ -451,13 +470,13 @@ def _norm_bwd(spec: NormSpec, z, mean, rstd, params, dy):
     grads: List[Optional[torch.Tensor]] = [None] * len(params)
     with torch.cuda.device(dev):
         stream = _stream(dev)
-        dz = torch.empty_like(z)
+        dz = _empty_like(z)
         for g in range(G):
             d = _norm_desc(spec, n, cg, hw, c_total)
-            partials = torch.empty(3 * n * cg + 2 * cg, device=dev, dtype=torch.float32)
-            dgam = torch.empty_like(gam[g]) if spec.affine else None
-            dbet = torch.empty_like(bet[g]) if spec.affine else None
-            dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
+            partials = _empty(3 * n * cg + 2 * cg, device=dev, dtype=torch.float32)
+            dgam = _empty_like(gam[g]) if spec.affine else None
+            dbet = _empty_like(bet[g]) if spec.affine else None
+            dalp = _empty_like(alp[g]) if alp[g] is not None else None
             sl = slice(g * cg, (g + 1) * cg)
             L.check(_timed("kc_norm_bwd_kernel", 0.0, 12.0 * n * cg * hw, lambda: lib.kc_norm_act_bwd(
                 ctypes.byref(d), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(gam[g]), _ptr(bet[g]),
@@ -548,9 +567,9 @@ class _KanLayerFn(torch.autograd.Function):
             if not lib.kc_norm_bwd_dz_flat_supported(ctypes.byref(d), ctypes.byref(nd)):
                 return None
             sl = slice(g * cg, (g + 1) * cg)
-            dzf = torch.empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
-            partials = torch.empty(3 * n * cg, device=dev, dtype=torch.float32)
-            dalp = torch.empty_like(alp[g]) if alp[g] is not None else None
+            dzf = _empty(lib.kc_tc_bytes(ctypes.byref(d), 2), device=dev, dtype=torch.uint8)
+            partials = _empty(3 * n * cg, device=dev, dtype=torch.float32)
+            dalp = _empty_like(alp[g]) if alp[g] is not None else None
             L.check(_timed("kc_norm_bwd_flat_kernel", 0.0, 10.0 * n * cg * hw, lambda: lib.kc_norm_bwd_dz_flat(
                 ctypes.byref(d), ctypes.byref(nd), _ptr(dy[:, sl]), _ptr(z[:, sl]), _ptr(mean[g]), _ptr(rstd[g]), _ptr(alp[g]),
                 _ptr(dzf), _ptr(dalp), _ptr(partials), _stream(dev))), "kc_norm_bwd_dz_flat")
@@ -606,9 +625,9 @@ class _LayerNormActFn(torch.autograd.Function):
         d = L.KcRowNormDesc()
         d.rows, d.features, d.out_act, d.affine, d.eps = z2.shape[0], feat, out_act, int(gamma is not None), eps
         with torch.cuda.device(dev):
-            y = torch.empty_like(z2)
-            mean = torch.empty(z2.shape[0], device=dev, dtype=torch.float32)
-            rstd = torch.empty_like(mean)
+            y = _empty_like(z2)
+            mean = _empty(z2.shape[0], device=dev, dtype=torch.float32)
+            rstd = _empty_like(mean)
             L.check(lib.kc_layernorm_act_fwd(ctypes.byref(d), _ptr(z2), _ptr(gamma), _ptr(beta), _ptr(alpha), _ptr(y), _ptr(mean),
                                              _ptr(rstd), _stream(dev)), "kc_layernorm_act_fwd")
         ctx.desc_fields = (z2.shape[0], feat, out_act, int(gamma is not None), eps)
@@ -626,11 +645,11 @@ class _LayerNormActFn(torch.autograd.Function):
         d.rows, d.features, d.out_act, d.affine, d.eps = ctx.desc_fields
         dy2 = dy.contiguous().reshape(z2.shape)
         with torch.cuda.device(dev):
-            dz = torch.empty_like(z2)
-            dgam = torch.empty_like(gamma) if gamma is not None else None
-            dbet = torch.empty_like(beta) if beta is not None else None
-            dalp = torch.empty_like(alpha) if alpha is not None else None
-            partials = torch.empty(z2.shape[0], device=dev, dtype=torch.float32)
+            dz = _empty_like(z2)
+            dgam = _empty_like(gamma) if gamma is not None else None
+            dbet = _empty_like(beta) if beta is not None else None
+            dalp = _empty_like(alpha) if alpha is not None else None
+            partials = _empty(z2.shape[0], device=dev, dtype=torch.float32)
             L.check(lib.kc_layernorm_act_bwd(ctypes.byref(d), _ptr(dy2), _ptr(z2), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
                                              _ptr(alpha), _ptr(dz), _ptr(dgam), _ptr(dbet), _ptr(dalp), _ptr(partials),
                                              _stream(dev)), "kc_layernorm_act_bwd")
@@ -657,8 +676,8 @@ class _MaxPoolFn(torch.autograd.Function):
             raise ValueError(f"max_pool2d: input {h}x{w} smaller than the window {k}")
         ho, wo = (h - k) // s + 1, (w - k) // s + 1
         with torch.cuda.device(dev):
-            y = torch.empty((n, c, ho, wo), device=dev, dtype=torch.float32)
-            idx = torch.empty((n, c, ho, wo), device=dev, dtype=torch.uint8)
+            y = _empty((n, c, ho, wo), device=dev, dtype=torch.float32)
+            idx = _empty((n, c, ho, wo), device=dev, dtype=torch.uint8)
             L.check(_timed("kc_maxpool_fwd_kernel", 0.0, 4.0 * x.numel() + 5.0 * y.numel(), lambda: lib.kc_maxpool2d_fwd(
                 _ptr(x), _ptr(y), _ptr(idx), n * c, h, w, k, s, ho, wo, _stream(dev))), "kc_maxpool2d_fwd")
         ctx.save_for_backward(idx)
@@ -674,7 +693,7 @@ class _MaxPoolFn(torch.autograd.Function):
         _same_device("max_pool2d backward", dev, dy)
         dy = dy.contiguous()
         with torch.cuda.device(dev):
-            dx = torch.empty((n, c, h, w), device=dev, dtype=torch.float32)
+            dx = _empty((n, c, h, w), device=dev, dtype=torch.float32)
             L.check(_timed("kc_maxpool_bwd_kernel", 0.0, 4.0 * dx.numel() + 5.0 * dy.numel(), lambda: lib.kc_maxpool2d_bwd(
                 _ptr(dy), _ptr(idx), _ptr(dx), n * c, h, w, k, s, ho, wo, _stream(dev))), "kc_maxpool2d_bwd")
         return dx, None, None

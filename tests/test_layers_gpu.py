@@ -651,10 +651,12 @@ def test_packed_weights_are_cached_per_parameter_version():
     del m, ref
 
 
-@pytest.mark.parametrize("n,c,h,w", [(3, 8, 224, 224), (2, 24, 112, 112), (2, 40, 56, 56), (2, 16, 64, 100), (1, 8, 300, 200)])
+@pytest.mark.parametrize("n,c,h,w", [(3, 8, 224, 224), (2, 24, 112, 112), (2, 40, 56, 56), (2, 16, 64, 100), (1, 8, 300, 200),
+                                     (2, 8, 28, 28), (3, 8, 16, 16), (5, 24, 8, 8), (2, 8, 6, 6), (3, 20, 4, 4), (70, 16, 2, 2)])
 def test_cluster_resident_instance_norm_forward(n, c, h, w):
-    """kc_instnorm_fwd_cluster_kernel (plane chunks resident in shared memory, statistics combined across the thread-block
-    cluster through DSMEM) against torch's instance_norm + prelu, FP32 tolerance; statistics are returned too."""
+    """The InstanceNorm forward kernels by plane size - kc_instnorm_fwd_cluster_kernel (plane chunks resident in shared memory,
+    statistics combined across the thread-block cluster through DSMEM), the warp-per-plane kernel (<= 1024 elements) and the
+    several-planes-per-warp micro kernel (<= 128) - against torch's instance_norm + prelu, FP32 tolerance; statistics too."""
     import torch.nn.functional as F
     from kanconv_b200 import functional as KF
     torch.manual_seed(0)
@@ -671,6 +673,8 @@ def test_cluster_resident_instance_norm_forward(n, c, h, w):
 @pytest.mark.parametrize("n,cin,cout,h,w,pad,kind", [(2, 16, 16, 224, 224, 1, "kan"), (2, 16, 24, 112, 112, 1, "kan"),
                                                    (2, 32, 40, 56, 56, 1, "kan"), (3, 16, 20, 28, 28, 1, "kan"),
                                                    (2, 16, 16, 14, 14, 1, "kan"), (2, 8, 12, 30, 44, 0, "kan"),
+                                                   (2, 16, 16, 16, 16, 1, "kan"), (5, 16, 24, 8, 8, 1, "kan"), (2, 8, 8, 6, 6, 1, "kan"),
+                                                   (3, 16, 20, 4, 4, 1, "kan"), (70, 8, 16, 2, 2, 1, "kan"),
                                                    (2, 16, 24, 20, 28, 1, "cheby"), (2, 16, 24, 20, 28, 1, "gram")])
 def test_fused_norm_backward_matches_two_step_path(n, cin, cout, h, w, pad, kind):
     """kc_norm_bwd_dz_flat (norm backward writing the bf16 flat dz of the tensor-core kernels directly; planes split over a
