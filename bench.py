@@ -402,12 +402,12 @@ def run_b200(args):
         # records the hash of the CUDA sources it was taken with; a capture of other kernels is refused (traffic = null).
         tpath = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
         if args.workload == "kan_vgg16_224" and batch == 64 and os.path.exists(tpath):
-            from kanconv_b200 import build as KB
+            src_hash = K._lib.source_hash()
             with open(tpath) as fh:
                 cap = json.load(fh)
-            if cap.get("source_hash") != KB.source_hash():
+            if cap.get("source_hash") != src_hash:
                 roof["traffic_stale"] = (f"profiles/{TRAFFIC_FILE} was captured with other kernel sources "
-                                         f"({str(cap.get('source_hash'))[:12]} != {KB.source_hash()[:12]}); not used")
+                                         f"({str(cap.get('source_hash'))[:12]} != {src_hash[:12]}); not used")
             else:
                 kern = cap["kernels"]
                 # template instantiations of one kernel are listed separately in the capture (kc_wgrad_tc_kernel<64>, <128>)
@@ -417,7 +417,7 @@ def run_b200(args):
                     tot = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in hits)
                     roof["traffic"] = int(tot / max(nl, 1e-9))
                     roof["traffic_source"] = (f"profiles/{TRAFFIC_FILE} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per "
-                                              f"launch; sources {KB.source_hash()[:12]})")
+                                              f"launch; sources {src_hash[:12]})")
 
     # ---- N > 1: gradient equality of the sharded step (outside the timed region) -----------------------------------
     selfcheck = None

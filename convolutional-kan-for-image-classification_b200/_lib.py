@@ -72,6 +72,11 @@ def library_path():
     return _build.LIB
 
 
+def source_hash():
+    """sha256 of the CUDA sources / headers / flags of the tree (what libkanconv.so must have been built from)."""
+    return _build.source_hash()
+
+
 def load():
     """Load and return the ctypes handle; raises if unavailable.  The library is (re)built first when it is missing, when
     KANCONV_REBUILD=1, or when the sources differ from the ones it was built from (content hash, build._stale); a box without nvcc

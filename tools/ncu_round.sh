@@ -8,7 +8,7 @@ TAG=${1:-r2}
 O=gpurun_out/$TAG
 mkdir -p $O
 set -x
-python -c "import kanconv_b200.build as B; print(B.source_hash())" > $O/source_hash.txt
+python -c "import kanconv_b200 as K; print(K._lib.source_hash())" > $O/source_hash.txt
 CMD="python bench.py --batch 16 --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline"
 $CMD > $O/plain_b16.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 800 --csv --log-file $O/launches.csv $CMD > $O/ncu_launches.log 2>&1

@@ -56,8 +56,9 @@ for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
               "dram_bytes_per_launch": round((a["rd"] + a["wr"]) / a["n"])}
     o = out[n]
     print(f"| `{n}` | {o['launches_per_step']:.0f} | {o['ms_per_step_under_ncu']:.2f} | {o['dram_read_bytes_per_step'] / 1e9:.2f} | {o['dram_write_bytes_per_step'] / 1e9:.2f} |")
-from kanconv_b200 import build as KB
-srchash = open(os.path.join(OUT, "source_hash.txt")).read().strip() if os.path.exists(os.path.join(OUT, "source_hash.txt")) else KB.source_hash()
+import kanconv_b200 as K
+srchash = open(os.path.join(OUT, "source_hash.txt")).read().strip() if os.path.exists(os.path.join(OUT, "source_hash.txt")) else ""
+srchash = srchash or K._lib.source_hash()
 json.dump({"source_hash": srchash, "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:kc_, "
            "python bench.py --steps 1 --warmup 3 --no-cpu-baseline (KAN-VGG16 @224, batch 64)", "steps_captured": nsteps, "kernels": out},
           open(os.path.join(PROF, TAG + "_traffic_b64.json"), "w"), indent=1)
