@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);      // CTA life cycle: entry, producer loop done, accumulators ready, results written
+  tre.stamp();
   const long long m0 = (long long)blockIdx.x * g.mcta;
   const int nt = blockIdx.y;
   const int T = d.kh * d.kw, HW = d.h * d.w;
@@ -408,36 +410,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
           }
         }
       } else {                  // base-activation chunk: k-core = 8 consecutive channels of one position
+        // Four batches (2 planes x 2 row pairs) of 16 loads per thread, software-pipelined: the loads of batch b + 1 are in
+        // flight while batch b is evaluated, so only the first batch's latency is exposed (the chunk used to expose four).
         const int bq = q - g.nsc;
         const int ncols = chunk_cols(g, q);
-        bool waited = false;
-        for (int pl = half; pl < ncols; pl += 2) {
-          const int grp = bq * kPL + pl;
+        auto loadb = [&](int b, float (&xv)[2][8]) {
+          const int pl = half + 2 * (b >> 1), kk = (b & 1) * 2, grp = bq * kPL + pl;
           const float* xc = a.x_base + (long long)grp * 8 * HW;
 #pragma unroll
-          for (int kk = 0; kk < kRB; kk += 2) {
-            float xv[2][8];
+          for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
+            for (int i = 0; i < 8; ++i)
+              xv[k][i] = (pl < ncols && offs[kk + k] >= 0 && grp * 8 + i < cin) ? __ldg(xc + (long long)i * HW + offs[kk + k]) : 0.0f;
+        };
+        auto emitb = [&](int b, const float (&xv)[2][8]) {
+          const int pl = half + 2 * (b >> 1), kk = (b & 1) * 2, grp = bq * kPL + pl;
+          if (pl >= ncols) return;
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                xv[k][i] = (offs[kk + k] >= 0 && grp * 8 + i < cin) ? __ldg(xc + (long long)i * HW + offs[kk + k]) : 0.0f;
-            if (!waited) { mbar_wait(&a_empty[buf], aphase ^ 1); waited = true; trp.stamp(); }
+          for (int k = 0; k < 2; ++k) {
+            if (offs[kk + k] == -2) continue;
+            const int b_row = r0 + (kk + k) * kRowThreads;
+            float f[8];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              if (offs[kk + k] == -2) continue;
-              const int b = r0 + (kk + k) * kRowThreads;
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = (offs[kk + k] >= 0 && grp * 8 + i < cin) ? kc_act(d.act, xv[k][i]) : 0.0f;
-              const uint4 v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-              reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b] = v;
-              if (MODE == kModeFwd && (ownmask >> (kk + k)) & 1u)
-                *reinterpret_cast<uint4*>(phi_row + (long long)(a.phi_base_plane0 + grp) * phi_ps + (kk + k) * (kRowThreads * 16)) = v;
-            }
+            for (int i = 0; i < 8; ++i) f[i] = (offs[kk + k] >= 0 && grp * 8 + i < cin) ? tc_act(d.act, xv[k][i]) : 0.0f;
+            const uint4 v = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            reinterpret_cast<uint4*>(ab + pl * plane_bytes)[b_row] = v;
+            if (MODE == kModeFwd && (ownmask >> (kk + k)) & 1u)
+              *reinterpret_cast<uint4*>(phi_row + (long long)(a.phi_base_plane0 + grp) * phi_ps + (kk + k) * (kRowThreads * 16)) = v;
           }
-        }
-        if (!waited) { mbar_wait(&a_empty[buf], aphase ^ 1); trp.stamp(); }
+        };
+        float xa[2][8], xb[2][8];
+        loadb(0, xa);
+        loadb(1, xb);
+        mbar_wait(&a_empty[buf], aphase ^ 1);
+        trp.stamp();
+        emitb(0, xa);
+        loadb(2, xa);
+        emitb(1, xb);
+        loadb(3, xb);
+        emitb(2, xa);
+        emitb(3, xb);
       }
       trp.stamp();                                   // stores done
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -527,7 +539,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     // ================================ epilogue: TMEM -> registers -> z (fp32 NCHW) =====================
     // All 16 producer warps: warp w reads the TMEM lanes of its hardware quarter (w % 4) and every fourth group of 16
     // columns (w / 4); a store instruction writes one output channel of 32 consecutive positions (128 B).
-    KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);
     tre.stamp();                                     // producer work done
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -578,7 +589,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     const bool gram = d.basis == KC_BASIS_GRAM && a.dbeta != nullptr;
     const int quarter = warp & 3, cgrp = warp >> 2;
     const int c0 = nt * 16 + cgrp * 4;
-    KC_TRACER(tre, g_trace, 3, threadIdx.x == 0);
     tre.stamp();                                     // epilogue entered (producer loop done)
     if (g.fast_cubic && !gram && same_x) {
       // ---- closed-form cubic path (nb == 8): everything stays in registers ----------------------------------------

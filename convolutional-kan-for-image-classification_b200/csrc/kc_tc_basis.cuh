@@ -26,6 +26,14 @@ struct Tracer {
 #define KC_TRACER(name, sym, role, on) Tracer name
 #endif
 
+// Base activation of the tensor-core paths: the result is rounded to bf16 (2^-9), so SiLU uses the fast exponential and
+// reciprocal (5 instructions instead of ~30 for expf + IEEE division; the forward producers evaluate one per input element
+// per N tile).  -Inf gives NaN and NaN propagates, like x * sigmoid(x) in the reference.
+__device__ __forceinline__ float tc_act(int kind, float x) {
+  if (kind == KC_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+  return kc_act(kind, x);
+}
+
 // ---- uniform cubic B-spline, closed form ---------------------------------------------------------
 // The 4 non-zero weights land at j = i0-3 .. i0.  Branch-free: the 4 weights are packed into 64 bits and moved to their
 // slots with clamped PTX shifts (shift amounts >= 64, including "negative" ones, yield 0), so independent evaluations

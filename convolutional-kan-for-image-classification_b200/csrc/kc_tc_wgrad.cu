@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = cb + pl * 8 + i;
-        f[i] = (inside && c < d.cin) ? kc_act(d.act, __ldg(a.x_base + off + (long long)c * HW)) : 0.0f;
+        f[i] = (inside && c < d.cin) ? tc_act(d.act, __ldg(a.x_base + off + (long long)c * HW)) : 0.0f;
       }
       *reinterpret_cast<uint4*>(dst + pl * pstride) =
           make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  KC_TRACER(trl, g_trace_w, 2, threadIdx.x == 0);          // CTA life cycle: entry, set-up done, mainloop done, accumulators ready, end
+  trl.stamp();
   // unit = ((cout tile * nchunks + chunk) * kh + r)
   const int unit = blockIdx.x, split = blockIdx.y;
   const int r = unit % d.kh;
@@ -270,10 +272,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  trl.stamp();
 
   if (warp < 16) {
     // ============================ producers: cp.async copies of the Phi (A) and dz (B) planes ===========================
     wg_produce<KS>(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
+    trl.stamp();
   }
   if (warp >= kMmaWarpW && (warp == kMmaWarpW || d.kw == 3)) {
     // ============================ MMA issuers (whole warp uniform, one elected lane issues) =========================
@@ -322,6 +326,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     // ============================ epilogue: TMEM -> fp32 partial sums in the split workspace ========================
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    trl.stamp();
     const int quarter = warp & 3, cgrp = warp >> 2;
     const int m = quarter * 32 + lane;
     const int ncol16 = d.kw * g.ntile / 16;
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  trl.stamp();
   if (warp == kMmaWarpW) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
@@ -484,11 +490,28 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->tmem_cols = 32;
   while (g->tmem_cols < d->kw * g->ntile) g->tmem_cols *= 2;
   g->nblk = (g->L + g->ks - 1) / g->ks;
-  long long want_split = (3LL * kc_sm_count() + g->units - 1) / g->units;
+  // Split-K count.  Every CTA of a launch does the same work and one CTA fits an SM, so the launch runs in whole waves of
+  // kc_sm_count() CTAs: among the counts that give about 2-4 waves take the one whose last wave is fullest (units * splits
+  // just below a multiple of the SM count; e.g. 15 units: 29 splits = 2.94 waves instead of 30 = 3.04), ties to the fewest
+  // splits (less workspace traffic, fewer prologues / epilogues).
+  const long long sms = kc_sm_count();
   const long long minblk = 1024 / g->ks;                            // at least 1024 positions per CTA
-  long long max_split = g->nblk / minblk > 0 ? g->nblk / minblk : 1;
-  long long ns = want_split < 1 ? 1 : want_split;
-  if (ns > max_split) ns = max_split;
+  const long long max_split = g->nblk / minblk > 0 ? g->nblk / minblk : 1;
+  long long lo = (2 * sms + g->units - 1) / g->units, hi = (4 * sms) / g->units;
+  if (lo < 1) lo = 1;
+  if (hi < lo) hi = lo;
+  if (hi > max_split) hi = max_split;
+  if (lo > hi) lo = hi;
+  long long ns = lo;
+  double best = -1.0;
+  for (long long c = lo; c <= hi; ++c) {
+    const long long bps = (g->nblk + c - 1) / c, real = (g->nblk + bps - 1) / bps;   // splits that actually get blocks
+    const long long ctas = real * g->units, waves = (ctas + sms - 1) / sms;
+    // time ~ waves * blocks per CTA (+ a fixed prologue / epilogue of ~10 block-times per CTA)
+    const double t = (double)waves * (double)(bps + 10);
+    const double score = (double)g->nblk * g->units / (double)sms / t;
+    if (score > best + 1e-9) { best = score; ns = c; }
+  }
   g->blk_per_split = (g->nblk + ns - 1) / ns;
   g->nsplit = (int)((g->nblk + g->blk_per_split - 1) / g->blk_per_split);
   g->ws_bytes = (((size_t)g->nsplit * g->units * d->kw * 128 * g->ntile * sizeof(float)) + 255) / 256 * 256;
