@@ -134,6 +134,91 @@ __global__ void __launch_bounds__(576, 1) kc_mma_rate2_kernel(int N, int mn_majo
   if (warp == 17) tmem_dealloc(tb, 512);
 }
 
+// Debug only: the same measurement for a CTA PAIR (tcgen05.mma.cta_group::2, M = 256: 128 rows of A per CTA, the N rows of B
+// split between the two CTAs).  The leader issues; out[0] = cycles per MMA, out[1] / out[2] = accumulator element (lane 0,
+// column 0) of the leader / the peer (all-ones operands: must equal the accumulated K), out[3] / out[4] = TMEM base addresses.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    kc_mma_rate_2cta_kernel(int N, int mn_major, int iters, int nsub, float* out) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3f803f80u;   // bf16 1.0
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  tc_fence_after();
+  const uint32_t tb = tmem_ptr;
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, N, mn_major, mn_major);
+    const uint32_t au = smem_u32(sm) >> 4, bu = (smem_u32(sm) + 100 * 1024) >> 4;
+    const uint32_t nh = (uint32_t)N / 2;                       // B rows held by each CTA
+    const uint32_t a_pitch = mn_major ? 1168u : 15456u, b_pitch = mn_major ? 1040u : nh * 16u;
+    const uint32_t a_lo_c = (mn_major ? 8u : (a_pitch >> 4)) << 16, b_lo_c = (mn_major ? 8u : (b_pitch >> 4)) << 16;
+    const uint32_t a_hi = (mn_major ? (a_pitch >> 4) : 8u) | (1u << 14), b_hi = (mn_major ? (b_pitch >> 4) : 8u) | (1u << 14);
+    const uint32_t a_step = mn_major ? 16u : (2u * a_pitch) >> 4, b_step = mn_major ? 16u : (2u * b_pitch) >> 4;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one_sync()) {
+        for (int s = 0; s < nsub; ++s) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_c | (au + s * 128 + ks * a_step));
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_c | (bu + ks * b_step));
+            const uint32_t acc = it > 0 || ks > 0 ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tb + s * N), "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
+                         : "memory");
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync())
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)),
+                   "h"((uint16_t)3)
+                   : "memory");
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = (float)(t1 - t0) / (float)(iters * nsub * 2);
+  }
+  if (warp == 0) {
+    if (rank != 0) mbar_wait(&bar, 0);
+    tc_fence_after();
+    uint32_t r[8];
+    tmem_ld8(tb, r);
+    tmem_ld_wait();
+    if (threadIdx.x == 0) { out[1 + rank] = __uint_as_float(r[0]); out[3 + rank] = (float)tb; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+extern "C" int kc_debug_mma_rate_2cta(int N, int mn_major, int iters, int nsub, float* host_out5) {
+  float* dev = nullptr;
+  KC_CUDA_CHECK(cudaMalloc(&dev, 5 * sizeof(float)));
+  KC_CUDA_CHECK(cudaMemset(dev, 0, 5 * sizeof(float)));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  kc_mma_rate_2cta_kernel<<<2, 128, 160 * 1024>>>(N, mn_major, iters, nsub, dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(host_out5, dev, 5 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate_2cta: %s", cudaGetErrorString(e));
+  return KC_OK;
+}
+
 extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, int nsub, int commit_each, int writers, int a_shift_rows, float* cycles) {
   float* dev = nullptr;
   KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));

@@ -12,6 +12,7 @@
 // so the three taps of the filter row are again shifted VIEWS (start row + s) of the same Phi stage.  Each tap has its own TMEM accumulator (kw * N <= 512 columns).  Partial sums go to a
 // workspace [split][unit][s][128][N] and kc_wgrad_tc_reduce_kernel adds the splits in fixed order (deterministic) while
 // scattering into the reference's parameter layouts.
+#include <stdlib.h>
 #include <string.h>
 
 #include "kc_common.cuh"
@@ -26,6 +27,7 @@ constexpr int kThreadsW = 576;       // warps 0-15 producers / epilogue, 16-17 M
 constexpr int kProdW = 512;
 constexpr int kMmaWarpW = 16;
 constexpr int kMaxStagesW = 6;
+constexpr int kNumBarsW = 3 * kMaxStagesW + 1;
 constexpr size_t kSmemLimitW = 227 * 1024;
 
 struct WgGeom {
@@ -36,6 +38,9 @@ struct WgGeom {
   int nsc, nbc, nchunks;        // spline / base chunks (M = 128 rows each)
   int ntile, n_ct;              // cout tile (MMA N), number of cout tiles
   int units;                    // n_ct * nchunks * kh
+  int pair;                     // 1 = CTA pairs (tcgen05 cta_group::2): two units of a cout tile share the dz stage, each CTA loads half
+  int units_ct, upc;            // units per cout tile (nchunks * kh), the same rounded up to an even number (grid.x = n_ct * upc)
+  int bplanes_cta;              // dz planes a CTA loads per stage (bplanes, or bplanes / 2 in a pair)
   int arows, aplane_bytes;      // Phi rows per stage (kKS + kw - 1, padded), plane pitch
   int bplanes, bplane_bytes;
   int stages, stage_bytes, a_bytes;
@@ -144,18 +149,18 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
 
 // Producer role of the wgrad kernel (512 threads): pure 16-byte cp.async copies of the Phi planes (A, with the filter-row
 // shift) and the dz planes (B) straight into the stage; rows are the fastest index so global reads are contiguous.
-// kPrefetchW stages are kept in flight per thread (commit_group / wait_group), then the landed stage is fenced for the
+// stages - 1 stages are kept in flight per thread (commit_group / wait_group), then the landed stage is fenced for the
 // tensor-core proxy and published on its `full` barrier.
-constexpr int kPrefetchW = 3;          // max stages in flight per producer thread
 
-template <int KS>
+template <int KS, bool PAIR>
 __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem, uint64_t* full, uint64_t* empty, int r, int chunk,
-                                           int ct, long long blk0, int nblocks) {
+                                           int ct, long long blk0, int nblocks, uint32_t rank, bool dummy) {
   constexpr int kItems = KS == 64 ? 3 : KS == 96 ? 4 : 5;       // 16-byte vectors per producer thread and operand per stage
   const kc_desc& d = a.d;
   const WgGeom& g = a.g;
   const int tid = threadIdx.x;
-  const int nAitems = g.arows * 16, nBitems = KS * g.bplanes;
+  const int nAitems = g.arows * 16, nBitems = KS * g.bplanes_cta;
+  const int bpl0 = ct * g.bplanes + (PAIR ? (int)rank * g.bplanes_cta : 0);        // first dz plane of this CTA
   const long long qoff = blk0 * KS + (long long)(r - d.pad_h) * g.P - d.pad_w;
   int arow[kItems], brow[kItems];
   uint32_t adst[kItems], bdst[kItems];                      // byte offsets inside a stage, 0xffffffff = no item
@@ -167,63 +172,65 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     arow[k] = it % g.arows;
     const int apl = it / g.arows;
     adst[k] = (it < nAitems) ? (uint32_t)(apl * g.aplane_bytes + arow[k] * 16) : 0xffffffffu;
-    aplane[k] = a.phi + ((long long)(chunk * 16 + (it < nAitems ? apl : 0)) * g.L) * 16;
+    aplane[k] = (it < nAitems && !dummy) ? a.phi + ((long long)(chunk * 16 + apl) * g.L) * 16 : nullptr;
     brow[k] = it % KS;
     const int bpl = it / KS;
-    const bool bok = it < nBitems && (ct * g.bplanes + bpl) * 8 < g.cq;
+    const bool bok = it < nBitems && (bpl0 + bpl) * 8 < g.cq;
     bdst[k] = (it < nBitems) ? (uint32_t)(g.a_bytes + bpl * g.bplane_bytes + brow[k] * 16) : 0xffffffffu;
-    bplane[k] = bok ? a.dzf + ((long long)(ct * g.bplanes + bpl) * g.L) * 16 : nullptr;
+    bplane[k] = bok ? a.dzf + ((long long)(bpl0 + bpl) * g.L) * 16 : nullptr;
   }
   KC_TRACER(trp, g_trace_w, 0, tid == 0);
-  const int depth = g.prefetch;
-  int st = 0, st_done = 0;                        // ring slot being filled / being published (no divisions in the loop)
+  // The arrival on a stage's `full` barrier is attached to the completion of this thread's copies
+  // (cp.async.mbarrier.arrive.noinc), so the thread never waits for its own data and every free stage is in flight.  (The
+  // former commit_group / wait_group / fence.proxy.async sequence stalled each thread until ALL its outstanding copies had
+  // landed: one stage in flight, a full memory latency per 128 positions.)
+  int st = 0;
   uint32_t ph = 1;
-  for (int it = 0; it < nblocks + depth; ++it) {
-    if (it < nblocks) {
-      trp.stamp();
-      mbar_wait(&empty[st], ph);
-      trp.stamp();
-      unsigned char* stage = smem + (size_t)st * g.stage_bytes;
-      const long long q0 = qoff + (long long)it * KS, m0 = (blk0 + it) * KS;
-      if (q0 >= 0 && q0 + g.arows <= g.L && m0 + KS <= g.L) {     // interior block: no per-row range checks
+  for (int it = 0; it < nblocks; ++it) {
+    trp.stamp();
+    mbar_wait(&empty[st], ph);
+    trp.stamp();
+    unsigned char* stage = smem + (size_t)st * g.stage_bytes;
+    const long long q0 = qoff + (long long)it * KS, m0 = (blk0 + it) * KS;
+    if (q0 >= 0 && q0 + g.arows <= g.L && m0 + KS <= g.L) {     // interior block: no per-row range checks
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-          if (adst[k] != 0xffffffffu) cp_async16(stage + adst[k], aplane[k] + (q0 + arow[k]) * 16, 16u);
-          if (bdst[k] != 0xffffffffu) {
-            const bool ok = bplane[k] != nullptr;
-            cp_async16(stage + bdst[k], ok ? bplane[k] + (m0 + brow[k]) * 16 : a.dzf, ok ? 16u : 0u);
-          }
+      for (int k = 0; k < kItems; ++k) {
+        if (adst[k] != 0xffffffffu) {
+          const bool ok = aplane[k] != nullptr;
+          cp_async16(stage + adst[k], ok ? aplane[k] + (q0 + arow[k]) * 16 : a.phi, ok ? 16u : 0u);
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-          if (adst[k] != 0xffffffffu) {
-            const long long q = q0 + arow[k];
-            const bool ok = q >= 0 && q < g.L;
-            cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
-          }
-          if (bdst[k] != 0xffffffffu) {
-            const long long m = m0 + brow[k];
-            const bool ok = bplane[k] != nullptr && m < g.L;
-            cp_async16(stage + bdst[k], ok ? bplane[k] + m * 16 : a.dzf, ok ? 16u : 0u);
-          }
+        if (bdst[k] != 0xffffffffu) {
+          const bool ok = bplane[k] != nullptr;
+          cp_async16(stage + bdst[k], ok ? bplane[k] + (m0 + brow[k]) * 16 : a.dzf, ok ? 16u : 0u);
         }
       }
-      if (++st == g.stages) { st = 0; ph ^= 1; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        if (adst[k] != 0xffffffffu) {
+          const long long q = q0 + arow[k];
+          const bool ok = aplane[k] != nullptr && q >= 0 && q < g.L;
+          cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
+        }
+        if (bdst[k] != 0xffffffffu) {
+          const long long m = m0 + brow[k];
+          const bool ok = bplane[k] != nullptr && m < g.L;
+          cp_async16(stage + bdst[k], ok ? bplane[k] + m * 16 : a.dzf, ok ? 16u : 0u);
+        }
+      }
     }
-    cp_async_commit();
-    if (it >= depth) {                             // every group older than the newest `depth` has landed
-      if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-      fence_proxy_async_smem();
-      mbar_arrive(&full[st_done]);
-      if (++st_done == g.stages) st_done = 0;
-    }
+    cp_async_mbar_arrive_noinc(&full[st]);
+    if (++st == g.stages) { st = 0; ph ^= 1; }
   }
 }
 
 // Straight-line issue of the KW x (kKS/16) MMAs of one stage (tap s reads the Phi planes from row s; k-step ks advances both
 // operands by 16 rows).  Descriptor low words differ by small constants only.
-template <int S0, int S1, int KS>          // taps [S0, S1)
+template <bool PAIR>
+__device__ __forceinline__ void wg_mma(uint32_t td, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if (PAIR) tc_mma_bf16_pair(td, ad, bd, idesc, acc); else tc_mma_bf16(td, ad, bd, idesc, acc);
+}
+template <int S0, int S1, int KS, bool PAIR>          // taps [S0, S1)
 __device__ __forceinline__ void wg_issue(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
                                          uint32_t b_hi, uint32_t idesc, uint32_t first) {
 #pragma unroll
@@ -231,12 +238,12 @@ __device__ __forceinline__ void wg_issue(uint32_t tmem_base, uint32_t ntile, uin
     const uint32_t td = tmem_base + (uint32_t)s * ntile;
 #pragma unroll
     for (int ks = 0; ks < KS / 16; ++ks)
-      tc_mma_bf16(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
-                  ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
+      wg_mma<PAIR>(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
+                   ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
   }
 }
 
-template <int KS>
+template <int KS, bool PAIR>
 __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
@@ -245,46 +252,62 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   uint64_t* full = bars;                         // [kMaxStagesW]
   uint64_t* empty = bars + kMaxStagesW;          // [kMaxStagesW]
   uint64_t* acc_full = bars + 2 * kMaxStagesW;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesW + 1);
+  uint64_t* pfull = bars + 2 * kMaxStagesW + 1;  // [kMaxStagesW] pair only, in the leader: the peer CTA's stage has landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kNumBarsW);
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   KC_TRACER(trl, g_trace_w, 2, threadIdx.x == 0);          // CTA life cycle: entry, set-up done, mainloop done, accumulators ready, end
   trl.stamp();
-  // unit = ((cout tile * nchunks + chunk) * kh + r)
-  const int unit = blockIdx.x, split = blockIdx.y;
-  const int r = unit % d.kh;
-  const int chunk = (unit / d.kh) % g.nchunks;
-  const int ct = unit / (d.kh * g.nchunks);
+  // unit = ((cout tile * nchunks + chunk) * kh + r); in a pair the two CTAs of a cluster are two units of the SAME cout tile
+  // (they share the dz stage) and a cout tile with an odd number of units gets a dummy partner that only loads its dz half
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  int unit, ct, chunk, r;
+  bool dummy = false;
+  if (PAIR) {
+    ct = blockIdx.x / g.upc;
+    const int u = blockIdx.x - ct * g.upc;
+    dummy = u >= g.units_ct;
+    r = u % d.kh;
+    chunk = dummy ? 0 : u / d.kh;
+    unit = ct * g.units_ct + u;
+  } else {
+    unit = blockIdx.x;
+    r = unit % d.kh;
+    chunk = (unit / d.kh) % g.nchunks;
+    ct = unit / (d.kh * g.nchunks);
+  }
+  const int split = blockIdx.y;
   const long long blk0 = (long long)split * g.blk_per_split;
   const long long blk1 = min(g.nblk, blk0 + g.blk_per_split);
   const int nblocks = (int)(blk1 - blk0);
 
   if (threadIdx.x == 0) {
     const uint32_t nmw = d.kw == 3 ? 2u : 1u;          // MMA-issuing warps: with three taps, warp 16 takes taps 0-1, warp 17 tap 2
-    for (int i = 0; i < kMaxStagesW; ++i) { mbar_init(&full[i], kProdW); mbar_init(&empty[i], nmw); }
+    for (int i = 0; i < kMaxStagesW; ++i) { mbar_init(&full[i], (uint32_t)kProdW); mbar_init(&empty[i], nmw); mbar_init(&pfull[i], 1u); }
     mbar_init(acc_full, nmw);
     fence_barrier_init();
   }
-  if (warp == kMmaWarpW) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
+  if (warp == kMmaWarpW) { if (PAIR) tmem_alloc_pair(tmem_ptr, (uint32_t)g.tmem_cols); else tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols); }
   kc_load_basis_ctx(B, d, a.beta);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) { cluster_arrive(); cluster_wait(); }        // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   trl.stamp();
 
   if (warp < 16) {
     // ============================ producers: cp.async copies of the Phi (A) and dz (B) planes ===========================
-    wg_produce<KS>(a, smem, full, empty, r, chunk, ct, blk0, nblocks);
+    wg_produce<KS, PAIR>(a, smem, full, empty, r, chunk, ct, blk0, nblocks, rank, dummy);
     trl.stamp();
   }
-  if (warp >= kMmaWarpW && (warp == kMmaWarpW || d.kw == 3)) {
+  if (warp >= kMmaWarpW && (warp == kMmaWarpW || d.kw == 3) && rank == 0) {
     // ============================ MMA issuers (whole warp uniform, one elected lane issues) =========================
     // The taps have separate accumulators, so two warps can issue independently: the barrier wait / commit overhead of one
-    // overlaps the MMAs of the other.
+    // overlaps the MMAs of the other.  In a pair only the leader CTA issues (M = 256: its own 128 Phi rows and the peer's).
     const int mw = warp - kMmaWarpW;
-    const uint32_t idesc = make_idesc_bf16(128, g.ntile, 1, 1);        // both operands MN-major
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, g.ntile, 1, 1);   // both operands MN-major
     const uint32_t lo_c = (128u >> 4) << 16;                            // LBO = 128 B between 8-row K groups
     const uint32_t a_hi = ((uint32_t)g.aplane_bytes >> 4) | (1u << 14); // SBO = plane pitch (8 M rows), version 1
     const uint32_t b_hi = ((uint32_t)g.bplane_bytes >> 4) | (1u << 14);
@@ -296,31 +319,43 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     for (int bi = 0; bi < nblocks; ++bi) {
       trm.stamp();
       mbar_wait(&full[st], ph);
+      if (PAIR) mbar_wait_cluster(&pfull[st], ph);
       tc_fence_after();
       trm.stamp();
       const uint32_t au = smem_u + (uint32_t)st * stage_u, bu = au + a_u;
       const uint32_t first = bi != 0 ? 1u : 0u;
       if (elect_one_sync()) {
         const uint32_t a_lo = lo_c | au, b_lo = lo_c | bu;
-        if (kw == 3 && mw == 0) wg_issue<0, 2, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
-        else if (kw == 3) wg_issue<2, 3, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
-        else if (kw == 1) wg_issue<0, 1, KS>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        if (kw == 3 && mw == 0) wg_issue<0, 2, KS, PAIR>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else if (kw == 3) wg_issue<2, 3, KS, PAIR>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
+        else if (kw == 1) wg_issue<0, 1, KS, PAIR>(tmem_base, (uint32_t)ntile, a_lo, b_lo, a_hi, b_hi, idesc, first);
         else {
           for (int s = 0; s < kw; ++s) {
             const uint32_t td = tmem_base + (uint32_t)(s * ntile);
 #pragma unroll
             for (int ks = 0; ks < KS / 16; ++ks)
-              tc_mma_bf16(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
-                          ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
+              wg_mma<PAIR>(td, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(s + 16 * ks)),
+                           ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(16 * ks)), idesc, ks == 0 ? first : 1u);
           }
         }
-        tc_commit(&empty[st]);
+        if (PAIR) tc_commit_pair(&empty[st]); else tc_commit(&empty[st]);
       }
       __syncwarp();
       if (++st == g.stages) { st = 0; ph ^= 1; }
     }
-    if (elect_one_sync()) tc_commit(acc_full);
+    if (elect_one_sync()) { if (PAIR) tc_commit_pair(acc_full); else tc_commit(acc_full); }
     __syncwarp();
+  }
+  if (PAIR && rank == 1 && warp == kMmaWarpW) {
+    // ============================ peer CTA: tell the leader that this CTA's half of a stage has landed ===============
+    int st = 0;
+    uint32_t ph = 0;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      mbar_wait(&full[st], ph);
+      if (lane == 0) mbar_arrive_cluster(&pfull[st], 0);
+      __syncwarp();
+      if (++st == g.stages) { st = 0; ph ^= 1; }
+    }
   }
   if (warp < 16) {
     // ============================ epilogue: TMEM -> fp32 partial sums in the split workspace ========================
@@ -329,7 +364,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
     trl.stamp();
     const int quarter = warp & 3, cgrp = warp >> 2;
     const int m = quarter * 32 + lane;
-    const int ncol16 = d.kw * g.ntile / 16;
+    const int ncol16 = dummy ? 0 : d.kw * g.ntile / 16;
     float* wsu = a.ws + ((long long)split * g.units + unit) * ((long long)d.kw * 128 * g.ntile);
     for (int c16 = cgrp; c16 < ncol16; c16 += 4) {
       uint32_t rr[16];
@@ -348,7 +383,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   trl.stamp();
-  if (warp == kMmaWarpW) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  if (PAIR) { cluster_arrive(); cluster_wait(); }        // both CTAs are done with the pair's tensor memory and shared memory
+  if (warp == kMmaWarpW) { if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)g.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols); }
 }
 
 // Sum the splits (fixed order) and scatter into the reference layouts dw_basis [cout][cin*nb][kh][kw] (inner index
@@ -463,11 +499,21 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->ntile = round_up_w((g->cq + want - 1) / want, 16);
   g->n_ct = (g->cq + g->ntile - 1) / g->ntile;
   g->units = g->n_ct * g->nchunks * d->kh;
+  // CTA pairs (tcgen05 cta_group::2, M = 256): two units of a cout tile share every dz stage and each CTA loads half of it.
+  // An M = 128 MMA with N <= 128 is bound by the operand fetch from shared memory (66 / 74 cycles at N = 64 / 128 instead of
+  // 32 / 64); the pair halves the B fetch per CTA (43 / 64 cycles, tools/mma_rate_2cta.py).  KANCONV_WGRAD_PAIR=0: single CTAs.
+  g->units_ct = g->nchunks * d->kh;
+  {
+    static const int pair_enabled = []() { const char* e = getenv("KANCONV_WGRAD_PAIR"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+    g->pair = (pair_enabled && g->units_ct >= 2) ? 1 : 0;
+  }
+  g->upc = g->pair ? round_up_w(g->units_ct, 2) : g->units_ct;
   // positions per ring stage: as many MMAs per barrier round as the producer mapping and a >= 3-deep ring allow
   // (128 -> 24 MMAs per tap row for cout tiles <= 64, else 96 -> 18, else 64 -> 12)
   g->bplanes = g->ntile / 8;
+  g->bplanes_cta = g->pair ? g->bplanes / 2 : g->bplanes;
   const int cand[3] = {128, 96, 64};
-  size_t fixed = (2 * kMaxStagesW + 1) * 8 + 16 + sizeof(KcBasisCtx) + 128;
+  size_t fixed = kNumBarsW * 8 + 16 + sizeof(KcBasisCtx) + 128;
   bool ok = false;
   for (int ci = 0; ci < 3 && !ok; ++ci) {
     g->ks = cand[ci];
@@ -475,17 +521,16 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
     g->aplane_bytes = g->arows * 16 + 16;
     g->a_bytes = 16 * g->aplane_bytes;
     g->bplane_bytes = g->ks * 16 + 16;
-    g->stage_bytes = round_up_w(g->a_bytes + g->bplanes * g->bplane_bytes, 128);
+    g->stage_bytes = round_up_w(g->a_bytes + g->bplanes_cta * g->bplane_bytes, 128);
     const int items = g->ks == 64 ? 3 : g->ks == 96 ? 4 : 5;
-    if (g->arows * 16 > items * kProdW || g->ks * g->bplanes > items * kProdW) continue;
+    if (g->arows * 16 > items * kProdW || g->ks * g->bplanes_cta > items * kProdW) continue;
     g->stages = (int)((kSmemLimitW - fixed) / g->stage_bytes);
     if (g->stages > kMaxStagesW) g->stages = kMaxStagesW;
     if (g->stages < (g->ks == 64 ? 2 : 3)) continue;
     ok = true;
   }
   if (!ok) KC_FAIL(KC_ERR_UNSUPPORTED, "tensor-core wgrad: stage does not fit shared memory / the producer mapping");
-  g->prefetch = g->stages - 2 < kPrefetchW ? g->stages - 2 : kPrefetchW;      // keep two slack stages for the MMA side
-  if (g->prefetch < 1) g->prefetch = 1;
+  g->prefetch = g->stages - 1;                     // informational: stages in flight while one is being consumed
   g->smem_bytes = fixed + (size_t)g->stages * g->stage_bytes;
   g->tmem_cols = 32;
   while (g->tmem_cols < d->kw * g->ntile) g->tmem_cols *= 2;
@@ -497,7 +542,8 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   const long long sms = kc_sm_count();
   const long long minblk = 1024 / g->ks;                            // at least 1024 positions per CTA
   const long long max_split = g->nblk / minblk > 0 ? g->nblk / minblk : 1;
-  long long lo = (2 * sms + g->units - 1) / g->units, hi = (4 * sms) / g->units;
+  const long long grid_x = g->pair ? (long long)g->n_ct * g->upc : g->units;      // CTAs per split (incl. dummy partners)
+  long long lo = (2 * sms + grid_x - 1) / grid_x, hi = (4 * sms) / grid_x;
   if (lo < 1) lo = 1;
   if (hi < lo) hi = lo;
   if (hi > max_split) hi = max_split;
@@ -506,10 +552,10 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   double best = -1.0;
   for (long long c = lo; c <= hi; ++c) {
     const long long bps = (g->nblk + c - 1) / c, real = (g->nblk + bps - 1) / bps;   // splits that actually get blocks
-    const long long ctas = real * g->units, waves = (ctas + sms - 1) / sms;
+    const long long ctas = real * grid_x, waves = (ctas + sms - 1) / sms;
     // time ~ waves * blocks per CTA (+ a fixed prologue / epilogue of ~10 block-times per CTA)
     const double t = (double)waves * (double)(bps + 10);
-    const double score = (double)g->nblk * g->units / (double)sms / t;
+    const double score = (double)g->nblk * grid_x / (double)sms / t;
     if (score > best + 1e-9) { best = score; ns = c; }
   }
   g->blk_per_split = (g->nblk + ns - 1) / ns;
@@ -518,6 +564,25 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->phi_bytes = (size_t)g->nchunks * 16 * (size_t)g->L * 16;
   g->fast_cubic = kc_knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
   return KC_OK;
+}
+
+template <int KS, bool PAIR>
+cudaError_t launch_wgrad(const WgArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kc_wgrad_tc_kernel<KS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreadsW, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2u : 1u;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kc_wgrad_tc_kernel<KS, PAIR>, a);
 }
 
 }  // namespace
@@ -584,16 +649,18 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
     kc_phi_flat_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a, phi);
     KC_LAUNCH_CHECK("kc_phi_flat_kernel");
   }
-  dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
-  if (g.ks == 96) {
-    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    kc_wgrad_tc_kernel<96><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
-  } else if (g.ks == 128) {
-    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    kc_wgrad_tc_kernel<128><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  if (g.pair) {
+    dim3 grid((unsigned)(g.n_ct * g.upc), (unsigned)g.nsplit);
+    cudaError_t e = g.ks == 96    ? launch_wgrad<96, true>(a, grid, g.smem_bytes, (cudaStream_t)stream)
+                    : g.ks == 128 ? launch_wgrad<128, true>(a, grid, g.smem_bytes, (cudaStream_t)stream)
+                                  : launch_wgrad<64, true>(a, grid, g.smem_bytes, (cudaStream_t)stream);
+    KC_CUDA_CHECK(e);
   } else {
-    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    kc_wgrad_tc_kernel<64><<<grid, kThreadsW, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    dim3 grid((unsigned)g.units, (unsigned)g.nsplit);
+    cudaError_t e = g.ks == 96    ? launch_wgrad<96, false>(a, grid, g.smem_bytes, (cudaStream_t)stream)
+                    : g.ks == 128 ? launch_wgrad<128, false>(a, grid, g.smem_bytes, (cudaStream_t)stream)
+                                  : launch_wgrad<64, false>(a, grid, g.smem_bytes, (cudaStream_t)stream);
+    KC_CUDA_CHECK(e);
   }
   KC_LAUNCH_CHECK("kc_wgrad_tc_kernel");
   long long total = (long long)g.units * d->kw * 128 * g.ntile;

@@ -47,6 +47,7 @@ else:
 pe = ev[0]
 k0 = (len(pe) // 2) // 4 * 4
 print("  producer thread 0: steady-state stamp gaps (chunk start, buffer free, stores done, arrived):", [pe[k + 1] - pe[k] for k in range(k0, min(k0 + 16, len(pe) - 1))])
+print("  producer thread 0: last 16 stamp gaps (base-activation chunks):", [pe[k + 1] - pe[k] for k in range(max(0, len(pe) - 17), len(pe) - 1)])
 print("  producer thread 0: first 12 stamp gaps", [pe[k + 1] - pe[k] for k in range(min(12, len(pe) - 1))], "last stamp at", pe[-1] - t0 if pe else None)
 lo = ev[2]
 if lo:
