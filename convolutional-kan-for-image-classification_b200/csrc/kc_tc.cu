@@ -24,6 +24,7 @@
 // The MMA issuer is the highest warp id on purpose: the scheduler arbitrates highest-warp-id-first, and the single issuing
 // thread must never wait behind the 16 ALU-heavy producer warps (measured: 245 -> ~50 cycles per tcgen05.mma).
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kc_common.cuh"
@@ -62,6 +63,7 @@ struct TcGeom {
   int cpt;                     // dgrad: input channels per N tile (16, or 14 for the persistent kernel with a base column)
   int persistent;              // dgrad: 1 = kc_dgrad_persistent_kernel (double-buffered TMEM, epilogue overlaps the MMAs)
   int from_phi;                // forward of a 1x1 convolution: basis rows come from the phi buffer (pre-pass + persistent GEMM)
+  int pair;                    // persistent dgrad: 1 = CTA pairs (tcgen05 cta_group::2), each CTA holds half of the N rows of a weight stage
   long long mtiles;
   long long wimg_bytes_per_ntile;
   size_t smem_bytes;
@@ -205,10 +207,24 @@ __device__ __forceinline__ int chunk_cols(const TcGeom& g, int q) {
   return (q < g.nsc || q - g.nsc != g.nbc - 1) ? kPL : g.last_base_cols;
 }
 
+// Order in which kc_tc_kernel walks the K chunks of a tile.  A base-activation chunk costs the producers 2-3x a spline chunk
+// (32 channels per chunk instead of 4), so the base chunks are spread between the spline chunks instead of following them all:
+// base chunk b comes right after the spline chunks of its own 32 channels (their x values are still in L2), the producers
+// bank their slack of the cheap chunks in the A ring and spend it on the expensive one, and the MMA warps rarely wait for
+// rows.  Producers, weight loader and MMA issuers run the same sequence.
+struct ChunkSeq {
+  int nsc, nbc, s, b;
+  __device__ __forceinline__ ChunkSeq(int nsc_, int nbc_) : nsc(nsc_), nbc(nbc_), s(0), b(0) {}
+  __device__ __forceinline__ int next() {           // chunk id: < nsc spline chunk, else base chunk (id - nsc)
+    if (b < nbc && (s >= nsc || nbc * s >= (b + 1) * nsc)) return nsc + b++;
+    return s++;
+  }
+};
+
 // Straight-line issue of the NSUB x (K/16) MMAs of one ring step.  a_lo / b_lo are complete low descriptor words
 // (LBO field | start address >> 4) of sub-tile 0, k-core pair 0; all other descriptors differ by small constants, so
 // the issuing thread executes ~2 integer adds per tcgen05.mma and no branches.
-template <int NSUB>
+template <int NSUB, bool PAIR = false>
 __device__ __forceinline__ void issue_step(uint32_t tmem_base, uint32_t ntile, uint32_t a_lo, uint32_t b_lo, uint32_t a_k2,
                                            uint32_t b_k2, uint32_t desc_hi, uint32_t idesc, uint32_t first, bool two, int i0,
                                            int istep) {
@@ -217,8 +233,13 @@ __device__ __forceinline__ void issue_step(uint32_t tmem_base, uint32_t ntile, u
     const int i = i0 + ii * istep;
     const uint32_t al = a_lo + (uint32_t)(i * kTileM);
     const uint32_t td = tmem_base + (uint32_t)i * ntile;
-    tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | al, ((uint64_t)desc_hi << 32) | b_lo, idesc, first);
-    if (two) tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | (al + a_k2), ((uint64_t)desc_hi << 32) | (b_lo + b_k2), idesc, 1u);
+    if (PAIR) {
+      tc_mma_bf16_pair(td, ((uint64_t)desc_hi << 32) | al, ((uint64_t)desc_hi << 32) | b_lo, idesc, first);
+      if (two) tc_mma_bf16_pair(td, ((uint64_t)desc_hi << 32) | (al + a_k2), ((uint64_t)desc_hi << 32) | (b_lo + b_k2), idesc, 1u);
+    } else {
+      tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | al, ((uint64_t)desc_hi << 32) | b_lo, idesc, first);
+      if (two) tc_mma_bf16(td, ((uint64_t)desc_hi << 32) | (al + a_k2), ((uint64_t)desc_hi << 32) | (b_lo + b_k2), idesc, 1u);
+    }
   }
 }
 
@@ -358,7 +379,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     }
     int buf = 0;
     uint32_t aphase = 0;
-    for (int q = 0; MODE != kModeDgrad && q < nchunks; ++q) {
+    ChunkSeq pseq(g.nsc, has_base ? g.nbc : 0);
+    for (int pq = 0; MODE != kModeDgrad && pq < nchunks; ++pq) {
+      const int q = pseq.next();
       unsigned char* ab = abuf0 + buf * abuf_bytes;
       trp.stamp();                                   // chunk start
       if (q < g.nsc && nb == 8) {
@@ -476,7 +499,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       int stage = 0, buf = 0;
       uint32_t bphase = 0, aphase = 0;
       KC_TRACER(trm, g_trace, 1, lane == 0 && mw == 0);
-      for (int q = 0; q < nchunks; ++q) {
+      ChunkSeq mseq(MODE == kModeDgrad ? 0 : g.nsc, MODE == kModeDgrad ? g.nbc : (has_base ? g.nbc : 0));
+      for (int pq = 0; pq < nchunks; ++pq) {
+        const int q = mseq.next();
         const int nk2 = chunk_cols(g, q) >> 1;
         const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);      // 16-byte units per tap image
         trm.stamp();                                 // before a_full wait
@@ -493,7 +518,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
           const bool two = nk2 == 2;
           const bool leader = elect_one_sync();
           for (int tt = 0; tt < tps; ++tt) {
-            const uint32_t first = (q | (t + tt)) != 0 ? 1u : 0u;
+            const uint32_t first = (pq | (t + tt)) != 0 ? 1u : 0u;
             if (leader) {
               if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
               else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
@@ -519,10 +544,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t bphase = 0;
-      const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
+      const unsigned char* wimg = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
       KC_TRACER(trl, g_trace, 2, true);
-      for (int q = 0; q < nchunks; ++q) {
-        const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
+      // the packed image holds the chunks in id order (spline chunks, then base chunks; only the last one can be narrower)
+      const long long full_chunk_bytes = (long long)kPL * g.ntile * 16 * T;
+      ChunkSeq lseq(MODE == kModeDgrad ? 0 : g.nsc, MODE == kModeDgrad ? g.nbc : (has_base ? g.nbc : 0));
+      for (int pq = 0; pq < nchunks; ++pq) {
+        const int q = lseq.next();
+        const unsigned char* wsrc = wimg + (long long)q * full_chunk_bytes;
+        uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
+#ifdef KANCONV_DEBUG_HALFB
+        bytes /= 2;          // timing experiment only (wrong results): half the weight traffic
+#endif
         for (int t = 0; t < T; t += g.tps) {
           mbar_wait(&b_empty[stage], bphase ^ 1);
           trl.stamp();                               // b_empty acquired
@@ -812,16 +845,22 @@ __device__ __forceinline__ void tc_gram_grad8(const KcBasisCtx& B, float x, cons
 //        written once by the pre-pass (it is needed for the weight gradient anyway) and this kernel streams it back.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kDgThreads = 640, kDgEpiWarps = 16, kDgProdWarp0 = 16, kDgLoaderWarp = 17, kDgMmaWarp0 = 18;
-constexpr int kDgBars = 2 * kMaxA + 2 * kMaxBStages + 4;
+constexpr int kDgBars = 3 * kMaxA + 3 * kMaxBStages + 4;
 
-template <int FAM>
+// PAIR: two CTAs of a cluster work on two neighbouring position tiles and the same N tile with tcgen05 cta_group::2 MMAs
+// (M = 256): each CTA loads its own dz rows and HALF of every weight stage (64 of the 128 N rows), the leader CTA issues the
+// MMAs for both.  An M = 128, N = 128 MMA is bound by the operand fetch from shared memory (74 cycles instead of 64); the
+// pair halves the weight fetch per CTA (64 cycles, tools/mma_rate_2cta.py) and the weight traffic from L2.
+template <int FAM, bool PAIR>
 __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(const __grid_constant__ TcFwdArgs a) {
   constexpr bool CUBIC = FAM == 1, FWD = FAM == 2, GRAMF = FAM == 3;
+  static_assert(!(FWD && PAIR), "the pointwise forward runs on single CTAs");
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
   const int abuf_bytes = kPL * g.plane_bytes;
-  const int btap_bytes = kPL * g.ntile * 16;
+  const int nw = PAIR ? g.ntile / 2 : g.ntile;     // weight rows (of the MMA's N) this CTA holds
+  const int btap_bytes = kPL * nw * 16;
   const int bstage_bytes = g.tps * btap_bytes;
   unsigned char* abuf0 = smem;
   unsigned char* bst0 = abuf0 + g.na * abuf_bytes;
@@ -832,6 +871,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   uint64_t* b_empty = b_full + kMaxBStages;
   uint64_t* acc_full = b_empty + kMaxBStages;      // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint64_t* pa_full = acc_empty + 2;               // [kMaxA]        pair, leader: the peer's dz rows have landed
+  uint64_t* pb_full = pa_full + kMaxA;             // [kMaxBStages]  pair, leader: the peer's half of a weight stage has landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kDgBars);
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);      // !CUBIC only
 
@@ -840,18 +881,25 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   const bool has_base = d.act != KC_ACT_NONE;
   const int wb = d.nb + (has_base ? 1 : 0);
   const int nchunks = FWD ? g.nsc + (has_base ? g.nbc : 0) : g.nbc;
-  const long long ntiles = g.mtiles * g.n_ntiles;
+  // tile walk: a (pair of) CTA(s) takes every tstep-th (position tile [pair], N tile); in a pair CTA `rank` owns position
+  // tile 2 * m + rank (an odd tile count leaves the last peer with positions >= L: nothing is loaded or stored for them)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const long long ntiles = (PAIR ? (g.mtiles + 1) / 2 : g.mtiles) * g.n_ntiles;
+  const long long tile0 = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long tstep = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  auto mt_of = [&](long long tile) -> long long { const long long m = tile / g.n_ntiles; return PAIR ? 2 * m + rank : m; };
   if (FAM == 0 || GRAMF) kc_load_basis_ctx(B, d, a.beta);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
-    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], kDgEpiWarps); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); mbar_init(&pa_full[i], 1); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); mbar_init(&pb_full[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], PAIR ? 2 * kDgEpiWarps : kDgEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == kDgMmaWarp0) tmem_alloc(tmem_ptr, 512u);
+  if (warp == kDgMmaWarp0) { if (PAIR) tmem_alloc_pair(tmem_ptr, 512u); else tmem_alloc(tmem_ptr, 512u); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) { cluster_arrive(); cluster_wait(); }        // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -865,8 +913,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     KC_TRACER(trp, g_trace, 0, lane == 0);
     int buf = 0;
     uint32_t ph = 1;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const long long qs = (tile / g.n_ntiles) * g.mcta - (long long)g.ph * g.P - g.pw + (long long)r * g.P;
+    for (long long tile = tile0; tile < ntiles; tile += tstep) {
+      const long long qs = mt_of(tile) * g.mcta - (long long)g.ph * g.P - g.pw + (long long)r * g.P;
       long long lo = qs < 0 ? -qs : 0, hi = qs + len > g.L ? g.L - qs : len;
       if (lo > len) lo = len;
       if (hi < lo) hi = lo;
@@ -902,11 +950,12 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       int stage = 0;
       uint32_t bphase = 1;
       KC_TRACER(trl, g_trace, 2, true);
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = tile0; tile < ntiles; tile += tstep) {
         const int nt = (int)(tile % g.n_ntiles);
-        const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
+        // pair: the image of an N tile is stored as two halves of nw rows each, CTA `rank` streams its half
+        const unsigned char* wsrc = a.wp + (long long)nt * g.wimg_bytes_per_ntile + (PAIR ? (long long)rank * (g.wimg_bytes_per_ntile / 2) : 0);
         for (int q = 0; q < nchunks; ++q) {
-          const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
+          const uint32_t bytes = (uint32_t)chunk_cols(g, q) * (uint32_t)nw * 16u * (uint32_t)g.tps;
           for (int t = 0; t < T; t += g.tps) {
             mbar_wait(&b_empty[stage], bphase);
             trl.stamp();
@@ -919,14 +968,39 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       }
     }
     __syncwarp();
+  } else if (warp >= kDgMmaWarp0 && rank != 0) {
+    // ================================ peer CTA of a pair: relay "landed" to the leader, which issues the MMAs ==========
+    // warp 18: dz buffers, warp 19: weight stages
+    if (warp == kDgMmaWarp0) {
+      int buf = 0;
+      uint32_t aphase = 0;
+      for (long long tile = tile0; tile < ntiles; tile += tstep)
+        for (int q = 0; q < nchunks; ++q) {
+          mbar_wait(&a_full[buf], aphase);
+          if (lane == 0) mbar_arrive_cluster(&pa_full[buf], 0);
+          __syncwarp();
+          if (++buf == g.na) { buf = 0; aphase ^= 1; }
+        }
+    } else {
+      int stage = 0;
+      uint32_t bphase = 0;
+      for (long long tile = tile0; tile < ntiles; tile += tstep)
+        for (int q = 0; q < nchunks; ++q)
+          for (int t = 0; t < T; t += g.tps) {
+            mbar_wait(&b_full[stage], bphase);
+            if (lane == 0) mbar_arrive_cluster(&pb_full[stage], 0);
+            __syncwarp();
+            if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
+          }
+    }
   } else if (warp >= kDgMmaWarp0) {
     // ================================ MMA issuers: warp mw accumulates sub-tile mw ====================
     const int mw = warp - kDgMmaWarp0;
-    const uint32_t idesc = make_idesc_bf16(kTileM, g.ntile, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTileM : kTileM, g.ntile, 0, 0);
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t a_lo_c = ((uint32_t)(g.plane_bytes >> 4) & 0x3FFFu) << 16;
-    const uint32_t b_lo_c = ((uint32_t)(g.ntile) & 0x3FFFu) << 16;
-    const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * g.ntile);
+    const uint32_t b_lo_c = ((uint32_t)(nw) & 0x3FFFu) << 16;
+    const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * nw);
     const uint32_t abuf_u = smem_u32(abuf0) >> 4, bst_u = smem_u32(bst0) >> 4;
     const uint32_t abuf_sz = (uint32_t)abuf_bytes >> 4, bst_sz = (uint32_t)bstage_bytes >> 4;
     const int ntile = g.ntile, kw = d.kw, SS = g.SS, tps = g.tps;
@@ -934,23 +1008,26 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     uint32_t bphase = 0, aphase = 0;
     uint32_t it = 0;
     KC_TRACER(trm, g_trace, 1, lane == 0 && mw == 0);
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (long long tile = tile0; tile < ntiles; tile += tstep, ++it) {
       const uint32_t acc = it & 1u;
       trm.stamp();                                           // tile start
-      mbar_wait(&acc_empty[acc], ((it >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator set
+      // the epilogue (of both CTAs in a pair) has drained this accumulator set
+      if (PAIR) mbar_wait_cluster(&acc_empty[acc], ((it >> 1) & 1u) ^ 1u); else mbar_wait(&acc_empty[acc], ((it >> 1) & 1u) ^ 1u);
       tc_fence_after();
       trm.stamp();                                           // accumulator set free
       const uint32_t tacc = tmem_base + acc * (uint32_t)(2 * ntile);
       for (int q = 0; q < nchunks; ++q) {
         const int nk2 = chunk_cols(g, q) >> 1;
-        const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);
+        const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * nw);
         mbar_wait(&a_full[buf], aphase);
+        if (PAIR) mbar_wait_cluster(&pa_full[buf], aphase);
         tc_fence_after();
         trm.stamp();                                         // a_full acquired
         uint32_t arow = abuf_u + (uint32_t)buf * abuf_sz;
         int s = 0;
         for (int t = 0; t < T; t += tps) {
           mbar_wait(&b_full[stage], bphase);
+          if (PAIR) mbar_wait_cluster(&pb_full[stage], bphase);
           tc_fence_after();
           trm.stamp();                                       // b_full acquired
           uint32_t b_lo = b_lo_c + bst_u + (uint32_t)stage * bst_sz;
@@ -958,20 +1035,25 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
           const bool leader = elect_one_sync();
           for (int tt = 0; tt < tps; ++tt) {
             const uint32_t first = (q | (t + tt)) != 0 ? 1u : 0u;
-            if (leader) issue_step<1>(tacc, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, 1);
+            if (leader) issue_step<1, PAIR>(tacc, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, 1);
             b_lo += btap_u;
             if (++s == kw) { s = 0; arow += (uint32_t)(SS - (kw - 1)); } else { arow += 1u; }
           }
           if (leader) {
-            tc_commit(&b_empty[stage]);
-            if (t + tps >= T) tc_commit(&a_empty[buf]);
+            if (PAIR) {
+              tc_commit_pair(&b_empty[stage]);
+              if (t + tps >= T) tc_commit_pair(&a_empty[buf]);
+            } else {
+              tc_commit(&b_empty[stage]);
+              if (t + tps >= T) tc_commit(&a_empty[buf]);
+            }
           }
           __syncwarp();
           if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
         }
         if (++buf == g.na) { buf = 0; aphase ^= 1; }
       }
-      if (elect_one_sync()) tc_commit(&acc_full[acc]);
+      if (elect_one_sync()) { if (PAIR) tc_commit_pair(&acc_full[acc]); else tc_commit(&acc_full[acc]); }
       __syncwarp();
     }
   } else {
@@ -979,11 +1061,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
       // ============================== epilogue (forward from phi): TMEM -> z (fp32 NCHW) ===========================
       const int quarter = warp & 3, cgrp = warp >> 2;
       const int HoWo = d.ho * d.wo;
-      const long long nsteps = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * 2;
+      const long long nsteps = tile0 < ntiles ? ((ntiles - tile0 + tstep - 1) / tstep) * 2 : 0;
 #pragma unroll 1
       for (long long step = 0; step < nsteps; ++step) {
         const uint32_t it = (uint32_t)(step >> 1), acc = it & 1u, sub = (uint32_t)(step & 1);
-        const long long tile = blockIdx.x + (step >> 1) * gridDim.x;
+        const long long tile = tile0 + (step >> 1) * tstep;
         const long long mt = tile / g.n_ntiles;
         const int n0 = (int)(tile - mt * g.n_ntiles) * g.ntile;
         const long long q = mt * g.mcta + sub * kTileM + quarter * 32 + lane;
@@ -1032,12 +1114,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
     const int chs = (cgrp * g.cpt) / 4, chn = ((cgrp + 1) * g.cpt) / 4 - chs;
     const int nint = d.nparams - 1, act = d.act, nb = d.nb;
     const float t0 = g.t0, inv_h = g.inv_h;
-    const long long nsteps = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * 2;     // (tile, sub-tile) pairs of this CTA
+    const long long nsteps = tile0 < ntiles ? ((ntiles - tile0 + tstep - 1) / tstep) * 2 : 0;     // (tile, sub-tile) pairs of this CTA
     auto locate = [&](long long step, int& c0) -> int {           // x offset of this lane's position in step, or -1
-      const long long tile = blockIdx.x + (step >> 1) * gridDim.x;
-      const long long mt = tile / g.n_ntiles;
-      c0 = (int)(tile - mt * g.n_ntiles) * g.cpt + chs;
-      const long long q = mt * g.mcta + (step & 1) * kTileM + quarter * 32 + lane;
+      const long long tile = tile0 + (step >> 1) * tstep;
+      c0 = (int)(tile % g.n_ntiles) * g.cpt + chs;
+      const long long q = mt_of(tile) * g.mcta + (step & 1) * kTileM + quarter * 32 + lane;
       if (q >= g.L) return -1;
       const unsigned uq = (unsigned)q, n = uq / (unsigned)g.IMG, rem = uq - n * (unsigned)g.IMG;
       const unsigned y = rem / (unsigned)g.P, x = rem - y * (unsigned)g.P;
@@ -1121,7 +1202,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
         tre.stamp();                                             // tile written
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
       }
     }
     if (GRAMF && a.dbeta != nullptr) {
@@ -1137,7 +1218,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kc_dgrad_persistent_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kDgMmaWarp0) tmem_dealloc(tmem_base, 512u);
+  if (PAIR) { cluster_arrive(); cluster_wait(); }        // both CTAs are done with the pair's tensor memory and shared memory
+  if (warp == kDgMmaWarp0) { if (PAIR) tmem_dealloc_pair(tmem_base, 512u); else tmem_dealloc(tmem_base, 512u); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1267,7 +1349,6 @@ __global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constan
   const bool has_base = d.act != KC_ACT_NONE;
   const int wb = nb + (has_base ? 1 : 0);
   const long long vec_per_ntile = g.wimg_bytes_per_ntile / 16;
-  const long long full_chunk = (long long)T * kPL * g.ntile;
   const long long per_chunk = (long long)kPL * g.ntile;
   const long long total = (long long)g.n_ntiles * g.nbc * per_chunk;
   for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
@@ -1288,8 +1369,11 @@ __global__ void __launch_bounds__(256) kc_pack_dgrad_kernel(const __grid_constan
         src[e] = jj < nb ? a.w_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, jj, d.cin, nb)) * T
                          : a.w_base + ((long long)co * d.cin + c) * T;
     }
-    uint4* dst = a.out + (long long)nt * vec_per_ntile + (long long)bq * full_chunk + (long long)kc * g.ntile + nl;
-    const long long tstride = (long long)ncols * g.ntile;
+    // CTA pairs: the image of an N tile is two halves of nw = ntile / 2 rows, each laid out like a whole image of nw rows
+    const int nw = g.pair ? g.ntile / 2 : g.ntile, half = nl / nw, nlh = nl - half * nw;
+    uint4* dst = a.out + (long long)nt * vec_per_ntile + (long long)half * (vec_per_ntile / 2) + (long long)bq * ((long long)T * kPL * nw) +
+                 (long long)kc * nw + nlh;
+    const long long tstride = (long long)ncols * nw;
     for (int t0 = 0; t0 < T; t0 += kPackMaxT) {
       float f[kPackMaxT][8];
 #pragma unroll
@@ -1447,7 +1531,11 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
     const int SS = g->P < seglen ? g->P : seglen;
     const int nrows = (d->kh - 1) * SS + seglen;
     const int plane_bytes = nrows * 16 + 16;
-    const size_t btap = (size_t)kPL * ntile * 16;
+    static const int pair_enabled = []() { const char* e = getenv("KANCONV_DGRAD_PAIR"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+    // pairs pay off where the kernel is bound by the MMA rate (>= 4 K chunks per tile, i.e. cout >= 128); with fewer chunks
+    // the epilogue sets the pace and coupling two CTAs only adds hand-over latency (64 -> 64 @224: 7 % slower)
+    const int pair = pair_enabled && (long long)((g->L + mcta - 1) / mcta) >= 2 && planes >= 4 * kPL ? 1 : 0;
+    const size_t btap = (size_t)kPL * (pair ? ntile / 2 : ntile) * 16;      // per CTA
     const size_t fixed0 = (size_t)kDgBars * 8 + 16 + sizeof(KcBasisCtx) + 128;
     if (d->kh * kPL <= 32) {
       // weight ring granularity, coarsest first: a whole 32-cout chunk (all taps) per stage, a filter row, a single tap -
@@ -1462,7 +1550,7 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
         if (fixed + cand_min[ci] * bstage > kSmemLimit) continue;
         int bst = (int)((kSmemLimit - fixed) / bstage);
         if (bst > kMaxBStages) bst = kMaxBStages;
-        g->persistent = 1; g->cpt = cpt; g->ntile = ntile; g->n_ntiles = (d->cin + cpt - 1) / cpt;
+        g->persistent = 1; g->pair = pair; g->cpt = cpt; g->ntile = ntile; g->n_ntiles = (d->cin + cpt - 1) / cpt;
         g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps; g->na = na;
         g->bstages = bst; g->mtiles = (g->L + mcta - 1) / mcta; g->smem_bytes = fixed + bst * bstage; g->tmem_cols = 512;
         g->wimg_bytes_per_ntile = (long long)T * ntile * 16 * planes;
@@ -1497,21 +1585,27 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
   g->ntile = round_up((d->cout + want_tiles - 1) / want_tiles, 16);
   g->n_ntiles = (d->cout + g->ntile - 1) / g->ntile;
   const int kcores = (has_base ? (g->nbc - 1) * kPL + g->last_base_cols : 0) + g->nsc * kPL;
-  // Pointwise layers: persistent GEMM over the saved basis rows (see kc_dgrad_persistent_kernel, FAM 2)
+  // Pointwise layers, and stem layers with <= 8 input channels (an RGB image): persistent GEMM over the basis rows of a pre-pass
+  // (see kc_dgrad_persistent_kernel, FAM 2).  Both have so little MMA work per position that the fused kernel's CTA (evaluate,
+  // multiply, store, one after the other) is latency-bound; the persistent kernel overlaps the epilogue of a tile with the
+  // MMAs of the next one, and the rows (18 B per position and channel) are what the weight gradient reads anyway.
   long long Lw = 0;
   int splanes = 0, bplanes = 0;
-  if (T == 1 && kc_tc_wgrad_phi_layout(d, &Lw, &splanes, &bplanes) == KC_OK && Lw == g->L) {
+  static const int stem_enabled = []() { const char* e = getenv("KANCONV_STEM_FROM_PHI"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  const bool stem = stem_enabled && T > 1 && d->cin <= 8 && d->kh * kPL <= 32 && d->stride_h == 1 && d->stride_w == 1;
+  if ((T == 1 || stem) && kc_tc_wgrad_phi_layout(d, &Lw, &splanes, &bplanes) == KC_OK && Lw == g->L) {
     const int ntile = d->cout >= 128 ? 128 : round_up(d->cout, 16);
     const int mcta = 2 * kTileM;
-    const int seglen = mcta, SS = g->P < seglen ? g->P : seglen, nrows = seglen;
+    const int seglen = T == 1 ? mcta : round_up(mcta + d->kw - 1, 8), SS = g->P < seglen ? g->P : seglen;
+    const int nrows = (d->kh - 1) * SS + seglen;
     const int plane_bytes = nrows * 16 + 16;
-    const size_t btap = (size_t)kPL * ntile * 16;
+    const size_t btap = (size_t)kPL * ntile * 16 * (T == 1 ? 1 : T);      // stem: all taps of a chunk per weight stage
     const size_t fixed = (size_t)kDgBars * 8 + 16 + sizeof(KcBasisCtx) + 128 + (size_t)3 * kPL * plane_bytes;
-    int bst = (int)((kSmemLimit - fixed) / btap);
+    int bst = fixed < kSmemLimit ? (int)((kSmemLimit - fixed) / btap) : 0;
     if (bst > kMaxBStages) bst = kMaxBStages;
-    if (bst >= 4) {
+    if (bst >= (T == 1 ? 4 : 2)) {
       g->from_phi = 1; g->persistent = 1; g->ntile = ntile; g->n_ntiles = (d->cout + ntile - 1) / ntile;
-      g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = 1; g->na = 3;
+      g->nsub = 2; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = T == 1 ? 1 : T; g->na = 3;
       g->bstages = bst; g->mtiles = (g->L + mcta - 1) / mcta; g->smem_bytes = fixed + bst * btap; g->tmem_cols = 512;
       g->wimg_bytes_per_ntile = (long long)T * ntile * 16 * kcores;
       g->fast_cubic = kc_knots_uniform_cubic(d, &g->t0, &g->inv_h) ? 1 : 0;
@@ -1609,6 +1703,25 @@ __global__ void __launch_bounds__(128, 1) kc_umma_selftest_kernel(int mode, floa
 // =========================================================================================================
 // C ABI
 // =========================================================================================================
+template <int FAM, bool PAIR>
+cudaError_t launch_dgrad(const TcFwdArgs& a, unsigned nctas, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kc_dgrad_persistent_kernel<FAM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nctas, 1, 1);
+  cfg.blockDim = dim3(kDgThreads, 1, 1);
+  cfg.dynamicSmemBytes = a.g.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2u : 1u;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kc_dgrad_persistent_kernel<FAM, PAIR>, a);
+}
+
 extern "C" int kc_tc_supported(const kc_desc* d) {
   if (kc_validate_desc(d) != KC_OK) return 0;
   TcGeom g;
@@ -1646,6 +1759,18 @@ int kc_tc_flat_layout(const kc_desc* d, int* P, int* IMG, long long* L, int* cq)
   return KC_OK;
 }
 
+// CTAs of the persistent dgrad launch: one per SM, or one per tile when there are fewer tiles (pairs: an even number, one
+// pair per two neighbouring position tiles).
+unsigned tc_dgrad_grid(const TcGeom& g) {
+  const long long sms = kc_sm_count();
+  if (g.pair) {
+    const long long npairs = ((g.mtiles + 1) / 2) * g.n_ntiles;
+    return (unsigned)(2 * (npairs < sms / 2 ? npairs : sms / 2));
+  }
+  const long long ntiles = g.mtiles * g.n_ntiles;
+  return (unsigned)(ntiles < sms ? ntiles : sms);
+}
+
 // GRAM only: floats of the `dbeta` buffer (KC_MAX_BASIS results + one partial row per thread block / epilogue warp).
 extern "C" size_t kc_dbeta_floats(const kc_desc* d, int tc) {
   if (kc_validate_desc(d) != KC_OK || d->basis != KC_BASIS_GRAM) return 0;
@@ -1654,8 +1779,7 @@ extern "C" size_t kc_dbeta_floats(const kc_desc* d, int tc) {
     TcGeom g;
     if (tc_dgrad_geometry(d, &g) != KC_OK) return 0;
     if (g.persistent) {           // one row per (CTA, epilogue warp) of the persistent grid
-      const long long ntiles = g.mtiles * g.n_ntiles, sms = kc_sm_count();
-      rows = (ntiles < sms ? ntiles : sms) * kDgEpiWarps;
+      rows = (long long)tc_dgrad_grid(g) * kDgEpiWarps;
     } else {
       rows = g.mtiles * g.n_ntiles * 16;
     }
@@ -1745,8 +1869,8 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
     a.phi_base_plane0 = splanes;
     const int sms = kc_sm_count();
     const long long ntiles = g.mtiles * g.n_ntiles;
-    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    kc_dgrad_persistent_kernel<2><<<(unsigned)(ntiles < sms ? ntiles : sms), kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kc_dgrad_persistent_kernel<2, false><<<(unsigned)(ntiles < sms ? ntiles : sms), kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
     KC_LAUNCH_CHECK("kc_tc_kernel<fwd>");
     return KC_OK;
   }
@@ -1758,12 +1882,8 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
     if (Lw != g.L) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_conv_fwd_tc: forward / wgrad flat lengths differ");
     a.phi_out = (unsigned char*)phi_out;
     a.phi_base_plane0 = splanes;
-    // planes the weight-gradient kernel reads but this kernel does not produce (channel padding): zero them
-    const int wrote_s = g.nsc * kPL, wrote_b = d->act != KC_ACT_NONE ? g.ngroups : 0;
-    if (splanes > wrote_s)
-      KC_CUDA_CHECK(cudaMemsetAsync(a.phi_out + (size_t)wrote_s * g.L * 16, 0, (size_t)(splanes - wrote_s) * g.L * 16, (cudaStream_t)stream));
-    if (bplanes > wrote_b)
-      KC_CUDA_CHECK(cudaMemsetAsync(a.phi_out + (size_t)(splanes + wrote_b) * g.L * 16, 0, (size_t)(bplanes - wrote_b) * g.L * 16, (cudaStream_t)stream));
+    // the planes behind the channels this kernel expands (padding of the weight gradient's M = 128 tiles) stay unwritten: the
+    // weight-gradient kernel zero-fills them in shared memory instead of reading them (WgGeom::vs_planes / vb_planes)
   }
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
@@ -1790,23 +1910,16 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
   a.dzf = (const unsigned char*)workspace; a.cq = g.Cp; a.dx_base = dx_base; a.dx_basis = dx_basis;
   a.dbeta = (d->basis == KC_BASIS_GRAM) ? dbeta : nullptr;
   if (g.persistent) {
-    const int sms = kc_sm_count();
-    const long long ntiles = g.mtiles * g.n_ntiles;
-    const unsigned nctas = (unsigned)(ntiles < sms ? ntiles : sms);
-    if (g.fast_cubic) {
-      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-      kc_dgrad_persistent_kernel<1><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
-    } else if (d->basis == KC_BASIS_GRAM) {
-      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-      kc_dgrad_persistent_kernel<3><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
-      KC_LAUNCH_CHECK("kc_dgrad_persistent_kernel");
-      if (a.dbeta != nullptr) return kc_dbeta_reduce(a.dbeta, (long long)nctas * kDgEpiWarps, stream);
-      return KC_OK;
-    } else {
-      KC_CUDA_CHECK(cudaFuncSetAttribute(kc_dgrad_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-      kc_dgrad_persistent_kernel<0><<<nctas, kDgThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
-    }
+    const unsigned nctas = tc_dgrad_grid(g);
+    const int fam = g.fast_cubic ? 1 : d->basis == KC_BASIS_GRAM ? 3 : 0;
+    cudaError_t e;
+    if (g.pair) e = fam == 1 ? launch_dgrad<1, true>(a, nctas, (cudaStream_t)stream) : fam == 3 ? launch_dgrad<3, true>(a, nctas, (cudaStream_t)stream)
+                                                                                         : launch_dgrad<0, true>(a, nctas, (cudaStream_t)stream);
+    else e = fam == 1 ? launch_dgrad<1, false>(a, nctas, (cudaStream_t)stream) : fam == 3 ? launch_dgrad<3, false>(a, nctas, (cudaStream_t)stream)
+                                                                                : launch_dgrad<0, false>(a, nctas, (cudaStream_t)stream);
+    KC_CUDA_CHECK(e);
     KC_LAUNCH_CHECK("kc_dgrad_persistent_kernel");
+    if (fam == 3 && a.dbeta != nullptr) return kc_dbeta_reduce(a.dbeta, (long long)nctas * kDgEpiWarps, stream);
     return KC_OK;
   }
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));

@@ -41,6 +41,8 @@ struct WgGeom {
   int pair;                     // 1 = CTA pairs (tcgen05 cta_group::2): two units of a cout tile share the dz stage, each CTA loads half
   int units_ct, upc;            // units per cout tile (nchunks * kh), the same rounded up to an even number (grid.x = n_ct * upc)
   int bplanes_cta;              // dz planes a CTA loads per stage (bplanes, or bplanes / 2 in a pair)
+  int vs_planes, vb_planes;     // spline / base planes of phi that hold data (channels < cin rounded up to 8); the planes behind
+                                // them exist only as padding of the M = 128 tiles: never written, never read (zero-filled in smem)
   int arows, aplane_bytes;      // Phi rows per stage (kKS + kw - 1, padded), plane pitch
   int bplanes, bplane_bytes;
   int stages, stage_bytes, a_bytes;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
     const int cb = (chunk - g.nsc) * 128;
 #pragma unroll 4
     for (int pl = 0; pl < 16; ++pl) {
+      if ((chunk - g.nsc) * 16 + pl >= g.vb_planes) break;
       float f[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
     }
 #pragma unroll
     for (int pl = 0; pl < 16; ++pl) {
+      if (chunk * 16 + pl >= g.vs_planes) break;
       const bool ok = inside && chunk * g.cps + pl < d.cin;
       uint4 v;
       if (g.fast_cubic) v = cubic8(xv[pl], g.t0, g.inv_h, Bs.nparams - 1, ok);
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(256) kc_phi_flat_kernel(const __grid_constant_
     }
   } else {
     for (int pl = 0; pl < 16; ++pl) {
+      if (chunk * 16 + pl >= g.vs_planes) break;
       const int c = chunk * g.cps + pl * 2;
       uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
       if (inside && c < d.cin) lo = basis4w(Bs, __ldg(a.x_basis + off + (long long)c * HW));
@@ -171,8 +176,11 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     const int it = tid + kProdW * k;
     arow[k] = it % g.arows;
     const int apl = it / g.arows;
-    adst[k] = (it < nAitems) ? (uint32_t)(apl * g.aplane_bytes + arow[k] * 16) : 0xffffffffu;
-    aplane[k] = (it < nAitems && !dummy) ? a.phi + ((long long)(chunk * 16 + apl) * g.L) * 16 : nullptr;
+    // planes without data (channel padding of the tile, or the dummy partner of a pair) are zeroed once by the kernel prologue
+    // and never copied
+    const bool aok = !dummy && (chunk < g.nsc ? chunk * 16 + apl < g.vs_planes : (chunk - g.nsc) * 16 + apl < g.vb_planes);
+    adst[k] = (it < nAitems && aok) ? (uint32_t)(apl * g.aplane_bytes + arow[k] * 16) : 0xffffffffu;
+    aplane[k] = a.phi + ((long long)(chunk * 16 + (it < nAitems ? apl : 0)) * g.L) * 16;
     brow[k] = it % KS;
     const int bpl = it / KS;
     const bool bok = it < nBitems && (bpl0 + bpl) * 8 < g.cq;
@@ -195,10 +203,7 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     if (q0 >= 0 && q0 + g.arows <= g.L && m0 + KS <= g.L) {     // interior block: no per-row range checks
 #pragma unroll
       for (int k = 0; k < kItems; ++k) {
-        if (adst[k] != 0xffffffffu) {
-          const bool ok = aplane[k] != nullptr;
-          cp_async16(stage + adst[k], ok ? aplane[k] + (q0 + arow[k]) * 16 : a.phi, ok ? 16u : 0u);
-        }
+        if (adst[k] != 0xffffffffu) cp_async16(stage + adst[k], aplane[k] + (q0 + arow[k]) * 16, 16u);
         if (bdst[k] != 0xffffffffu) {
           const bool ok = bplane[k] != nullptr;
           cp_async16(stage + bdst[k], ok ? bplane[k] + (m0 + brow[k]) * 16 : a.dzf, ok ? 16u : 0u);
@@ -209,7 +214,7 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
       for (int k = 0; k < kItems; ++k) {
         if (adst[k] != 0xffffffffu) {
           const long long q = q0 + arow[k];
-          const bool ok = aplane[k] != nullptr && q >= 0 && q < g.L;
+          const bool ok = q >= 0 && q < g.L;
           cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
         }
         if (bdst[k] != 0xffffffffu) {
@@ -290,6 +295,19 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   }
   if (warp == kMmaWarpW) { if (PAIR) tmem_alloc_pair(tmem_ptr, (uint32_t)g.tmem_cols); else tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols); }
   kc_load_basis_ctx(B, d, a.beta);
+  {
+    // Phi planes of this unit that hold no data (channel padding / dummy partner): zero them in every stage, once
+    const int chunk_planes = dummy ? 0 : chunk < g.nsc ? g.vs_planes - chunk * 16 : g.vb_planes - (chunk - g.nsc) * 16;
+    const int nvalid = chunk_planes < 0 ? 0 : chunk_planes > 16 ? 16 : chunk_planes;
+    if (nvalid < 16) {
+      const int vec_per_plane = g.aplane_bytes / 16, nvec = (16 - nvalid) * vec_per_plane;
+      for (int st = 0; st < g.stages; ++st) {
+        uint4* base = reinterpret_cast<uint4*>(smem + (size_t)st * g.stage_bytes + (size_t)nvalid * g.aplane_bytes);
+        for (int i = threadIdx.x; i < nvec; i += kThreadsW) base[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (PAIR) { cluster_arrive(); cluster_wait(); }        // the peer's barriers are initialised before anything arrives on them
@@ -493,6 +511,13 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->nsc = (d->cin + g->cps - 1) / g->cps;
   g->nbc = has_base ? (d->cin + 127) / 128 : 0;
   g->nchunks = g->nsc + g->nbc;
+  {
+    const int Cp = round_up_w(d->cin, 8);            // channels the forward kernel expands (its k-cores hold 8 channels)
+    g->vs_planes = d->nb > 4 ? Cp : Cp / 2;
+    g->vb_planes = has_base ? round_up_w(Cp / 8, 2) : 0;
+    if (g->vs_planes > g->nsc * 16) g->vs_planes = g->nsc * 16;
+    if (g->vb_planes > g->nbc * 16) g->vb_planes = g->nbc * 16;
+  }
   int nmax = (512 / d->kw) / 16 * 16;
   if (nmax > 192) nmax = 192;            // 64 positions x (ntile / 8) dz planes must fit the producer mapping (3 vectors per thread)
   int want = (g->cq + nmax - 1) / nmax;
