@@ -41,6 +41,9 @@ struct WgGeom {
   int pair;                     // 1 = CTA pairs (tcgen05 cta_group::2): two units of a cout tile share the dz stage, each CTA loads half
   int units_ct, upc;            // units per cout tile (nchunks * kh), the same rounded up to an even number (grid.x = n_ct * upc)
   int bplanes_cta;              // dz planes a CTA loads per stage (bplanes, or bplanes / 2 in a pair)
+  int merged;                   // stem layers (kh * (cin + base planes) <= 16): ONE unit per cout tile whose 16 Phi planes are
+                                // (filter row r, channel | base plane) - all filter rows and both branches in one M = 128 tile
+  int mnv;                      // merged: planes per filter row = cin + base planes
   int vs_planes, vb_planes;     // spline / base planes of phi that hold data (channels < cin rounded up to 8); the planes behind
                                 // them exist only as padding of the M = 128 tiles: never written, never read (zero-filled in smem)
   int arows, aplane_bytes;      // Phi rows per stage (kKS + kw - 1, padded), plane pitch
@@ -168,6 +171,7 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
   const int bpl0 = ct * g.bplanes + (PAIR ? (int)rank * g.bplanes_cta : 0);        // first dz plane of this CTA
   const long long qoff = blk0 * KS + (long long)(r - d.pad_h) * g.P - d.pad_w;
   int arow[kItems], brow[kItems];
+  int ashift[kItems];                                       // merged units: extra row offset of the item's filter row
   uint32_t adst[kItems], bdst[kItems];                      // byte offsets inside a stage, 0xffffffff = no item
   const unsigned char* aplane[kItems];
   const unsigned char* bplane[kItems];
@@ -178,9 +182,17 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     const int apl = it / g.arows;
     // planes without data (channel padding of the tile, or the dummy partner of a pair) are zeroed once by the kernel prologue
     // and never copied
-    const bool aok = !dummy && (chunk < g.nsc ? chunk * 16 + apl < g.vs_planes : (chunk - g.nsc) * 16 + apl < g.vb_planes);
+    bool aok = !dummy && (chunk < g.nsc ? chunk * 16 + apl < g.vs_planes : (chunk - g.nsc) * 16 + apl < g.vb_planes);
+    int src_plane = chunk * 16 + (it < nAitems ? apl : 0);
+    ashift[k] = 0;
+    if (g.merged) {                                         // plane apl = (filter row, channel c < cin | base plane)
+      const int mr = apl / g.mnv, v = apl - mr * g.mnv;
+      aok = mr < d.kh;
+      src_plane = v < d.cin ? v : g.nsc * 16 + (v - d.cin);
+      ashift[k] = aok ? mr * g.P : 0;
+    }
     adst[k] = (it < nAitems && aok) ? (uint32_t)(apl * g.aplane_bytes + arow[k] * 16) : 0xffffffffu;
-    aplane[k] = a.phi + ((long long)(chunk * 16 + (it < nAitems ? apl : 0)) * g.L) * 16;
+    aplane[k] = a.phi + ((long long)src_plane * g.L) * 16;
     brow[k] = it % KS;
     const int bpl = it / KS;
     const bool bok = it < nBitems && (bpl0 + bpl) * 8 < g.cq;
@@ -200,10 +212,10 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
     trp.stamp();
     unsigned char* stage = smem + (size_t)st * g.stage_bytes;
     const long long q0 = qoff + (long long)it * KS, m0 = (blk0 + it) * KS;
-    if (q0 >= 0 && q0 + g.arows <= g.L && m0 + KS <= g.L) {     // interior block: no per-row range checks
+    if (q0 >= 0 && q0 + (g.merged ? (long long)(d.kh - 1) * g.P : 0) + g.arows <= g.L && m0 + KS <= g.L) {     // interior block: no per-row range checks
 #pragma unroll
       for (int k = 0; k < kItems; ++k) {
-        if (adst[k] != 0xffffffffu) cp_async16(stage + adst[k], aplane[k] + (q0 + arow[k]) * 16, 16u);
+        if (adst[k] != 0xffffffffu) cp_async16(stage + adst[k], aplane[k] + (q0 + ashift[k] + arow[k]) * 16, 16u);
         if (bdst[k] != 0xffffffffu) {
           const bool ok = bplane[k] != nullptr;
           cp_async16(stage + bdst[k], ok ? bplane[k] + (m0 + brow[k]) * 16 : a.dzf, ok ? 16u : 0u);
@@ -213,7 +225,7 @@ __device__ __forceinline__ void wg_produce(const WgArgs& a, unsigned char* smem,
 #pragma unroll
       for (int k = 0; k < kItems; ++k) {
         if (adst[k] != 0xffffffffu) {
-          const long long q = q0 + arow[k];
+          const long long q = q0 + ashift[k] + arow[k];
           const bool ok = q >= 0 && q < g.L;
           cp_async16(stage + adst[k], ok ? aplane[k] + q * 16 : a.phi, ok ? 16u : 0u);
         }
@@ -269,7 +281,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   int unit, ct, chunk, r;
   bool dummy = false;
-  if (PAIR) {
+  if (g.merged) {
+    unit = ct = blockIdx.x; chunk = 0; r = 0;
+  } else if (PAIR) {
     ct = blockIdx.x / g.upc;
     const int u = blockIdx.x - ct * g.upc;
     dummy = u >= g.units_ct;
@@ -297,7 +311,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) kc_wgrad_tc_kernel(const __grid_
   kc_load_basis_ctx(B, d, a.beta);
   {
     // Phi planes of this unit that hold no data (channel padding / dummy partner): zero them in every stage, once
-    const int chunk_planes = dummy ? 0 : chunk < g.nsc ? g.vs_planes - chunk * 16 : g.vb_planes - (chunk - g.nsc) * 16;
+    const int chunk_planes = dummy      ? 0
+                             : g.merged ? d.kh * g.mnv
+                             : chunk < g.nsc ? g.vs_planes - chunk * 16 : g.vb_planes - (chunk - g.nsc) * 16;
     const int nvalid = chunk_planes < 0 ? 0 : chunk_planes > 16 ? 16 : chunk_planes;
     if (nvalid < 16) {
       const int vec_per_plane = g.aplane_bytes / 16, nvec = (16 - nvalid) * vec_per_plane;
@@ -420,19 +436,27 @@ __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_kernel(const __grid_co
     const int m = (int)(rest % 128); rest /= 128;
     const int s = (int)(rest % d.kw);
     const int unit = (int)(rest / d.kw);
-    const int r = unit % d.kh;
-    const int chunk = (unit / d.kh) % g.nchunks;
-    const int ct = unit / (d.kh * g.nchunks);
+    int r = unit % d.kh;
+    int chunk = (unit / d.kh) % g.nchunks;
+    int ct = unit / (d.kh * g.nchunks);
+    int mm = m;                                  // row inside the (chunk, r) tile
+    if (g.merged) {                              // row m = 8 x plane (r, v) + j: v < cin a spline plane, else a base plane
+      ct = unit;
+      const int apl = m / 8, mr = apl / g.mnv, v = apl - mr * g.mnv;
+      if (mr >= d.kh) continue;
+      r = mr;
+      if (v < d.cin) { chunk = 0; mm = v * 8 + (m & 7); } else { chunk = g.nsc; mm = (v - d.cin) * 8 + (m & 7); }
+    }
     const int co = ct * g.ntile + n;
     if (co >= d.cout) continue;
     float* dst;
     if (chunk < g.nsc) {
       const int nbp = nb > 4 ? 8 : 4;
-      const int c = chunk * g.cps + m / nbp, j = m % nbp;
+      const int c = chunk * g.cps + mm / nbp, j = mm % nbp;
       if (c >= d.cin || j >= nb) continue;
       dst = dw_basis + ((long long)co * d.cin * nb + kc_wbasis_index(d.basis, c, j, d.cin, nb)) * T + r * d.kw + s;
     } else {
-      const int c = (chunk - g.nsc) * 128 + m;
+      const int c = (chunk - g.nsc) * 128 + mm;
       if (c >= d.cin) continue;
       dst = dw_base + ((long long)co * d.cin + c) * T + r * d.kw + s;
     }
@@ -524,10 +548,20 @@ int wgrad_geometry(const kc_desc* d, WgGeom* g) {
   g->ntile = round_up_w((g->cq + want - 1) / want, 16);
   g->n_ct = (g->cq + g->ntile - 1) / g->ntile;
   g->units = g->n_ct * g->nchunks * d->kh;
+  {
+    // stem layers: every filter row and both branches fit ONE M = 128 tile -> one unit per cout tile instead of nchunks * kh
+    static const int merge_enabled = []() { const char* e = getenv("KANCONV_WGRAD_MERGE"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+    const int nbase = has_base ? (d->cin + 7) / 8 : 0;
+    if (merge_enabled && d->nb > 4 && d->nb <= 8 && d->kh * (d->cin + nbase) <= 16) {
+      g->merged = 1;
+      g->mnv = d->cin + nbase;
+      g->units = g->n_ct;
+    }
+  }
   // CTA pairs (tcgen05 cta_group::2, M = 256): two units of a cout tile share every dz stage and each CTA loads half of it.
   // An M = 128 MMA with N <= 128 is bound by the operand fetch from shared memory (66 / 74 cycles at N = 64 / 128 instead of
   // 32 / 64); the pair halves the B fetch per CTA (43 / 64 cycles, tools/mma_rate_2cta.py).  KANCONV_WGRAD_PAIR=0: single CTAs.
-  g->units_ct = g->nchunks * d->kh;
+  g->units_ct = g->merged ? 1 : g->nchunks * d->kh;
   {
     static const int pair_enabled = []() { const char* e = getenv("KANCONV_WGRAD_PAIR"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
     g->pair = (pair_enabled && g->units_ct >= 2) ? 1 : 0;
@@ -694,7 +728,7 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   // the tile kernel needs enough (cout tile, chunk) pairs to fill the machine; few-channel layers (many splits, few
   // units) keep the element-parallel kernel
   const long long tile_blocks = (long long)((g.ntile + 31) / 32) * 4 * g.n_ct * g.nchunks;
-  if (d->kh * d->kw <= kRedT && (long long)g.n_ct * g.nchunks <= 65535 && tile_blocks >= 2 * kc_sm_count()) {
+  if (!g.merged && d->kh * d->kw <= kRedT && (long long)g.n_ct * g.nchunks <= 65535 && tile_blocks >= 2 * kc_sm_count()) {
     dim3 rgrid((unsigned)(((g.ntile + 31) / 32) * 4), (unsigned)(g.n_ct * g.nchunks));
     kc_wgrad_tc_reduce_tile_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
   } else {
