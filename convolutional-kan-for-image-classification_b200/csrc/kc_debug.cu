@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(576, 1) kc_mma_rate_kernel(int N, int a_lbo, i
 extern "C" int kc_debug_mma_rate(int N, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int iters, int a_rowshift, int nsub,
                                  int commit_every, int writers, int mn_major, float* cycles) {
   float* dev = nullptr;
-  KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
+  KC_CUDA_CHECK(cudaMalloc(&dev, 32 * sizeof(float)));
+  KC_CUDA_CHECK(cudaMemset(dev, 0, 32 * sizeof(float)));
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   kc_mma_rate_kernel<<<1, 576, 160 * 1024>>>(N, a_lbo, a_sbo, b_lbo, b_sbo, iters, a_rowshift, nsub, commit_every, writers, mn_major, dev);
   cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, 32 * sizeof(float), cudaMemcpyDeviceToHost);     // caller passes float[32]
   cudaFree(dev);
   if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate: %s", cudaGetErrorString(e));
   return KC_OK;
@@ -79,14 +80,14 @@ extern "C" int kc_debug_mma_rate(int N, int a_lbo, int a_sbo, int b_lbo, int b_s
 // kernels: nsub accumulators x 2 k-steps per iteration, optional commit per iteration, optional writer warps hammering
 // shared memory with 16-byte stores, optional unaligned A view.
 __global__ void __launch_bounds__(576, 1) kc_mma_rate2_kernel(int N, int mn_major, int iters, int nsub, int commit_each, int writers,
-                                                               int a_shift_rows, float* out) {
+                                                               int a_shift_rows, float* out, const unsigned char* bulk_src, int bulk_streams) {
   extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar, dummy[8];
+  __shared__ __align__(8) uint64_t bar, dummy[8], bbar[4];
   __shared__ uint32_t tmem_ptr;
   __shared__ volatile int done;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1000000); done = 0; fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1000000); for (int i = 0; i < 4; ++i) mbar_init(&bbar[i], 1); done = 0; fence_barrier_init(); }
   if (warp == 17) tmem_alloc(&tmem_ptr, 512);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -120,6 +121,23 @@ __global__ void __launch_bounds__(576, 1) kc_mma_rate2_kernel(int N, int mn_majo
     mbar_wait(&bar, 0);
     long long t1 = clock64();
     if (threadIdx.x == 17 * 32) { out[0] = (float)(t1 - t0) / (float)(iters * nsub * 2); done = 1; }
+  } else if (warp == 16 && bulk_streams > 0 && bulk_src != nullptr) {
+    // bulk_streams (<= 4) cp.async.bulk copies of 4 KB each kept in flight into an unrelated shared-memory region while the
+    // MMAs run (the weight loader of the convolution kernels); out[1] = bytes per clock achieved
+    if (threadIdx.x == 16 * 32) {
+      uint32_t ph[4] = {0, 0, 0, 0};
+      long long n = 0, t0 = clock64();
+      for (int i = 0; i < bulk_streams; ++i) { mbar_arrive_expect_tx(&bbar[i], 4096u); bulk_g2s(sm + 144 * 1024 + i * 4096, bulk_src + i * 4096, 4096u, &bbar[i]); }
+      while (!done) {
+        for (int i = 0; i < bulk_streams; ++i) {
+          mbar_wait(&bbar[i], ph[i]); ph[i] ^= 1u; ++n;
+          mbar_arrive_expect_tx(&bbar[i], 4096u);
+          bulk_g2s(sm + 144 * 1024 + i * 4096, bulk_src + ((n * 4096) & 0xffffff), 4096u, &bbar[i]);
+        }
+      }
+      for (int i = 0; i < bulk_streams; ++i) mbar_wait(&bbar[i], ph[i]);
+      out[1] = (float)(n * 4096) / (float)(clock64() - t0);
+    }
   } else if (warp < writers) {
     uint4* dst = reinterpret_cast<uint4*>(sm + 128 * 1024) + threadIdx.x;
     uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
@@ -219,11 +237,28 @@ extern "C" int kc_debug_mma_rate_2cta(int N, int mn_major, int iters, int nsub, 
   return KC_OK;
 }
 
+extern "C" int kc_debug_mma_rate2_bulk(int N, int mn_major, int iters, int nsub, int commit_each, int writers, int a_shift_rows,
+                                       int bulk_streams, float* cycles2) {
+  float* dev = nullptr;
+  unsigned char* src = nullptr;
+  KC_CUDA_CHECK(cudaMalloc(&dev, 2 * sizeof(float)));
+  KC_CUDA_CHECK(cudaMalloc(&src, (1 << 24) + 65536));
+  KC_CUDA_CHECK(cudaMemset(src, 0x3c, (1 << 24) + 65536));
+  KC_CUDA_CHECK(cudaMemset(dev, 0, 2 * sizeof(float)));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  kc_mma_rate2_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, nsub, commit_each, writers, a_shift_rows, dev, src, bulk_streams);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles2, dev, 2 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dev); cudaFree(src);
+  if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "kc_debug_mma_rate2_bulk: %s", cudaGetErrorString(e));
+  return KC_OK;
+}
+
 extern "C" int kc_debug_mma_rate2(int N, int mn_major, int iters, int nsub, int commit_each, int writers, int a_shift_rows, float* cycles) {
   float* dev = nullptr;
   KC_CUDA_CHECK(cudaMalloc(&dev, sizeof(float)));
   KC_CUDA_CHECK(cudaFuncSetAttribute(kc_mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  kc_mma_rate2_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, nsub, commit_each, writers, a_shift_rows, dev);
+  kc_mma_rate2_kernel<<<1, 576, 160 * 1024>>>(N, mn_major, iters, nsub, commit_each, writers, a_shift_rows, dev, nullptr, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(cycles, dev, sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(dev);

@@ -49,7 +49,7 @@ constexpr int kPL = 4;                 // k-cores ("planes") per chunk: K = 32 p
 constexpr int kTileM = 128;
 constexpr int kMaxA = 3;
 constexpr int kMaxBStages = 16;
-constexpr int kNumBars = 2 * kMaxA + 2 * kMaxBStages + 1;
+constexpr int kNumBars = 3 * kMaxA + 3 * kMaxBStages + 1;
 constexpr size_t kSmemLimit = 227 * 1024;
 
 struct TcGeom {
@@ -246,14 +246,20 @@ __device__ __forceinline__ void issue_step(uint32_t tmem_base, uint32_t ntile, u
 // ---------------------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE>
+// PAIR (forward only): the two CTAs of a cluster own two neighbouring position tiles and the same N tile and run
+// tcgen05 cta_group::2 MMAs (M = 256): each CTA evaluates its own basis rows and loads HALF of every weight stage (ntile / 2 of
+// the N rows), the leader CTA issues for both.  Narrow tiles stop being bound by the operand fetch (N = 64: 43 instead of 66
+// cycles, N = 128: 64 instead of 74), the weight stream from L2 halves, and a whole chunk of taps fits one ring stage.
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_constant__ TcFwdArgs a) {
+  static_assert(!(PAIR && MODE != kModeFwd), "pairs: forward only");
   extern __shared__ __align__(128) unsigned char smem[];
   const kc_desc& d = a.d;
   const TcGeom& g = a.g;
   // ---- carve shared memory ---------------------------------------------------------------------------
   const int abuf_bytes = kPL * g.plane_bytes;
-  const int btap_bytes = kPL * g.ntile * 16;
+  const int nw = PAIR ? g.ntile / 2 : g.ntile;   // weight rows (of the MMA's N) this CTA holds
+  const int btap_bytes = kPL * nw * 16;
   const int bstage_bytes = g.tps * btap_bytes;
   unsigned char* abuf0 = smem;
   unsigned char* bst0 = abuf0 + g.na * abuf_bytes;
@@ -263,7 +269,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
   uint64_t* b_full = bars + 2 * kMaxA;           // [kMaxBStages]
   uint64_t* b_empty = b_full + kMaxBStages;      // [kMaxBStages]
   uint64_t* acc_full = b_empty + kMaxBStages;
+  uint64_t* pa_full = acc_full + 1;              // [kMaxA]        pair, leader: the peer's basis rows are in place
+  uint64_t* pb_full = pa_full + kMaxA;           // [kMaxBStages]  pair, leader: the peer's half of a weight stage has landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   KcBasisCtx* B = reinterpret_cast<KcBasisCtx*>(reinterpret_cast<unsigned char*>(tmem_ptr) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,15 +286,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     const uint32_t nmw = g.nsub >= 2 ? 2u : 1u;      // issuing warps
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], kProdThreads); mbar_init(&a_empty[i], nmw); }
-    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], nmw); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], kProdThreads); mbar_init(&a_empty[i], nmw); mbar_init(&pa_full[i], 1); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], nmw); mbar_init(&pb_full[s], 1); }
     mbar_init(acc_full, nmw);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols);
+  if (warp == kMmaWarp) { if (PAIR) tmem_alloc_pair(tmem_ptr, (uint32_t)g.tmem_cols); else tmem_alloc(tmem_ptr, (uint32_t)g.tmem_cols); }
   kc_load_basis_ctx(B, d, a.beta);        // ends with __syncthreads()
   tc_fence_before();
   __syncthreads();
+  if (PAIR) { cluster_arrive(); cluster_wait(); }        // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -481,16 +491,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       if (++buf == g.na) { buf = 0; aphase ^= 1; }
     }
   }
-  if (warp >= kMmaWarp && warp - kMmaWarp < (g.nsub >= 2 ? 2 : 1)) {
+  if (PAIR && rank != 0 && warp >= kMmaWarp) {
+    // ================================ peer CTA of a pair: relay "in place" to the leader, which issues the MMAs ========
+    // warp 17: basis-row buffers, warp 18: weight stages
+    if (warp == kMmaWarp) {
+      int buf = 0;
+      uint32_t aphase = 0;
+      for (int pq = 0; pq < nchunks; ++pq) {
+        mbar_wait(&a_full[buf], aphase);
+        if (lane == 0) mbar_arrive_cluster(&pa_full[buf], 0);
+        __syncwarp();
+        if (++buf == g.na) { buf = 0; aphase ^= 1; }
+      }
+    } else if (warp == kMmaWarp + 1) {
+      int stage = 0;
+      uint32_t bphase = 0;
+      for (int pq = 0; pq < nchunks; ++pq)
+        for (int t = 0; t < T; t += g.tps) {
+          mbar_wait(&b_full[stage], bphase);
+          if (lane == 0) mbar_arrive_cluster(&pb_full[stage], 0);
+          __syncwarp();
+          if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
+        }
+    }
+  } else if (warp >= kMmaWarp && warp - kMmaWarp < (g.nsub >= 2 ? 2 : 1)) {
     // ================================ MMA issuers =====================================================
     // The whole warp walks the pipeline with warp-uniform state; one elected lane issues tcgen05.mma / commit.
     // Per MMA only the 14-bit start-address fields of the two descriptors change (a few uniform integer adds).
     {
-      const uint32_t idesc = make_idesc_bf16(kTileM, g.ntile, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTileM : kTileM, g.ntile, 0, 0);
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version = 1
       const uint32_t a_lo_c = ((uint32_t)(g.plane_bytes >> 4) & 0x3FFFu) << 16;         // LBO = plane pitch
-      const uint32_t b_lo_c = ((uint32_t)(g.ntile) & 0x3FFFu) << 16;                    // LBO = ntile * 16 B
-      const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * g.ntile);
+      const uint32_t b_lo_c = ((uint32_t)(nw) & 0x3FFFu) << 16;                         // LBO = (weight rows held) * 16 B
+      const uint32_t a_k2 = (uint32_t)(2 * g.plane_bytes) >> 4, b_k2 = (uint32_t)(2 * nw);
       const uint32_t abuf_u = smem_u32(abuf0) >> 4, bst_u = smem_u32(bst0) >> 4;
       const uint32_t abuf_sz = (uint32_t)abuf_bytes >> 4, bst_sz = (uint32_t)bstage_bytes >> 4;
       const int ntile = g.ntile, kw = d.kw, SS = g.SS, tps = g.tps;
@@ -503,15 +536,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       for (int pq = 0; pq < nchunks; ++pq) {
         const int q = mseq.next();
         const int nk2 = chunk_cols(g, q) >> 1;
-        const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * ntile);      // 16-byte units per tap image
+        const uint32_t btap_u = (uint32_t)(chunk_cols(g, q) * nw);         // 16-byte units per tap image
         trm.stamp();                                 // before a_full wait
         mbar_wait(&a_full[buf], aphase);
+        if (PAIR) mbar_wait_cluster(&pa_full[buf], aphase);
         tc_fence_after();
         trm.stamp();                                 // a_full acquired
         uint32_t arow = abuf_u + (uint32_t)buf * abuf_sz;      // (address >> 4) of tap (0,0), sub-tile 0, k2 = 0
         int s = 0;
         for (int t = 0; t < T; t += tps) {
           mbar_wait(&b_full[stage], bphase);
+          if (PAIR) mbar_wait_cluster(&pb_full[stage], bphase);
           tc_fence_after();
           trm.stamp();                               // b_full acquired
           uint32_t b_lo = b_lo_c + bst_u + (uint32_t)stage * bst_sz;
@@ -520,28 +555,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
           for (int tt = 0; tt < tps; ++tt) {
             const uint32_t first = (pq | (t + tt)) != 0 ? 1u : 0u;
             if (leader) {
-              if (nsub == 2) issue_step<2>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
-              else issue_step<1>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
+              if (nsub == 2) issue_step<2, PAIR>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
+              else issue_step<1, PAIR>(tmem_base, (uint32_t)ntile, a_lo_c + arow, b_lo, a_k2, b_k2, desc_hi, idesc, first, two, mw, nmw);
             }
             b_lo += btap_u;
             // next tap: one position right, or first position of the next filter row (SS rows down)
             if (++s == kw) { s = 0; arow += (uint32_t)(SS - (kw - 1)); } else { arow += 1u; }
           }
           if (leader) {
-            tc_commit(&b_empty[stage]);
-            if (t + tps >= T) tc_commit(&a_empty[buf]);
+            if (PAIR) {
+              tc_commit_pair(&b_empty[stage]);
+              if (t + tps >= T) tc_commit_pair(&a_empty[buf]);
+            } else {
+              tc_commit(&b_empty[stage]);
+              if (t + tps >= T) tc_commit(&a_empty[buf]);
+            }
           }
           __syncwarp();
           if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
         }
         if (++buf == g.na) { buf = 0; aphase ^= 1; }
       }
-      if (elect_one_sync()) tc_commit(acc_full);
+      if (elect_one_sync()) { if (PAIR) tc_commit_pair(acc_full); else tc_commit(acc_full); }
     }
     __syncwarp();
   } else if (warp == kLoaderWarp) {
     // ================================ weight loader (TMA engine bulk copies) ==========================
-    if (lane == 0) {
+    if (PAIR) {
+      // the image rows are [chunk][tap][k-core][ntile][8]: this CTA's half of a (tap, k-core) slab is nw * 16 contiguous
+      // bytes; lane i copies the slabs i, i + 32, ... of a stage
+      int stage = 0;
+      uint32_t bphase = 0;
+      const unsigned char* wimg = a.wp + (long long)nt * g.wimg_bytes_per_ntile + (long long)rank * nw * 16;
+      const long long full_chunk_bytes = (long long)kPL * g.ntile * 16 * T;
+      ChunkSeq lseq(g.nsc, has_base ? g.nbc : 0);
+      for (int pq = 0; pq < nchunks; ++pq) {
+        const int q = lseq.next();
+        const int ncols = chunk_cols(g, q);
+        const int nslab = g.tps * ncols;                                   // slabs per stage
+        const unsigned char* wsrc = wimg + (long long)q * full_chunk_bytes;
+        for (int t = 0; t < T; t += g.tps) {
+          mbar_wait(&b_empty[stage], bphase ^ 1);
+          if (lane == 0) mbar_arrive_expect_tx(&b_full[stage], (uint32_t)nslab * (uint32_t)nw * 16u);
+          __syncwarp();
+          unsigned char* dstb = bst0 + stage * bstage_bytes;
+          for (int sl = lane; sl < nslab; sl += 32)
+            bulk_g2s(dstb + (size_t)sl * nw * 16, wsrc + (size_t)sl * g.ntile * 16, (uint32_t)nw * 16u, &b_full[stage]);
+          wsrc += (size_t)nslab * g.ntile * 16;
+          if (++stage == g.bstages) { stage = 0; bphase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t bphase = 0;
       const unsigned char* wimg = a.wp + (long long)nt * g.wimg_bytes_per_ntile;
@@ -760,7 +824,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  if (PAIR) { cluster_arrive(); cluster_wait(); }        // both CTAs are done with the pair's tensor memory and shared memory
+  if (warp == kMmaWarp) { if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)g.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols); }
 }
 
 // d(basis_j)/dx for the RBF and Chebyshev families, j < 8, registers only (every index is a compile-time constant):
@@ -1427,8 +1492,8 @@ size_t tc_fixed_smem() { return (size_t)kNumBars * 8 + 16 + sizeof(KcBasisCtx) +
 
 // Common tail of the forward / dgrad geometry: choose nsub, ring depths and shared-memory carve-up.
 // kcores = total number of 16-byte k-cores per tap in the weight image of one N tile.
-int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
-  const size_t btap = (size_t)kPL * g->ntile * 16;
+int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores, int pair) {
+  const size_t btap = (size_t)kPL * (pair ? g->ntile / 2 : g->ntile) * 16;        // per CTA
   // nsub: 128-row sub-tiles per CTA, bounded by TMEM (512 columns), the producer row mapping (1024 rows) and shared memory.
   // Among the nsub that fit, take the one with the smallest estimated kernel time:
   //   waves(nsub) * [ max(nsub * MMA cycles of the K loop, weight-image bytes / ~32 B per cycle from L2) + fixed + nsub * epilogue ]
@@ -1446,7 +1511,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
     const int nrows = (d->kh - 1) * SS + seglen;
     if (nrows > kRB * kRowThreads) continue;
     const long long mtiles = (g->L + mcta - 1) / mcta;
-    const long long ctas = mtiles * g->n_ntiles;
+    const long long ctas = (pair ? (mtiles + 1) / 2 * 2 : mtiles) * g->n_ntiles;
     // CTAs do not run in lockstep, so wave quantisation only matters while the grid is a wave or two
     const double waves = ctas < 2 * sms ? (double)((ctas + sms - 1) / sms) : (double)ctas / (double)sms;
     const double mma_cyc = (double)nchunks * T * 2.0 * (g->ntile / 2 > 48 ? g->ntile / 2 : 48);     // per sub-tile
@@ -1472,7 +1537,7 @@ int tc_fit(const kc_desc* d, TcGeom* g, int T, int kcores) {
       int bst = (int)((kSmemLimit - fixed) / bstage);
       if (bst > kMaxBStages) bst = kMaxBStages;
       g->nsub = nsub; g->mcta = mcta; g->SS = SS; g->nrows = nrows; g->plane_bytes = plane_bytes; g->tps = tps;
-      g->na = na; g->bstages = bst; g->mtiles = mtiles; g->smem_bytes = fixed + bst * bstage;
+      g->na = na; g->bstages = bst; g->mtiles = mtiles; g->smem_bytes = fixed + bst * bstage; g->pair = pair;
       found = true;
       best_cost = cost;
       break;
@@ -1562,7 +1627,7 @@ int tc_dgrad_geometry(const kc_desc* d, TcGeom* g) {
   g->cpt = 16;
   g->ntile = 16 * wb;
   g->n_ntiles = (d->cin + 15) / 16;
-  return tc_fit(d, g, T, planes);
+  return tc_fit(d, g, T, planes, 0);
 }
 
 int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
@@ -1612,7 +1677,9 @@ int tc_forward_geometry(const kc_desc* d, TcGeom* g) {
       return KC_OK;
     }
   }
-  return tc_fit(d, g, T, kcores);
+  static const int fwd_pair_enabled = []() { const char* e = getenv("KANCONV_FWD_PAIR"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  // (not for N tiles below 128: those layers are bound by the basis producers, and coupling two CTAs' producers costs 10 %)
+  return tc_fit(d, g, T, kcores, fwd_pair_enabled && g->ntile % 16 == 0 && g->ntile >= 128 && g->L > 2 * kTileM ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1885,9 +1952,24 @@ extern "C" int kc_conv_fwd_tc(const kc_desc* d, const float* x_base, const float
     // the planes behind the channels this kernel expands (padding of the weight gradient's M = 128 tiles) stay unwritten: the
     // weight-gradient kernel zero-fills them in shared memory instead of reading them (WgGeom::vs_planes / vb_planes)
   }
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
-  kc_tc_kernel<kModeFwd><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  if (g.pair) {
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeFwd, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((g.mtiles + 1) / 2 * 2), (unsigned)g.n_ntiles, 1);      // an odd tile count gets an idle partner
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = g.smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kc_tc_kernel<kModeFwd, true>, a));
+  } else {
+    KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeFwd, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
+    kc_tc_kernel<kModeFwd, false><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  }
   KC_LAUNCH_CHECK("kc_tc_kernel<fwd>");
   return KC_OK;
 }
@@ -1922,9 +2004,9 @@ extern "C" int kc_conv_dgrad_tc(const kc_desc* d, const float* dz, const float* 
     if (fam == 3 && a.dbeta != nullptr) return kc_dbeta_reduce(a.dbeta, (long long)nctas * kDgEpiWarps, stream);
     return KC_OK;
   }
-  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  KC_CUDA_CHECK(cudaFuncSetAttribute(kc_tc_kernel<kModeDgrad, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   dim3 grid((unsigned)g.mtiles, (unsigned)g.n_ntiles);
-  kc_tc_kernel<kModeDgrad><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
+  kc_tc_kernel<kModeDgrad, false><<<grid, kTcThreads, g.smem_bytes, (cudaStream_t)stream>>>(a);
   KC_LAUNCH_CHECK("kc_tc_kernel<dgrad>");
   if (a.dbeta != nullptr) return kc_dbeta_reduce(a.dbeta, (long long)grid.x * grid.y * 16, stream);
   return KC_OK;
