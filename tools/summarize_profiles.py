@@ -18,7 +18,13 @@ def rows_of(path):
 
 def short(n):
     n = n.replace("void ", "").replace("<unnamed>::", "").split("(")[0]
-    return n.replace("kc_tc_kernel<0>", "kc_tc_kernel<fwd>").replace("kc_tc_kernel<1>", "kc_tc_kernel<dgrad>")[:80]
+    # template arguments -> readable names; CTA-pair (cta_group::2) instantiations keep a "<pair>" suffix, and the forward of the
+    # stem / pointwise layers (pre-pass + persistent GEMM, FAM 2) is listed with the forward kernel it replaces
+    for a, b in (("kc_tc_kernel<0, true>", "kc_tc_kernel<fwd><pair>"), ("kc_tc_kernel<0, false>", "kc_tc_kernel<fwd>"),
+                 ("kc_tc_kernel<1, false>", "kc_tc_kernel<dgrad>"), ("kc_tc_kernel<0>", "kc_tc_kernel<fwd>"), ("kc_tc_kernel<1>", "kc_tc_kernel<dgrad>"),
+                 ("kc_dgrad_persistent_kernel<2, false>", "kc_tc_kernel<fwd><from phi>"), (", true>", "><pair>"), (", false>", ">")):
+        n = n.replace(a, b)
+    return n[:80]
 
 
 shutil.copy(os.path.join(OUT, "launches.csv"), os.path.join(PROF, TAG + "_ncu_launches_b16.csv"))
@@ -44,7 +50,7 @@ for r in data:
     d = launch.setdefault(r[col["ID"]], {"name": short(r[col["Kernel Name"]])})
     d[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", "")) * scale[r[col["Metric Unit"]]]
 L = list(launch.values())
-nsteps = sum(1 for l in L if l["name"] == "kc_tc_kernel<fwd>") / 13.0          # 13 conv layers per step
+nsteps = sum(1 for l in L if l["name"].startswith("kc_tc_kernel<fwd>")) / 13.0          # 13 conv layers per step
 agg = collections.defaultdict(lambda: {"n": 0, "ms": 0.0, "rd": 0.0, "wr": 0.0})
 for l in L:
     a = agg[l["name"]]; a["n"] += 1; a["ms"] += l.get("gpu__time_duration.sum", 0); a["rd"] += l.get("dram__bytes_read.sum", 0); a["wr"] += l.get("dram__bytes_write.sum", 0)
