@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 DEBUG = os.environ.get("KANCONV_DEBUG") == "1"
 if DEBUG:
     SOURCES = SOURCES + ["kc_debug.cu"]
-    NVCC_FLAGS = NVCC_FLAGS + ["-DKANCONV_DEBUG"] + [f for f in os.environ.get("KANCONV_DEBUG_DEFS", "").split() if f.startswith("-D")]
+    NVCC_FLAGS = NVCC_FLAGS + ["-DKANCONV_DEBUG"]
 
 
 def _nvcc():

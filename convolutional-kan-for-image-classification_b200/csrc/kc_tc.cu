@@ -616,10 +616,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kc_tc_kernel(const __grid_const
       for (int pq = 0; pq < nchunks; ++pq) {
         const int q = lseq.next();
         const unsigned char* wsrc = wimg + (long long)q * full_chunk_bytes;
-        uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
-#ifdef KANCONV_DEBUG_HALFB
-        bytes /= 2;          // timing experiment only (wrong results): half the weight traffic
-#endif
+        const uint32_t bytes = (uint32_t)chunk_cols(g, q) * g.ntile * 16u * (uint32_t)g.tps;
         for (int t = 0; t < T; t += g.tps) {
           mbar_wait(&b_empty[stage], bphase ^ 1);
           trl.stamp();                               // b_empty acquired
