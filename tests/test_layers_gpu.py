@@ -151,9 +151,15 @@ def _conv_only_oracle(kind, ora, x, g):
     return z.detach(), xx.grad, {k: v.grad for k, v in params.items()}
 
 
+# The rows with <= 8 input channels take the stem routes (forward = basis pre-pass + persistent GEMM; <= 4 channels: the weight
+# gradient as ONE merged unit per cout tile); cout >= 128 runs the forward / dgrad as CTA pairs (cta_group::2), 320 output
+# channels as two N tiles of 160 with 80 weight rows per CTA, odd position-tile counts leave an idle partner CTA.
 @pytest.mark.parametrize("kind,cin,cout,hw,n", [("kan", 64, 128, 32, 2), ("kan", 16, 320, 20, 3), ("kan", 24, 40, 9, 5),
                                                ("kan", 40, 24, 13, 3), ("kan", 8, 16, 40, 2), ("cheby", 32, 64, 16, 2),
-                                               ("fast", 16, 32, 14, 2), ("gram", 32, 64, 16, 2), ("gram", 64, 128, 32, 2)])
+                                               ("fast", 16, 32, 14, 2), ("gram", 32, 64, 16, 2), ("gram", 64, 128, 32, 2),
+                                               ("kan", 3, 64, 37, 3), ("kan", 1, 16, 21, 2), ("kan", 4, 136, 16, 2),
+                                               ("kan", 5, 40, 12, 1), ("fast", 3, 32, 18, 2), ("cheby", 3, 32, 18, 2),
+                                               ("kan", 128, 256, 15, 1)])
 def test_bf16_tensor_core_conv_op_fwd_dgrad_wgrad(kind, cin, cout, hw, n):
     """The convolution op alone (no norm / PReLU): z, dX, dW (and GRAM's d/d beta_weights, reduced deterministically in the
     tcgen05 dgrad epilogue) of the tensor-core kernels vs the fp64 oracle, BF16 tolerance.  Also prints the fraction of

@@ -1,6 +1,6 @@
 """SASS evidence of the shipped library (no GPU needed): per kernel, the counts of the mnemonics that prove a Blackwell-native
 kernel (B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, cp.async.bulk -> UBLKCP, cluster barriers -> UCGABAR,
-legacy tensor path -> HMMA).  python tools/sass_evidence.py > profiles/r2_sass_evidence.txt"""
+legacy tensor path -> HMMA; UTCHMMA.2CTA = tcgen05.mma.cta_group::2, listed separately from the single-CTA UTCHMMA).  python tools/sass_evidence.py > profiles/r2_sass_evidence.txt"""
 import collections
 import os
 import re
@@ -13,7 +13,7 @@ import kanconv_b200 as K  # noqa: E402
 
 lib = K._lib.library_path()
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-MNEM = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "LDGSTS", "HMMA", "HGMMA", "MUFU"]
+MNEM = ["UTCHMMA.2CTA", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "LDGSTS", "HMMA", "HGMMA", "MUFU"]
 cur, counts, order = None, collections.defaultdict(collections.Counter), []
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -23,7 +23,7 @@ for line in sass.splitlines():
         cur = re.sub(r"\(.*", "", cur)[:90]
         order.append(cur)
         continue
-    m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+    m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and cur:
         op = m.group(1)
         for k in MNEM:

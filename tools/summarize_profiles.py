@@ -20,10 +20,18 @@ def short(n):
     n = n.replace("void ", "").replace("<unnamed>::", "").split("(")[0]
     # template arguments -> readable names; CTA-pair (cta_group::2) instantiations keep a "<pair>" suffix, and the forward of the
     # stem / pointwise layers (pre-pass + persistent GEMM, FAM 2) is listed with the forward kernel it replaces
-    for a, b in (("kc_tc_kernel<0, true>", "kc_tc_kernel<fwd><pair>"), ("kc_tc_kernel<0, false>", "kc_tc_kernel<fwd>"),
-                 ("kc_tc_kernel<1, false>", "kc_tc_kernel<dgrad>"), ("kc_tc_kernel<0>", "kc_tc_kernel<fwd>"), ("kc_tc_kernel<1>", "kc_tc_kernel<dgrad>"),
-                 ("kc_dgrad_persistent_kernel<2, false>", "kc_tc_kernel<fwd><from phi>"), (", true>", "><pair>"), (", false>", ">")):
-        n = n.replace(a, b)
+    import re
+    m = re.match(r"(kc_tc_kernel|kc_dgrad_persistent_kernel|kc_wgrad_tc_kernel)<(\d+)(?:, (0|1|true|false))?>", n)
+    if m:
+        base, a, b = m.group(1), m.group(2), m.group(3) in ("1", "true")
+        if base == "kc_tc_kernel":
+            n = "kc_tc_kernel<" + ("fwd" if a == "0" else "dgrad") + ">"
+        elif base == "kc_dgrad_persistent_kernel" and a == "2":
+            n = "kc_tc_kernel<fwd><from phi>"
+        else:
+            n = f"{base}<{a}>"
+        if b:
+            n += "<pair>"
     return n[:80]
 
 
