@@ -64,3 +64,41 @@ def test_two_gpu_ddp_matches_single_gpu(tmp_path):
         scale = float(ref.abs().max()) or 1.0
         # same kernels, same per-sample results; only the order of the cross-sample sums differs (wgrad split-K vs all-reduce)
         assert float((got[k] - ref).abs().max()) <= 2e-2 * scale, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sharded_batch_gradients_equal_whole_batch_on_one_gpu(precision):
+    """The data-parallel property without NCCL (runs on one GPU): the mean of the gradients of the shards of a batch equals the
+    gradient of the whole batch, because every layer works per sample (InstanceNorm statistics per (n, c)) and the kernels'
+    per-sample results do not depend on the batch they are computed in - tile geometry, CTA pairs, split-K counts and the
+    dynamic tile queue only change WHICH CTA computes a value and the order of the fp32 cross-sample sums."""
+    import kanconv_b200 as K
+    dev = torch.device("cuda", 0)
+    old = K.get_precision() if hasattr(K, "get_precision") else None
+    K.set_precision(precision)
+    try:
+        model = _build(dev)
+        model.eval()
+        x, y = _batch()
+        x, y = x.to(dev), y.to(dev)
+
+        def grads(xs, ys):
+            model.zero_grad(set_to_none=True)
+            torch.nn.functional.cross_entropy(model(xs), ys).backward()
+            return [p.grad.detach().double().clone() for p in model.parameters()]
+
+        whole = grads(x, y)
+        for shards in (2, 4):
+            per = x.shape[0] // shards
+            acc = None
+            for s in range(shards):
+                g = grads(x[s * per:(s + 1) * per], y[s * per:(s + 1) * per])
+                acc = g if acc is None else [a + b for a, b in zip(acc, g)]
+            num = sum(float((a / shards - w).square().sum()) for a, w in zip(acc, whole))
+            den = sum(float(w.square().sum()) for w in whole)
+            rel = (num / den) ** 0.5
+            print(f"{precision}: {shards} shards of {per}: relative L2 of mean(shard gradients) - whole-batch gradient = {rel:.2e}")
+            assert rel < 1e-4, rel
+    finally:
+        if old is not None:
+            K.set_precision(old)

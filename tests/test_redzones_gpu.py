@@ -111,3 +111,43 @@ def test_repeated_runs_are_bit_identical(name, ctor, shape):
             first = cur
         else:
             assert all(torch.equal(a, b) for a, b in zip(first, cur))
+
+
+def test_results_do_not_depend_on_the_contents_of_free_memory():
+    """No kernel may consume bytes that no kernel wrote (compute-sanitizer's initcheck is not available on the GPU pool): the
+    first six modules of KAN-VGG16 (four KAN convolution layers - stem route, CTA pairs, cluster / warp norm kernels - and two
+    pooling stages) run forward + backward twice, once after the caching allocator's free blocks were filled with zeros and once
+    after they were filled with 3000.0; every parameter gradient and the input gradient must be bit-identical.
+    (tools/uninit_check.py is the NaN-poisoning variant, tools/garbage_check*.py the per-layer / per-prefix versions.)"""
+    import kanconv_b200 as K
+    from kanconv_b200.models.kan_vgg import vggkan
+    dev = torch.device("cuda")
+    K.set_precision("bf16")
+    try:
+        torch.manual_seed(0)
+        model = vggkan(3, 10, arch="VGG16", classifier_type="Linear", expected_feature_shape=(1, 1), spline_order=3, grid_size=5).to(dev)
+        feats = list(model.features.children())[:6]
+        x = torch.randn(3, 3, 48, 48, device=dev)
+
+        def run(val):
+            torch.cuda.synchronize()
+            junk = [torch.full((1 << 28,), val, device=dev)] + [torch.full((s,), val, device=dev) for s in (16, 256, 4096, 65536, 200000) for _ in range(8)]
+            del junk
+            model.zero_grad(set_to_none=True)
+            xx = x.clone().requires_grad_(True)
+            h = xx
+            for f in feats:
+                h = f(h)
+            torch.manual_seed(1)
+            (h * torch.randn_like(h)).sum().backward()
+            torch.cuda.synchronize()
+            out = {"dx": xx.grad.clone(), "y": h.detach().clone()}
+            out.update({n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+            return out
+
+        a, b = run(0.0), run(3000.0)
+        assert len(a) > 8
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    finally:
+        K.set_precision("auto")
