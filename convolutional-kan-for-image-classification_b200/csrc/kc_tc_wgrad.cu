@@ -470,6 +470,10 @@ __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_kernel(const __grid_co
 // (cout tile, chunk) for ALL taps, sums the splits with coalesced 128-byte reads, and writes runs that are contiguous in
 // the reference layout ([cout][(c, j)][kh][kw]: 32 rows x T taps = 288 consecutive floats per cout for nb = 8).
 constexpr int kRedT = 9;
+// KH, KW > 0: compile-time filter size - the kh * kw * 4 * nsplit workspace reads of a thread are independent, and with the
+// loops unrolled they are all in flight at once (the run-time loops issued one 128-byte row per round trip: 124 us for the
+// 100 MB of a 512 -> 512 layer, 0.8 TB/s).  KH = 0: any filter with kh * kw <= 9.
+template <int KH, int KW>
 __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_tile_kernel(const __grid_constant__ kc_desc d, const __grid_constant__ WgGeom g,
                                                                       const float* __restrict__ ws, float* __restrict__ dw_base,
                                                                       float* __restrict__ dw_basis) {
@@ -482,18 +486,43 @@ __global__ void __launch_bounds__(256) kc_wgrad_tc_reduce_tile_kernel(const __gr
   const long long total = (long long)g.units * unit_sz;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool ncol_ok = n0 + lane < g.ntile;
-  for (int r = 0; r < d.kh; ++r) {
-    const int unit = (ct * g.nchunks + chunk) * d.kh + r;
-    for (int s = 0; s < d.kw; ++s)
+  if (KH > 0) {
+    float acc[KH * KW * 4 + 1];
 #pragma unroll
-      for (int mm = 0; mm < 4; ++mm) {
-        const int ml = warp + 8 * mm;
-        const long long i = (long long)unit * unit_sz + ((long long)s * 128 + m0 + ml) * g.ntile + n0 + lane;
-        float acc = 0.0f;
-        if (ncol_ok)
-          for (int k = 0; k < g.nsplit; ++k) acc += ws[(long long)k * total + i];
-        tile[lane][ml * T + r * d.kw + s] = acc;
+    for (int e = 0; e < KH * KW * 4; ++e) acc[e] = 0.0f;
+    if (ncol_ok) {
+      const float* base = ws + (long long)((ct * g.nchunks + chunk) * KH) * unit_sz + (long long)(m0 + warp) * g.ntile + n0 + lane;
+      for (int k = 0; k < g.nsplit; ++k) {                      // splits in fixed order (deterministic)
+        const float* bk = base + (long long)k * total;
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int s = 0; s < KW; ++s)
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm)
+              acc[(r * KW + s) * 4 + mm] += __ldg(bk + (long long)r * unit_sz + ((long long)s * 128 + 8 * mm) * g.ntile);
       }
+    }
+#pragma unroll
+    for (int r = 0; r < KH; ++r)
+#pragma unroll
+      for (int s = 0; s < KW; ++s)
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) tile[lane][(warp + 8 * mm) * (KH * KW) + r * KW + s] = acc[(r * KW + s) * 4 + mm];
+  } else {
+    for (int r = 0; r < d.kh; ++r) {
+      const int unit = (ct * g.nchunks + chunk) * d.kh + r;
+      for (int s = 0; s < d.kw; ++s)
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+          const int ml = warp + 8 * mm;
+          const long long i = (long long)unit * unit_sz + ((long long)s * 128 + m0 + ml) * g.ntile + n0 + lane;
+          float acc = 0.0f;
+          if (ncol_ok)
+            for (int k = 0; k < g.nsplit; ++k) acc += ws[(long long)k * total + i];
+          tile[lane][ml * T + r * d.kw + s] = acc;
+        }
+    }
   }
   __syncthreads();
   const int run = 32 * T;
@@ -730,7 +759,8 @@ extern "C" int kc_conv_wgrad_tc(const kc_desc* d, const void* dz_flat, const flo
   const long long tile_blocks = (long long)((g.ntile + 31) / 32) * 4 * g.n_ct * g.nchunks;
   if (!g.merged && d->kh * d->kw <= kRedT && (long long)g.n_ct * g.nchunks <= 65535 && tile_blocks >= 2 * kc_sm_count()) {
     dim3 rgrid((unsigned)(((g.ntile + 31) / 32) * 4), (unsigned)(g.n_ct * g.nchunks));
-    kc_wgrad_tc_reduce_tile_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
+    if (d->kh == 3 && d->kw == 3) kc_wgrad_tc_reduce_tile_kernel<3, 3><<<rgrid, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
+    else kc_wgrad_tc_reduce_tile_kernel<0, 0><<<rgrid, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
   } else {
     kc_wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d, g, (const float*)workspace, dw_base, dw_basis);
   }
