@@ -25,6 +25,7 @@ using namespace kc;
 
 constexpr int kFwdThreads = 256;
 constexpr int kBwdThreadsBig = 1024, kBwdThreadsSmall = 256;  // one CTA per SM (chunk up to 200 KB) / four CTAs per SM (<= 52 KB)
+constexpr int kBwdThreadsMid = 512;                           // two CTAs per SM (chunk <= 100 KB, clusters of 16)
 constexpr int kBwdThreadsTiny = 64;                           // chunks of <= 64 float4 columns per channel (14x14 planes)
 constexpr uint32_t kBulkPiece = 32 * 1024;       // bytes per cp.async.bulk request
 constexpr size_t kSmemMax = 200 * 1024 + 1024;   // largest resident chunk (8 channels x 28 rows x 224 floats = 200 704 B)
@@ -148,7 +149,7 @@ __device__ __forceinline__ float act_grad_t(float v, float alpha) {
 // used for the 224x224 planes so that the resident chunk is 100 KB and TWO CTAs share an SM - with one CTA per SM the bulk
 // load, the two phases and the cluster barriers of a chunk run back to back and the SM idles in between).
 template <int kBwdThreads, int CH, int KIND, bool FULL>
-__global__ void __launch_bounds__(kBwdThreads, kBwdThreads >= 1024 ? 1 : kBwdThreads >= 256 ? 4 : 16)
+__global__ void __launch_bounds__(kBwdThreads, kBwdThreads >= 1024 ? 1 : kBwdThreads >= 512 ? 2 : kBwdThreads >= 256 ? 4 : 16)
 kc_norm_bwd_flat_cluster_kernel(const __grid_constant__ NbfArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* zbuf = reinterpret_cast<float*>(smem_raw);           // [CH][cap] zhat of this CTA's rows
@@ -547,6 +548,10 @@ int pick_cluster(int units, size_t bytes_per_unit, size_t want, size_t limit, in
 
 template <typename Kernel, typename... Args>
 cudaError_t launch_cluster(Kernel kernel, unsigned grid, unsigned threads, size_t smem, int cs, cudaStream_t st, Args... args) {
+  if (cs > 8) {                      // clusters of 16 are a non-portable size: opt in per kernel
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);
@@ -586,18 +591,25 @@ cudaError_t launch_nbf_kind(const NbfArgs& a, unsigned grid, size_t smem, int cs
 // kept <= 52 KB when a cluster of <= 8 CTAs allows it (four 256-thread CTAs per SM; 64-thread CTAs for the 14x14 planes), else
 // <= 200 KB with one 1024-thread CTA per SM (the 224x224 planes).  A thread owns at most two float4 columns per channel.
 // (Splitting the 8 channels over two CTAs - 100 KB chunks, two CTAs per SM, 8-byte half-vector stores - measured 6 % slower.)
+// Planes that do not fit 52 KB chunks in a cluster of 8 (224x224): a cluster of 16 (non-portable size) with 100 KB chunks and
+// 512-thread CTAs puts TWO CTAs on an SM, so the phases of one (bulk load, sums, cluster exchange, apply) overlap the other's
+// instead of running back to back on an otherwise idle SM; KANCONV_NORM_BWD_CS16=0 keeps the 8 x 200 KB / 1024-thread shape.
 struct NbfPlan { int ch, cs, rows, threads; size_t smem; };
 bool plan_nbf(int ho, int wo, NbfPlan* pl) {
-  for (int pass = 0; pass < 2; ++pass)
-    for (int cs = 1; cs <= 8; cs *= 2) {
+  static const int cs16 = []() { const char* e = getenv("KANCONV_NORM_BWD_CS16"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass == 1 && !cs16) continue;
+    for (int cs = pass == 1 ? 16 : 1; cs <= (pass == 1 ? 16 : 8); cs *= 2) {
       const int rows = (ho + cs - 1) / cs;
       const size_t smem = (size_t)rows * wo * 32;
-      if (smem > (pass == 0 ? (size_t)52 * 1024 : kSmemMax)) continue;
-      const int threads = pass == 1 ? kBwdThreadsBig : rows * wo <= 4 * kBwdThreadsTiny ? kBwdThreadsTiny : kBwdThreadsSmall;
+      if (smem > (pass == 0 ? (size_t)52 * 1024 : pass == 1 ? (size_t)101 * 1024 : kSmemMax)) continue;
+      const int threads = pass == 2 ? kBwdThreadsBig : pass == 1 ? kBwdThreadsMid : rows * wo <= 4 * kBwdThreadsTiny ? kBwdThreadsTiny : kBwdThreadsSmall;
       if (rows * wo > 8 * threads) continue;
+      if (pass == 1 && (rows * cs != ho || ((rows * wo) & 3))) continue;      // equal, 16-byte aligned chunks only
       *pl = {8, cs, rows, threads, smem};
       return true;
     }
+  }
   return false;
 }
 
@@ -706,6 +718,7 @@ extern "C" int kc_norm_bwd_dz_flat(const kc_desc* conv, const kc_norm_desc* d, c
   if (grid > 0x7fffffffLL) KC_FAIL(KC_ERR_UNSUPPORTED, "kc_norm_bwd_dz_flat: grid too large");
   const bool full = (d->c % 8) == 0 && a.groups8 * 8 == d->c;          // every 8-channel group of the flat buffer is complete
   cudaError_t e = pl.threads == kBwdThreadsBig ? launch_nbf_kind<kBwdThreadsBig, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream)
+                  : pl.threads == kBwdThreadsMid ? launch_nbf_kind<kBwdThreadsMid, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream)
                   : pl.threads == kBwdThreadsTiny ? launch_nbf_kind<kBwdThreadsTiny, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream)
                                                   : launch_nbf_kind<kBwdThreadsSmall, 8>(a, (unsigned)grid, pl.smem, pl.cs, full, (cudaStream_t)stream);
   kc_count_launch();

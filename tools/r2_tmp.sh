@@ -1,11 +1,5 @@
 #!/bin/bash
 O=gpurun_out/r2; mkdir -p $O
-( time timeout 900 python -m pytest tests -m gpu -q -x ) > $O/pytest_c51.log 2>&1
-grep -E "passed|failed|FAILED|Error" $O/pytest_c51.log | tail -n 8 | cut -c1-300
-timeout 300 python tools/layer_bench.py --bwd 2>&1 | grep shape | python -c "
-import sys, json
-for l in sys.stdin:
-    r = json.loads(l); k = r.get('kernels', {})
-    print(r['shape'], {n: v[0] for n, v in k.items() if 'wgrad' in n or 'reduce' in n}, 'fwd+bwd', r.get('fwd_bwd_ms'))"
-python bench.py --steps 12 --warmup 4 --no-cpu-baseline --no-gpu-eager-baseline 2>/dev/null | python -c "
-import json,sys; l=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=l['roofline']['by_kernel_ms']; print('1 GPU', round(l['value'],1), round(l['ms_per_step'],2), k)"
+echo "--- clusters of 16 x 100 KB"; NORM_BENCH_SHAPES="64,64,224;64,128,112" timeout 200 python tools/norm_bench.py 2>&1 | tail -4 | cut -c1-400
+echo "--- clusters of 8 x 200 KB"; KANCONV_NORM_BWD_CS16=0 NORM_BENCH_SHAPES="64,64,224;64,128,112" timeout 200 python tools/norm_bench.py 2>&1 | tail -4 | cut -c1-400
+timeout 300 python -m pytest tests -m gpu -q -x -k "norm or layer or vgg or redzone" 2>&1 | tail -3
