@@ -26,7 +26,17 @@ def pair(v, ndim: int, fill: int = 1) -> Tuple[int, int]:
         v = (int(v),) * ndim
     if ndim == 1:
         return (fill, v[0]) if len(v) == 1 else (fill, v[-1])
+    if ndim == 3:
+        return (v[1], v[2])            # (h, w) of a (d, h, w) triple; the depth axis is handled by depth_of()
     return (v[0], v[1])
+
+
+def depth_of(v, ndim: int) -> int:
+    """Depth component of a 3-D conv hyper-parameter (int or (d, h, w))."""
+    if isinstance(v, (tuple, list)):
+        v = tuple(int(i) for i in v)
+        return v[0]
+    return int(v)
 
 
 def act_kind(module: nn.Module) -> int:
@@ -72,10 +82,57 @@ class KANConvBase(nn.Module):
             if x.dim() != 3:
                 raise ValueError(f"expected a 3-D input [N, C, L], got {tuple(x.shape)}")
             return x.unsqueeze(2)
-        raise NotImplementedError("3-D KAN convolutions are not implemented in the CUDA kernels")
+        raise NotImplementedError("3-D inputs go through _kan_conv3d / _norm_act3d")
 
     def _from4d(self, y: torch.Tensor) -> torch.Tensor:
         return y.squeeze(2) if self.ndim == 1 else y
+
+    # ---- 3-D layers: the volume convolution as kd depth-shifted 2-D convolutions on the CUDA kernels --------------------------
+    #   z[:, :, do] = sum_k  conv2d_kan( x[:, :, do * sd + k * dd - pd],  W[:, :, k] )
+    # For one depth tap k every output slice that has an input slice is one image of a 2-D batch (depth folded into the batch
+    # axis), so a layer costs kd calls of the 2-D op, not D * kd.  Depth padding contributes nothing: the reference pads the
+    # EXPANDED tensor (Conv3d's zero padding), not x, so out-of-range slices are skipped rather than evaluated at x = 0.
+    def _kan_conv3d(self, spec2, x5: torch.Tensor, u5, beta, w_base5, w_basis5) -> torch.Tensor:
+        if x5.dim() != 5:
+            raise ValueError(f"expected a 5-D input [N, C, D, H, W], got {tuple(x5.shape)}")
+        kd, sd = depth_of(self.kernel_size, 3), depth_of(self.stride, 3)
+        pd, dd = depth_of(self.padding, 3), depth_of(self.dilation, 3)
+        n, c, d, h, w = x5.shape
+        do = (d + 2 * pd - dd * (kd - 1) - 1) // sd + 1
+        if do <= 0:
+            raise ValueError("3-D KAN convolution: empty output depth")
+        z5 = None
+        for k in range(kd):
+            off = k * dd - pd                                  # input slice of output slice o: o * sd + off
+            lo = max(0, -(off // sd)) if off < 0 else 0        # first o with o * sd + off >= 0
+            while lo * sd + off < 0:
+                lo += 1
+            hi = min(do - 1, (d - 1 - off) // sd)              # last o with o * sd + off <= d - 1
+            if hi < lo:
+                continue
+            cnt = hi - lo + 1
+            sl = slice(lo * sd + off, (hi * sd + off) + 1, sd)
+
+            def fold(t):                                       # [N, C, cnt, H, W] -> [N * cnt, C, H, W]
+                return t[:, :, sl].permute(0, 2, 1, 3, 4).reshape(n * cnt, c, h, w).contiguous()
+
+            xb = fold(x5)
+            xs = None if u5 is None else fold(u5)
+            wb = [wt[:, :, k].contiguous() for wt in w_base5]
+            ws = [wt[:, :, k].contiguous() for wt in w_basis5]
+            zk = KF.kan_conv(spec2, xb, xs, beta, wb, ws, self.precision)             # [N * cnt, Cout, Ho, Wo]
+            zk = zk.reshape(n, cnt, zk.shape[1], zk.shape[2], zk.shape[3]).permute(0, 2, 1, 3, 4)
+            zk = F.pad(zk, (0, 0, 0, 0, lo, do - 1 - hi))
+            z5 = zk if z5 is None else z5 + zk
+        if z5 is None:
+            raise ValueError("3-D KAN convolution: no depth tap touches the input")
+        return z5.contiguous()
+
+    def _norm_act3d(self, z5: torch.Tensor, norms, out_act: int, alphas=()) -> torch.Tensor:
+        """InstanceNorm3d / BatchNorm3d (+ activation) of [N, C, D, H, W]: the statistics run over D * H * W, which is the plane of
+        the 2-D kernels when the volume is viewed as [N, C, D * H, W]."""
+        n, c, d, h, w = z5.shape
+        return self._norm_act(z5.reshape(n, c, d * h, w), norms, out_act, alphas).reshape(n, c, d, h, w)
 
     def _w4d(self, w: torch.Tensor) -> torch.Tensor:
         return w.unsqueeze(2) if self.ndim == 1 else w

@@ -35,6 +35,10 @@ class ChebyKANConvNDLayer(KANConvBase):
                                  dilation=pair(dilation, ndim), groups=groups)
 
     def forward(self, x):
+        if self.ndim == 3:
+            z = self._kan_conv3d(self._spec, x, None, None, [], [m.weight for m in self.poly_conv])
+            y = self._norm_act3d(z, self.layer_norm, L.OUT_NONE)
+            return y if self.dropout is None else self.dropout(y)
         x4 = self._to4d(x)
         y = self._from4d(self._conv_norm_act(self._spec, x4, None, [], [self._w4d(m.weight) for m in self.poly_conv],
                                              self.layer_norm, L.OUT_NONE))

@@ -40,6 +40,12 @@ class FastKANConvNDLayer(KANConvBase):
                           dilation=pair(dilation, ndim), groups=groups)
 
     def forward(self, x):
+        if self.ndim == 3:
+            xd = x if self.dropout is None else self.dropout(x)
+            u = self._norm_act3d(xd, self.layer_norm, L.OUT_NONE)
+            spec = KF.ConvSpec(basis=L.BASIS_RBF, act=self._act, nb=self.grid_size, order=0, params=self.rbf.host_params(),
+                               **self._geom)
+            return self._kan_conv3d(spec, x, u, None, [m.weight for m in self.base_conv], [m.weight for m in self.spline_conv])
         x4 = self._to4d(x)
         xd = x4 if self.dropout is None else self._to4d(self.dropout(x))
         u = self._norm_act(xd, self.layer_norm, L.OUT_NONE)

@@ -48,6 +48,13 @@ class GRAMKANConvNDLayer(KANConvBase):
         self._spec_presquashed = KF.ConvSpec(**dict(self._spec.__dict__, params=(1.0,)))
 
     def forward(self, x):
+        if self.ndim == 3:
+            t, spec = None, self._spec
+            if self.dropout is not None and self.training:        # Dropout3d on tanh(x), as in the 2-D branch below
+                t, spec = self.dropout(torch.tanh(x)), self._spec_presquashed
+            z = self._kan_conv3d(spec, x, t, self.beta_weights, [m.weight for m in self.base_conv],
+                                 [self.poly_weights[g] for g in range(self.groups)])
+            return self._norm_act3d(z, self.layer_norm, L.OUT_SILU)
         x4 = self._to4d(x)
         x_basis, spec = None, self._spec
         if self.dropout is not None and self.training:

@@ -52,6 +52,10 @@ class KANConvNDLayer(KANConvBase):
                                  dilation=pair(dilation, ndim), groups=groups)
 
     def forward(self, x):
+        if self.ndim == 3:
+            z = self._kan_conv3d(self._spec, x, None, None, [m.weight for m in self.base_conv], [m.weight for m in self.spline_conv])
+            y = self._norm_act3d(z, self.layer_norm, L.OUT_PRELU, [m.weight for m in self.prelus])
+            return y if self.dropout is None else self.dropout(y)
         x4 = self._to4d(x)
         y = self._conv_norm_act(self._spec, x4, None, [self._w4d(m.weight) for m in self.base_conv],
                                 [self._w4d(m.weight) for m in self.spline_conv], self.layer_norm, L.OUT_PRELU,

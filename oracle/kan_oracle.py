@@ -22,6 +22,8 @@ Reference call sites restated here (paths relative to the reference tree):
   * RadialBasisFunction.forward .................. utils/utils.py:19-33
   * KANLayer.forward (fully-connected layer) ..... layers/kan_layers.py:8-114
   * KANConv1DLayer (ndim = 1 binding) ............ layers/kan_layers.py:287-297
+  * *KANConv3DLayer (ndim = 3 bindings) .......... layers/kan_layers.py:261-271, cheby_kan_layers.py:114-121,
+                                                   gram_kan_layers.py:202-209, fast_kan_layers.py:123-134
   * KAN (MLP of KANLayers) ....................... models/kans.py:300-327
   * VGG.make_layers / forward .................... models/kan_vgg.py:40-188
 
@@ -42,6 +44,7 @@ __all__ = [
     "make_knots", "bspline_basis", "cheby_basis", "gram_basis", "rbf_basis",
     "kan_conv2d", "cheby_conv2d", "gram_conv2d", "fastkan_conv2d",
     "OracleKANConv2D", "OracleChebyKANConv2D", "OracleGRAMKANConv2D", "OracleFastKANConv2D",
+    "OracleKANConv3D", "OracleChebyKANConv3D", "OracleGRAMKANConv3D", "OracleFastKANConv3D",
     "OracleKANConv1D", "OracleKANLayer", "OracleKAN", "kan_conv1d", "kan_linear",
     "OracleVGG", "VGG_CFGS", "conv_flops",
 ]
@@ -132,6 +135,12 @@ def _norm(z: torch.Tensor, kind: str, eps: float, weight, bias, running=None, tr
     raise ValueError(kind)
 
 
+def _convnd(x, w, stride, padding, dilation):
+    """nn.Conv1d / nn.Conv2d / nn.Conv3d forward (bias-free, groups = 1) chosen by the rank of the filter: the reference binds the
+    same N-D layer body to the three conv classes (kan_layers.py:261-297 and the sibling files' *1D/*2D/*3D classes)."""
+    return (F.conv1d, F.conv2d, F.conv3d)[w.dim() - 3](x, w, None, stride, padding, dilation)
+
+
 def _expand(basis: torch.Tensor) -> torch.Tensor:
     """[N, C, H, W, nb] -> [N, C*nb, H, W] with expanded channel c*nb + j (kan_layers.py:236-237)."""
     return basis.movedim(-1, 2).flatten(1, 2)
@@ -145,9 +154,9 @@ def kan_conv2d(x, w_base, w_spline, prelu_weight, knots, spline_order, act="gelu
                norm="instance", eps=1e-5, norm_weight=None, norm_bias=None, running=None, training=True):
     """One group of KANConvNDLayer.forward_kan (kan_layers.py:197-247), ndim = 2, no dropout.
     ``running`` = (running_mean, running_var) of a BatchNorm2d norm layer (updated in training, used in eval)."""
-    base = F.conv2d(_act(act)(x), w_base, None, stride, padding, dilation)
+    base = _convnd(_act(act)(x), w_base, stride, padding, dilation)
     phi = _expand(bspline_basis(x, knots, spline_order))
-    z = base + F.conv2d(phi, w_spline, None, stride, padding, dilation)
+    z = base + _convnd(phi, w_spline, stride, padding, dilation)
     return F.prelu(_norm(z, norm, eps, norm_weight, norm_bias, running, training), prelu_weight)
 
 
@@ -155,7 +164,7 @@ def cheby_conv2d(x, w_poly, degree, stride=1, padding=0, dilation=1,
                  norm="instance", eps=1e-5, norm_weight=None, norm_bias=None):
     """One group of ChebyKANConvNDLayer.forward_ChebyKAN (cheby_kan_layers.py:91-101)."""
     phi = _expand(cheby_basis(x, degree))
-    return _norm(F.conv2d(phi, w_poly, None, stride, padding, dilation), norm, eps, norm_weight, norm_bias)
+    return _norm(_convnd(phi, w_poly, stride, padding, dilation), norm, eps, norm_weight, norm_bias)
 
 
 def gram_conv2d(x, w_base, w_poly, beta_weights, degree, stride=1, padding=0, dilation=1,
@@ -163,13 +172,13 @@ def gram_conv2d(x, w_base, w_poly, beta_weights, degree, stride=1, padding=0, di
     """One group of GRAMKANConvNDLayer.forward_kag (gram_kan_layers.py:172-189); SiLU everywhere.
     ``tanh_scale`` ([N, C, 1, 1], entries 0 or 1/(1-p)) stands for the Dropout2d the reference applies to tanh(x)
     (:178-179) with a mask chosen by the caller."""
-    base = F.conv2d(F.silu(x), w_base, None, stride, padding, dilation)
+    base = _convnd(F.silu(x), w_base, stride, padding, dilation)
     t = torch.tanh(x)
     if tanh_scale is not None:
         t = t * tanh_scale
     polys = gram_basis(t, degree, beta_weights)
     phi = F.silu(torch.cat(polys, dim=1))               # degree-major: channel d*C + c
-    z = F.conv2d(phi, w_poly, None, stride, padding, dilation) + base
+    z = _convnd(phi, w_poly, stride, padding, dilation) + base
     return F.silu(_norm(z, norm, eps, norm_weight, norm_bias))
 
 
@@ -180,10 +189,10 @@ def fastkan_conv2d(x, w_base, w_spline, grid, denominator, act="silu", stride=1,
 
     NB the normalisation is applied to the *input* of the RBF branch; there is no output norm/act.
     """
-    base = F.conv2d(_act(act)(x), w_base, None, stride, padding, dilation)
+    base = _convnd(_act(act)(x), w_base, stride, padding, dilation)
     u = _norm(x, norm, eps, norm_weight, norm_bias, running, training)
     phi = _expand(rbf_basis(u, grid, denominator))
-    return base + F.conv2d(phi, w_spline, None, stride, padding, dilation)
+    return base + _convnd(phi, w_spline, stride, padding, dilation)
 
 
 def kan_conv1d(x, w_base, w_spline, prelu_weight, knots, spline_order, act="gelu", stride=1, padding=0, dilation=1,
@@ -246,6 +255,13 @@ class _Weight(nn.Module):
 
 
 class _OracleBase(nn.Module):
+    _nd = 2                       # spatial rank; the *3D subclasses set 3 (Conv3d / InstanceNorm3d / BatchNorm3d underneath)
+
+    def _kshape(self, kernel_size):
+        if self._nd == 2:
+            return _pair(kernel_size)
+        return (int(kernel_size),) * self._nd if isinstance(kernel_size, int) else tuple(int(k) for k in kernel_size)
+
     def _check_groups(self, cin, cout, groups):
         if groups <= 0:
             raise ValueError("groups must be a positive integer")
@@ -258,9 +274,9 @@ class _OracleBase(nn.Module):
         mods = []
         for _ in range(groups):
             if kind == "instance":
-                mods.append(nn.InstanceNorm2d(ch, affine=affine))
+                mods.append((nn.InstanceNorm2d if self._nd == 2 else nn.InstanceNorm3d)(ch, affine=affine))
             elif kind == "batch":
-                mods.append(nn.BatchNorm2d(ch))
+                mods.append((nn.BatchNorm2d if self._nd == 2 else nn.BatchNorm3d)(ch))
             else:
                 mods.append(nn.Identity())
         return nn.ModuleList(mods)
@@ -276,14 +292,14 @@ class OracleKANConv2D(_OracleBase):
                  affine=False):
         super().__init__()
         self._check_groups(input_dim, output_dim, groups)
-        kh, kw = _pair(kernel_size)
+        ks = self._kshape(kernel_size)
         cg, og = input_dim // groups, output_dim // groups
         self.groups, self.cg, self.og = groups, cg, og
         self.spline_order, self.act = spline_order, _act_name(base_activation)
         self.stride, self.padding, self.dilation = stride, padding, dilation
         self.norm_kind = _norm_kind(norm_layer)
-        self.base_conv = nn.ModuleList([_Weight((og, cg, kh, kw)) for _ in range(groups)])
-        self.spline_conv = nn.ModuleList([_Weight((og, cg * (grid_size + spline_order), kh, kw)) for _ in range(groups)])
+        self.base_conv = nn.ModuleList([_Weight((og, cg) + ks) for _ in range(groups)])
+        self.spline_conv = nn.ModuleList([_Weight((og, cg * (grid_size + spline_order)) + ks) for _ in range(groups)])
         self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
         self.prelus = nn.ModuleList([nn.PReLU() for _ in range(groups)])
         self.knots = make_knots(grid_size, spline_order, grid_range)   # plain attribute, like the reference
@@ -295,7 +311,7 @@ class OracleKANConv2D(_OracleBase):
         for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
             nm = self.layer_norm[g]
             nw, nb = self._nw(nm)
-            running = (nm.running_mean, nm.running_var) if isinstance(nm, nn.BatchNorm2d) else None
+            running = (nm.running_mean, nm.running_var) if isinstance(nm, nn.modules.batchnorm._BatchNorm) else None
             outs.append(kan_conv2d(xg, self.base_conv[g].weight, self.spline_conv[g].weight,
                                    self.prelus[g].weight, self.knots, self.spline_order, self.act,
                                    self.stride, self.padding, self.dilation, self.norm_kind,
@@ -308,16 +324,16 @@ class OracleChebyKANConv2D(_OracleBase):
                  norm_layer=nn.InstanceNorm2d, affine=False):
         super().__init__()
         self._check_groups(input_dim, output_dim, groups)
-        kh, kw = _pair(kernel_size)
+        ks = self._kshape(kernel_size)
         cg, og = input_dim // groups, output_dim // groups
         self.groups, self.cg, self.og, self.degree = groups, cg, og, degree
         self.stride, self.padding, self.dilation = stride, padding, dilation
         self.norm_kind = _norm_kind(norm_layer)
         self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
-        self.poly_conv = nn.ModuleList([_Weight((og, (degree + 1) * cg, kh, kw)) for _ in range(groups)])
-        self.register_buffer("arange", torch.arange(0, degree + 1, 1).view(1, 1, -1, 1, 1))
+        self.poly_conv = nn.ModuleList([_Weight((og, (degree + 1) * cg) + ks) for _ in range(groups)])
+        self.register_buffer("arange", torch.arange(0, degree + 1, 1).view(1, 1, -1, *([1] * self._nd)))
         for m in self.poly_conv:
-            nn.init.normal_(m.weight, mean=0.0, std=1 / (input_dim * (degree + 1) * kh * kw))   # overwritten next line
+            nn.init.normal_(m.weight, mean=0.0, std=1 / (input_dim * (degree + 1) * math.prod(ks)))   # overwritten next line
             nn.init.kaiming_normal_(m.weight, mode="fan_in", nonlinearity="relu")
 
     def forward(self, x):
@@ -334,19 +350,19 @@ class OracleGRAMKANConv2D(_OracleBase):
                  norm_layer=nn.InstanceNorm2d, affine=False):
         super().__init__()
         self._check_groups(input_dim, output_dim, groups)
-        kh, kw = _pair(kernel_size)
+        ks = self._kshape(kernel_size)
         cg, og = input_dim // groups, output_dim // groups
         self.groups, self.cg, self.og, self.degree = groups, cg, og, degree
         self.stride, self.padding, self.dilation = stride, padding, dilation
         self.norm_kind = _norm_kind(norm_layer)
-        self.base_conv = nn.ModuleList([_Weight((og, cg, kh, kw)) for _ in range(groups)])
+        self.base_conv = nn.ModuleList([_Weight((og, cg) + ks) for _ in range(groups)])
         self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
-        self.poly_weights = nn.Parameter(torch.randn(groups, og, cg * (degree + 1), kh, kw))
+        self.poly_weights = nn.Parameter(torch.randn(groups, og, cg * (degree + 1), *ks))
         self.beta_weights = nn.Parameter(torch.zeros(degree + 1))
         for m in self.base_conv:
             nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
         nn.init.kaiming_uniform_(self.poly_weights, nonlinearity="linear")
-        nn.init.normal_(self.beta_weights, 0.0, 1.0 / (kh * kw * input_dim * (degree + 1.0)))
+        nn.init.normal_(self.beta_weights, 0.0, 1.0 / (math.prod(ks) * input_dim * (degree + 1.0)))
 
     def forward(self, x, tanh_scale=None):
         outs = []
@@ -372,14 +388,14 @@ class OracleFastKANConv2D(_OracleBase):
                  affine=False):
         super().__init__()
         self._check_groups(input_dim, output_dim, groups)
-        kh, kw = _pair(kernel_size)
+        ks = self._kshape(kernel_size)
         cg, og = input_dim // groups, output_dim // groups
         self.groups, self.cg, self.og = groups, cg, og
         self.act = _act_name(base_activation)
         self.stride, self.padding, self.dilation = stride, padding, dilation
         self.norm_kind = _norm_kind(norm_layer)
-        self.base_conv = nn.ModuleList([_Weight((og, cg, kh, kw)) for _ in range(groups)])
-        self.spline_conv = nn.ModuleList([_Weight((og, grid_size * cg, kh, kw)) for _ in range(groups)])
+        self.base_conv = nn.ModuleList([_Weight((og, cg) + ks) for _ in range(groups)])
+        self.spline_conv = nn.ModuleList([_Weight((og, grid_size * cg) + ks) for _ in range(groups)])
         self.layer_norm = self._make_norm(cg, self.norm_kind, affine, groups)   # sized by INPUT channels
         self.rbf = _RBF(float(grid_range[0]), float(grid_range[1]), grid_size)
         for m in list(self.base_conv) + list(self.spline_conv):
@@ -391,12 +407,32 @@ class OracleFastKANConv2D(_OracleBase):
             nm = self.layer_norm[g]
             nw, nb = self._nw(nm)
             running = None
-            if isinstance(nm, nn.BatchNorm2d):
+            if isinstance(nm, nn.modules.batchnorm._BatchNorm):
                 running = (nm.running_mean, nm.running_var)
             outs.append(fastkan_conv2d(xg, self.base_conv[g].weight, self.spline_conv[g].weight, self.rbf.grid,
                                        self.rbf.denominator, self.act, self.stride, self.padding, self.dilation,
                                        self.norm_kind, 1e-5, nw, nb, running, self.training))
         return torch.cat(outs, dim=1)
+
+
+class OracleKANConv3D(OracleKANConv2D):
+    """KANConv3DLayer (kan_layers.py:261-271): the N-D layer body over nn.Conv3d / nn.InstanceNorm3d; x [N, C, D, H, W]."""
+    _nd = 3
+
+
+class OracleChebyKANConv3D(OracleChebyKANConv2D):
+    """ChebyKANConv3DLayer (cheby_kan_layers.py:114-121)."""
+    _nd = 3
+
+
+class OracleGRAMKANConv3D(OracleGRAMKANConv2D):
+    """GRAMKANConv3DLayer (gram_kan_layers.py:202-209)."""
+    _nd = 3
+
+
+class OracleFastKANConv3D(OracleFastKANConv2D):
+    """FastKANConv3DLayer (fast_kan_layers.py:123-134)."""
+    _nd = 3
 
 
 class OracleKANConv1D(_OracleBase):

@@ -10,9 +10,11 @@ import torch.nn as nn
 from oracle import kan_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d}
+NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d, "batch3d": nn.BatchNorm3d}
 ORACLE_CTORS = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram": O.OracleGRAMKANConv2D,
-                "fast": O.OracleFastKANConv2D, "kan1d": O.OracleKANConv1D, "kanlayer": O.OracleKANLayer}
+                "fast": O.OracleFastKANConv2D, "kan1d": O.OracleKANConv1D, "kanlayer": O.OracleKANLayer,
+                "kan3d": O.OracleKANConv3D, "cheby3d": O.OracleChebyKANConv3D, "gram3d": O.OracleGRAMKANConv3D,
+                "fast3d": O.OracleFastKANConv3D}
 
 
 # whole-model fixtures (make_model_golden.py): a different record layout

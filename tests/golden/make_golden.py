@@ -23,12 +23,13 @@ import layers as ref_layers  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 ACTS = {"gelu": nn.GELU, "silu": nn.SiLU, None: None}
-NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d}
+NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d, "batch3d": nn.BatchNorm3d}
 
 
 def adversarial_(x, kind):
     """Overwrite a few entries with values at the basis' discontinuities / saturation points."""
     flat = x.view(-1)
+    kind = kind[:-2] if kind.endswith("3d") else kind
     if kind in ("kan", "kan1d", "kanlayer"):
         vals = [-2.2000000477, -1.8000000715, -1.0, -0.6000000238, 0.2000000179, 1.0, 2.2000000477,
                 2.1999998, -2.3, 2.5, 7.0, -9.0, 0.0]
@@ -71,6 +72,16 @@ CASES = [
     ("kanlayer_small", "kanlayer", dict(input_features=7, output_features=5, base_activation="gelu"), (6, 7)),
     ("kanlayer_silu_g3k2", "kanlayer", dict(input_features=12, output_features=9, grid_size=3, spline_order=2,
                                             grid_range=[-2, 2], base_activation="silu"), (5, 12)),
+    # round 2: 3-D convolution layers (the *KANConv3DLayer bindings of the four families)
+    ("kan3d_small", "kan3d", dict(input_dim=3, output_dim=5, kernel_size=3, padding=1, base_activation="gelu"), (2, 3, 5, 7, 6)),
+    ("kan3d_groups_s2", "kan3d", dict(input_dim=4, output_dim=4, kernel_size=3, padding=1, stride=2, groups=2,
+                                      base_activation="silu", affine=True), (2, 4, 6, 7, 8)),
+    ("kan3d_k2_dil2_bn", "kan3d", dict(input_dim=2, output_dim=3, kernel_size=2, padding=1, dilation=2,
+                                       base_activation="silu", norm_layer="batch3d"), (3, 2, 5, 6, 6)),
+    ("cheby3d_small", "cheby3d", dict(input_dim=3, output_dim=4, kernel_size=3, padding=1, degree=3), (2, 3, 4, 6, 5)),
+    ("gram3d_small", "gram3d", dict(input_dim=3, output_dim=4, kernel_size=3, padding=1, degree=3), (2, 3, 4, 6, 5)),
+    ("fast3d_small", "fast3d", dict(input_dim=3, output_dim=4, kernel_size=3, padding=1), (2, 3, 4, 6, 5)),
+    ("fast3d_s2_nopad", "fast3d", dict(input_dim=4, output_dim=4, kernel_size=3, padding=0, stride=2, groups=2), (2, 4, 7, 7, 9)),
     # round 2: non-finite inputs (NaN => NaN, +-Inf => NaN through 0 * Inf in the Cox-de Boor recursion).
     # One poisoned element per image: the fixture records which outputs / gradients the reference turns into NaN.
     ("kan_naninf", "kan", dict(input_dim=4, output_dim=6, kernel_size=3, padding=1, base_activation="silu"), (4, 4, 9, 7),
@@ -82,7 +93,9 @@ CASES = [
 ]
 
 CTORS = {"kan": "KANConv2DLayer", "cheby": "ChebyKANConv2DLayer", "gram": "GRAMKANConv2DLayer",
-         "fast": "FastKANConv2DLayer", "kan1d": "KANConv1DLayer", "kanlayer": "KANLayer"}
+         "fast": "FastKANConv2DLayer", "kan1d": "KANConv1DLayer", "kanlayer": "KANLayer",
+         "kan3d": "KANConv3DLayer", "cheby3d": "ChebyKANConv3DLayer", "gram3d": "GRAMKANConv3DLayer",
+         "fast3d": "FastKANConv3DLayer"}
 
 
 def build(kind, kw):

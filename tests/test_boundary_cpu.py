@@ -15,7 +15,8 @@ from _util import Golden, golden_names
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer,
-         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer}
+         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer, "kan3d": K.KANConv3DLayer, "cheby3d": K.ChebyKANConv3DLayer,
+         "gram3d": K.GRAMKANConv3DLayer, "fast3d": K.FastKANConv3DLayer}
 
 
 def test_library_exports_every_declared_symbol():
@@ -67,7 +68,8 @@ def test_state_dict_compatible_with_reference(name):
     m.load_state_dict(gd.sd)                                   # strict
 
 
-@pytest.mark.parametrize("name", ["kan_small", "kan_silu_groups_s2", "cheby_small", "fast_small", "kan_c8_16"])
+@pytest.mark.parametrize("name", ["kan_small", "kan_silu_groups_s2", "cheby_small", "fast_small", "kan_c8_16", "kan3d_small",
+                                  "cheby3d_small", "fast3d_small"])
 def test_same_seed_same_weights_as_reference(name):
     """Construction consumes the RNG like the reference ctor, so seed 0 reproduces the fixture's weights exactly."""
     gd = Golden(name)

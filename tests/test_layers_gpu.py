@@ -14,7 +14,8 @@ from _util import Golden, golden_names, rel_err, run_fwd_bwd, tol_violations
 
 pytestmark = pytest.mark.gpu
 CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer,
-         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer}
+         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer, "kan3d": K.KANConv3DLayer, "cheby3d": K.ChebyKANConv3DLayer,
+         "gram3d": K.GRAMKANConv3DLayer, "fast3d": K.FastKANConv3DLayer}
 FP32_TOL = 1e-5
 BF16_TOL = 2e-2
 
@@ -57,6 +58,7 @@ def test_fp32_path_matches_reference_golden(name):
 
 TC_CASES = ["kan_small", "kan_c8_16", "kan_batchnorm", "cheby_small", "gram_small", "fast_small", "kan_g3k2_1x1",
             "fast_bn_g5_1x1", "kan1d_small", "kan1d_groups_s2", "kanlayer_small", "kanlayer_silu_g3k2",
+            "kan3d_small", "kan3d_groups_s2", "cheby3d_small", "gram3d_small", "fast3d_small",
             "kan_naninf", "cheby_naninf", "gram_naninf"]      # the *_naninf cases: NaN / +-Inf inputs, NaN masks must match
 
 
