@@ -9,7 +9,7 @@ from . import build as _build
 c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
 KC_OK, KC_ERR_INVALID, KC_ERR_UNSUPPORTED, KC_ERR_CUDA = 0, -1, -2, -3
-BASIS_BSPLINE, BASIS_CHEBY, BASIS_GRAM, BASIS_RBF = 0, 1, 2, 3
+BASIS_BSPLINE, BASIS_CHEBY, BASIS_GRAM, BASIS_RBF, BASIS_RECUR, BASIS_RECUR_DM = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_IDENTITY, ACT_GELU, ACT_SILU = -1, 0, 1, 2
 NORM_NONE, NORM_INSTANCE, NORM_BATCH = 0, 1, 2
 OUT_NONE, OUT_PRELU, OUT_SILU = 0, 1, 2

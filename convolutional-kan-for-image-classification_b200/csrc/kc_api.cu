@@ -66,7 +66,7 @@ int kc_sm_count() {
 
 int kc_validate_desc(const kc_desc* d) {
   if (!d) KC_FAIL(KC_ERR_INVALID, "null kc_desc");
-  if (d->basis < KC_BASIS_BSPLINE || d->basis > KC_BASIS_RBF) KC_FAIL(KC_ERR_INVALID, "kc_desc: unknown basis kind %d", d->basis);
+  if (d->basis < KC_BASIS_BSPLINE || d->basis > KC_BASIS_RECUR_DM) KC_FAIL(KC_ERR_INVALID, "kc_desc: unknown basis kind %d", d->basis);
   if (d->act < KC_ACT_NONE || d->act > KC_ACT_SILU) KC_FAIL(KC_ERR_INVALID, "kc_desc: unknown activation kind %d", d->act);
   if (d->n <= 0 || d->cin <= 0 || d->h <= 0 || d->w <= 0 || d->cout <= 0)
     KC_FAIL(KC_ERR_INVALID, "kc_desc: n, cin, h, w, cout must be positive");
@@ -85,6 +85,8 @@ int kc_validate_desc(const kc_desc* d) {
   if ((d->basis == KC_BASIS_CHEBY || d->basis == KC_BASIS_GRAM) && d->nb != d->order + 1)
     KC_FAIL(KC_ERR_INVALID, "kc_desc: polynomial basis needs nb == degree+1");
   if (d->basis == KC_BASIS_CHEBY && d->act != KC_ACT_NONE) KC_FAIL(KC_ERR_INVALID, "kc_desc: Chebyshev layer has no base branch");
+  if ((d->basis == KC_BASIS_RECUR || d->basis == KC_BASIS_RECUR_DM) && d->nparams != 4 + 3 * (d->nb > 2 ? d->nb - 2 : 0))
+    KC_FAIL(KC_ERR_INVALID, "kc_desc: recurrence basis of width %d needs %d params, got %d", d->nb, 4 + 3 * (d->nb > 2 ? d->nb - 2 : 0), d->nparams);
   if (d->basis == KC_BASIS_RBF && d->nparams != d->nb + 1) KC_FAIL(KC_ERR_INVALID, "kc_desc: RBF needs nb grid points + denominator");
   if (d->x_batch_stride < (long long)d->cin * d->h * d->w) KC_FAIL(KC_ERR_INVALID, "kc_desc: x_batch_stride too small");
   if (d->z_batch_stride < (long long)d->cout * d->ho * d->wo) KC_FAIL(KC_ERR_INVALID, "kc_desc: z_batch_stride too small");

@@ -191,6 +191,28 @@ __device__ __forceinline__ int kc_bspline_local(const KcBasisCtx& B, float x, fl
   return i0 - K;
 }
 
+// Three-term recurrence polynomials p_j(t) and d p_j / dx = p_j'(t) * dt for j < nb (KC_BASIS_RECUR*; coefficient layout in
+// kanconv.h).  Host + device so that the arithmetic can be checked on the CPU (tests/test_recur_host_cpu.py).
+__host__ __device__ inline void kc_recur_eval(const float* p, int nb, float t, float dt, float* phi, float* dphi, int stride) {
+  float p0 = p[1], d0 = 0.0f;                       // p_0 = c0
+  float p1 = p[2] * t + p[3], d1 = p[2];            // p_1 = a1 t + b1
+  phi[0] = p0;
+  if (dphi) dphi[0] = 0.0f;
+  if (nb > 1) {
+    phi[stride] = p1;
+    if (dphi) dphi[stride] = d1 * dt;
+  }
+  for (int i = 2; i < nb; ++i) {
+    const float A = p[4 + 3 * (i - 2)], Bc = p[5 + 3 * (i - 2)], C = p[6 + 3 * (i - 2)];
+    const float m = A * t + Bc;
+    const float p2 = m * p1 + C * p0;
+    const float d2 = A * p1 + m * d1 + C * d0;
+    phi[i * stride] = p2;
+    if (dphi) dphi[i * stride] = d2 * dt;
+    p0 = p1; p1 = p2; d0 = d1; d1 = d2;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Generic evaluation into memory (shared or local): phi[j*stride], dphi[j*stride] for j < nb.
 // dphi may be nullptr.  For GRAM, dphi is d/dx (through tanh); see kc_gram_dbeta for d/d beta.
@@ -247,6 +269,13 @@ __device__ inline void kc_eval_basis(const KcBasisCtx& B, float x, float* phi, f
       if (dphi) dphi[i * stride] = kc_silu_grad(p2) * d2 * dt;
       p0 = p1; p1 = p2; d0 = d1; d1 = d2;
     }
+  } else if (B.kind == KC_BASIS_RECUR || B.kind == KC_BASIS_RECUR_DM) {
+    // three-term recurrence families (kanconv.h, kc_basis_kind): hermite_kan_layers.py:127-150 and siblings, on t = tanh(x);
+    // Legendre's min-max normalised input arrives "pre-squashed" (params[0] != 0), like GRAM's dropout path
+    const bool pre = B.p[0] != 0.0f;
+    const float t = pre ? x : tanhf(x);
+    const float dt = pre ? 1.0f : 1.0f - t * t;
+    kc_recur_eval(B.p, nb, t, dt, phi, dphi, stride);
   } else {
     // utils/utils.py:32-33: exp(-((u - g_j)/den)^2); params = grid[0..G-1], den
     float den = B.p[nb];
@@ -280,7 +309,7 @@ __device__ inline void kc_gram_dbeta(const KcBasisCtx& B, float x, const float* 
 
 // index of (channel c, basis j) inside the reference's w_basis inner dimension
 __device__ __forceinline__ int kc_wbasis_index(int kind, int c, int j, int cin, int nb) {
-  return (kind == KC_BASIS_GRAM) ? (j * cin + c) : (c * nb + j);
+  return (kind == KC_BASIS_GRAM || kind == KC_BASIS_RECUR_DM) ? (j * cin + c) : (c * nb + j);
 }
 
 __device__ __forceinline__ float kc_warp_sum(float v) {

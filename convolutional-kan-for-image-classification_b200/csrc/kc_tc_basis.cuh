@@ -113,6 +113,10 @@ __device__ inline void tc_eval_basis(const KcBasisCtx& B, float x, float* phi, f
       const float p2 = t * p1 - b * p0, d2 = p1 + t * d1 - b * d0;
       p0 = p1; p1 = p2; d0 = d1; d1 = d2;
     }
+  } else if (B.kind == KC_BASIS_RECUR || B.kind == KC_BASIS_RECUR_DM) {
+    const bool pre = B.p[0] != 0.0f;
+    const float t = pre ? x : tc_tanh(x), dt = pre ? 1.0f : 1.0f - t * t;
+    kc_recur_eval(B.p, nb, t, dt, phi, dphi, 1);
   } else {
     kc_eval_basis(B, x, phi, dphi, 1);
   }

@@ -42,7 +42,16 @@ typedef enum kc_basis_kind {
   KC_BASIS_BSPLINE = 0, /* KANConvNDLayer      layers/kan_layers.py:203-233  (Cox-de Boor)               */
   KC_BASIS_CHEBY = 1,   /* ChebyKANConvNDLayer layers/cheby_kan_layers.py:93-96                          */
   KC_BASIS_GRAM = 2,    /* GRAMKANConvNDLayer  layers/gram_kan_layers.py:150-181 (SiLU of Gram polys)    */
-  KC_BASIS_RBF = 3      /* FastKANConvNDLayer  utils/utils.py:19-33 (Gaussian RBF)                       */
+  KC_BASIS_RBF = 3,     /* FastKANConvNDLayer  utils/utils.py:19-33 (Gaussian RBF)                       */
+  /* Polynomials by a three-term recurrence with constant coefficients on t = tanh(x) (or on x itself, params[0] != 0):
+   *   p_0 = c0,  p_1 = a1 t + b1,  p_i = (A_i t + B_i) p_{i-1} + C_i p_{i-2}     (i = 2 .. nb-1)
+   * params = { pre, c0, a1, b1, A_2, B_2, C_2, A_3, B_3, C_3, ... }, nparams = 4 + 3 * max(nb - 2, 0).
+   * One functor for the reference's Hermite / Gegenbauer / Laguerre / Lucas / Fibonacci / Bessel / Taylor layers
+   * (layers/hermite_kan_layers.py:127-150 and the same method of the sibling files: expanded channel c*nb + j) and, with
+   * the degree-major channel order j*cin + c of `torch.concatenate(polys, dim=1)`, for the Legendre / Jacobi layers
+   * (layers/legendre_kan_layers.py:108-121, layers/jacobi_kan_layers.py:119-137). */
+  KC_BASIS_RECUR = 4,   /* channel-major  (c*nb + j)  */
+  KC_BASIS_RECUR_DM = 5 /* degree-major   (j*cin + c) */
 } kc_basis_kind;
 
 typedef enum kc_act_kind {
@@ -64,7 +73,8 @@ typedef struct kc_desc {
   int32_t kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int32_t nb;                 /* basis width: G+K | D+1 | G                                        */
   int32_t order;              /* spline order K | polynomial degree D | unused                     */
-  int32_t nparams;            /* B-spline: G+2K+1 knots; RBF: G grid points then the denominator   */
+  int32_t nparams;            /* B-spline: G+2K+1 knots; RBF: G grid points then the denominator;
+                                 RECUR: 4 + 3*(nb-2) recurrence coefficients (see kc_basis_kind)     */
   int64_t x_batch_stride;     /* elements between images of x   (>= cin*h*w)                       */
   int64_t z_batch_stride;     /* elements between images of z/dz (>= cout*ho*wo)                   */
   float params[KC_MAX_PARAMS];

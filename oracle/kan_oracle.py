@@ -24,6 +24,8 @@ Reference call sites restated here (paths relative to the reference tree):
   * KANConv1DLayer (ndim = 1 binding) ............ layers/kan_layers.py:287-297
   * *KANConv3DLayer (ndim = 3 bindings) .......... layers/kan_layers.py:261-271, cheby_kan_layers.py:114-121,
                                                    gram_kan_layers.py:202-209, fast_kan_layers.py:123-134
+  * Hermite / Gegenbauer / Laguerre / Lucas / Fibonacci / Bessel / Taylor / Legendre / Jacobi KANConvNDLayer
+    (three-term-recurrence polynomial families) .. layers/<family>_kan_layers.py, lines cited at recurrence_polys()
   * KAN (MLP of KANLayers) ....................... models/kans.py:300-327
   * VGG.make_layers / forward .................... models/kan_vgg.py:40-188
 
@@ -45,6 +47,7 @@ __all__ = [
     "kan_conv2d", "cheby_conv2d", "gram_conv2d", "fastkan_conv2d",
     "OracleKANConv2D", "OracleChebyKANConv2D", "OracleGRAMKANConv2D", "OracleFastKANConv2D",
     "OracleKANConv3D", "OracleChebyKANConv3D", "OracleGRAMKANConv3D", "OracleFastKANConv3D",
+    "OraclePolyKANConv", "OracleDegreeMajorPolyKANConv", "recurrence_polys", "polykan_conv", "degree_major_polykan_conv",
     "OracleKANConv1D", "OracleKANLayer", "OracleKAN", "kan_conv1d", "kan_linear",
     "OracleVGG", "VGG_CFGS", "conv_flops",
 ]
@@ -112,6 +115,72 @@ def gram_basis(t: torch.Tensor, degree: int, beta_weights: torch.Tensor) -> List
 def rbf_basis(u: torch.Tensor, grid: torch.Tensor, denominator: float) -> torch.Tensor:
     """exp(-((u - g_j) / den)^2), utils/utils.py:32-33.  [..., G]."""
     return torch.exp(-((u.unsqueeze(-1) - grid.to(u.dtype)) / denominator) ** 2)
+
+
+def recurrence_polys(family: str, t: torch.Tensor, degree: int, **fam) -> List[torch.Tensor]:
+    """Polynomials [p_0(t), ..., p_D(t)] of the reference's three-term-recurrence families, each written as its own file writes it:
+      hermite     hermite_kan_layers.py:136-146     H_0 = 1, H_1 = 2t, H_i = 2t H_{i-1} - 2(i-1) H_{i-2}
+      gegenbauer  gegenbauer_kan_layers.py:143-153  C_0 = 1, C_1 = 2at, C_{n+1} = (2(n+a) t C_n - (n+2a-1) C_{n-1}) / (n+1)
+      laguerre    laguerre_kan_layers.py:151-163    L_0 = 1, L_1 = 1+a-t, L_k = ((2(k-1)+1+a-t) L_{k-1} - (k-1+a) L_{k-2}) / k
+      lucas       lucas_kan_layers.py:163-171       L_0 = 2, L_1 = t, L_i = t L_{i-1} + L_{i-2}
+      fibonacci   fibonacci_kan_layers.py:152-160   F_0 = 0, F_1 = 1, F_i = t F_{i-1} + F_{i-2}
+      bessel      bessel_kan_layers.py:144-153      y_0 = 1, y_1 = t+1, y_i = (2i-1) t y_{i-1} + y_{i-2}
+      taylor      taylor_kan_layers.py:143-148      t^0 .. t^(degree-1)   (``degree`` counts the TERMS)
+      legendre    legendre_kan_layers.py:108-121    P_0 = 1, P_1 = t, P_{n+1} = ((2n+1) t P_n - n P_{n-1}) / (n+1)
+      jacobi      jacobi_kan_layers.py:119-137      P_1 = ((a-b) + (a+b+2) t) / 2, theta recurrences"""
+    one = torch.ones_like(t)
+    if family == "taylor":
+        polys = [one]
+        if degree > 1:
+            polys.append(t)
+            for _ in range(2, degree):
+                polys.append(polys[-1] * t)
+        return polys
+    if family == "fibonacci":
+        polys = [torch.zeros_like(t)]
+    elif family == "lucas":
+        polys = [2 * one]
+    else:
+        polys = [one]
+    if degree < 1:
+        return polys
+    if family == "hermite":
+        polys.append(2 * t)
+        for i in range(2, degree + 1):
+            polys.append(2 * t * polys[i - 1] - 2 * (i - 1) * polys[i - 2])
+    elif family == "gegenbauer":
+        a = fam["alpha_param"]
+        polys.append(2 * a * t)
+        for n in range(1, degree):
+            polys.append((2 * (n + a) * t * polys[n] - (n + 2 * a - 1) * polys[n - 1]) / (n + 1))
+    elif family == "laguerre":
+        a = fam["alpha"]
+        polys.append((1 + a) - t)
+        for k in range(2, degree + 1):
+            polys.append(((2 * (k - 1) + 1 + a - t) * polys[k - 1] - (k - 1 + a) * polys[k - 2]) / k)
+    elif family in ("lucas", "fibonacci"):
+        polys.append(t if family == "lucas" else one)
+        for i in range(2, degree + 1):
+            polys.append(t * polys[i - 1] + polys[i - 2])
+    elif family == "bessel":
+        polys.append(t + 1)
+        for i in range(2, degree + 1):
+            polys.append((2 * i - 1) * t * polys[i - 1] + polys[i - 2])
+    elif family == "legendre":
+        polys.append(t)
+        for n in range(1, degree):
+            polys.append(((2.0 * n + 1.0) * t * polys[-1] - n * polys[-2]) / (n + 1.0))
+    elif family == "jacobi":
+        a, b = fam["a"], fam["b"]
+        polys.append(((a - b) + (a + b + 2) * t) / 2)
+        for i in range(2, degree + 1):
+            th_k = (2 * i + a + b) * (2 * i + a + b - 1) / (2 * i * (i + a + b))
+            th_k1 = (2 * i + a + b - 1) * (a * a - b * b) / (2 * i * (i + a + b) * (2 * i + a + b - 2))
+            th_k2 = (i + a - 1) * (i + b - 1) * (2 * i + a + b) / (i * (i + a + b) * (2 * i + a + b - 2))
+            polys.append((th_k * t + th_k1) * polys[i - 1] - th_k2 * polys[i - 2])
+    else:
+        raise ValueError(family)
+    return polys
 
 
 def _act(name: Optional[str]) -> Callable[[torch.Tensor], torch.Tensor]:
@@ -195,6 +264,32 @@ def fastkan_conv2d(x, w_base, w_spline, grid, denominator, act="silu", stride=1,
     return base + _convnd(phi, w_spline, stride, padding, dilation)
 
 
+def polykan_conv(family, x, w_base, w_poly, prelu_weight, degree, act="gelu", stride=1, padding=0, dilation=1,
+                 norm="instance", eps=1e-5, norm_weight=None, norm_bias=None, running=None, training=True, **fam):
+    """One group of the template-A layers (hermite_kan_layers.py:152-161 and the same method of the gegenbauer / laguerre /
+    lucas / fibonacci / bessel / taylor files): PReLU(norm(conv(act(x)) + conv(P(tanh x)))), expanded channel c*nb + j
+    (``basis.view(batch, channels * (degree + 1), ...)`` of a [B, C, D+1, ...] tensor)."""
+    base = _convnd(_act(act)(x), w_base, stride, padding, dilation)
+    phi = torch.stack(recurrence_polys(family, torch.tanh(x), degree, **fam), dim=2).flatten(1, 2)
+    z = base + _convnd(phi, w_poly, stride, padding, dilation)
+    return F.prelu(_norm(z, norm, eps, norm_weight, norm_bias, running, training), prelu_weight)
+
+
+def degree_major_polykan_conv(family, x, w_base, w_poly, degree, out_act="silu", stride=1, padding=0, dilation=1,
+                              norm="instance", eps=1e-5, norm_weight=None, norm_bias=None, **fam):
+    """One group of LegendreKANConvNDLayer.forward_kal (legendre_kan_layers.py:123-152) / JacobiKANConvNDLayer.forward_kaj
+    (jacobi_kan_layers.py:139-168): base conv on x itself, polynomials concatenated degree-major (channel j*C + c), output
+    activation after the norm.  Legendre normalises x with the min / max of the whole group tensor, Jacobi with tanh."""
+    base = _convnd(x, w_base, stride, padding, dilation)
+    if family == "legendre":
+        t = 2 * (x - x.min()) / (x.max() - x.min()) - 1
+    else:
+        t = torch.tanh(x)
+    phi = torch.cat(recurrence_polys(family, t, degree, **fam), dim=1)
+    z = base + _convnd(phi, w_poly, stride, padding, dilation)
+    return _act(out_act)(_norm(z, norm, eps, norm_weight, norm_bias))
+
+
 def kan_conv1d(x, w_base, w_spline, prelu_weight, knots, spline_order, act="gelu", stride=1, padding=0, dilation=1,
                eps=1e-5, norm_weight=None, norm_bias=None):
     """One group of KANConvNDLayer.forward_kan with ndim = 1 (kan_layers.py:197-247 bound by KANConv1DLayer :287-297):
@@ -274,9 +369,9 @@ class _OracleBase(nn.Module):
         mods = []
         for _ in range(groups):
             if kind == "instance":
-                mods.append((nn.InstanceNorm2d if self._nd == 2 else nn.InstanceNorm3d)(ch, affine=affine))
+                mods.append({1: nn.InstanceNorm1d, 2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}[self._nd](ch, affine=affine))
             elif kind == "batch":
-                mods.append((nn.BatchNorm2d if self._nd == 2 else nn.BatchNorm3d)(ch))
+                mods.append({1: nn.BatchNorm1d, 2: nn.BatchNorm2d, 3: nn.BatchNorm3d}[self._nd](ch))
             else:
                 mods.append(nn.Identity())
         return nn.ModuleList(mods)
@@ -462,6 +557,78 @@ class OracleKANConv1D(_OracleBase):
             outs.append(kan_conv1d(xg, self.base_conv[g].weight, self.spline_conv[g].weight, self.prelus[g].weight,
                                    self.knots, self.spline_order, self.act, self.stride, self.padding, self.dilation,
                                    1e-5, nw, nb))
+        return torch.cat(outs, dim=1)
+
+
+class OraclePolyKANConv(_OracleBase):
+    """Template-A family layer (``family`` in hermite / gegenbauer / laguerre / lucas / fibonacci / bessel / taylor), any rank:
+    module tree base_conv / poly_conv / layer_norm / prelus like <Family>KANConvNDLayer.__init__ (hermite_kan_layers.py:30-125)."""
+
+    def __init__(self, family, nd, input_dim, output_dim, kernel_size, degree, groups=1, padding=0, stride=1, dilation=1,
+                 base_activation="gelu", norm_layer=nn.InstanceNorm2d, affine=False, **fam):
+        super().__init__()
+        self._nd = nd
+        self._check_groups(input_dim, output_dim, groups)
+        ks = self._kshape(kernel_size) if nd != 1 else (int(kernel_size),)
+        cg, og = input_dim // groups, output_dim // groups
+        nb = degree if family == "taylor" else degree + 1
+        self.family, self.fam, self.degree = family, fam, degree
+        self.groups, self.cg, self.og, self.act = groups, cg, og, _act_name(base_activation)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.norm_kind = _norm_kind(norm_layer)
+        self.base_conv = nn.ModuleList([_Weight((og, cg) + ks) for _ in range(groups)])
+        self.poly_conv = nn.ModuleList([_Weight((og, cg * nb) + ks) for _ in range(groups)])
+        self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
+        self.prelus = nn.ModuleList([nn.PReLU() for _ in range(groups)])
+        for m in list(self.base_conv) + list(self.poly_conv):
+            nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nm = self.layer_norm[g]
+            nw, nb = self._nw(nm)
+            running = (nm.running_mean, nm.running_var) if isinstance(nm, nn.modules.batchnorm._BatchNorm) else None
+            outs.append(polykan_conv(self.family, xg, self.base_conv[g].weight, self.poly_conv[g].weight,
+                                     self.prelus[g].weight, self.degree, self.act, self.stride, self.padding, self.dilation,
+                                     self.norm_kind, 1e-5, nw, nb, running, self.training, **self.fam))
+        return torch.cat(outs, dim=1)
+
+
+class OracleDegreeMajorPolyKANConv(_OracleBase):
+    """LegendreKANConvNDLayer (legendre_kan_layers.py:50-161) / JacobiKANConvNDLayer (jacobi_kan_layers.py:56-178)."""
+
+    def __init__(self, family, nd, input_dim, output_dim, kernel_size, degree=3, groups=1, padding=0, stride=1, dilation=1,
+                 base_activation="gelu", norm_layer=nn.InstanceNorm2d, affine=False, **fam):
+        super().__init__()
+        self._nd = nd
+        self._check_groups(input_dim, output_dim, groups)
+        ks = self._kshape(kernel_size) if nd != 1 else (int(kernel_size),)
+        cg, og = input_dim // groups, output_dim // groups
+        if family == "jacobi":
+            fam = dict({"a": 1.0, "b": 1.0}, **fam)           # JacobiKANConv2DLayer defaults (jacobi_kan_layers.py:191)
+        self.family, self.fam, self.degree = family, fam, degree
+        self.groups, self.cg, self.og = groups, cg, og
+        self.out_act = "silu" if family == "legendre" else _act_name(base_activation)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.norm_kind = _norm_kind(norm_layer)
+        self.base_conv = nn.ModuleList([_Weight((og, cg) + ks) for _ in range(groups)])
+        self.layer_norm = self._make_norm(og, self.norm_kind, affine, groups)
+        self.poly_weights = nn.Parameter(torch.randn(groups, og, cg * (degree + 1), *ks))
+        for m in self.base_conv:
+            nn.init.kaiming_uniform_(m.weight, nonlinearity="linear")
+        if family == "legendre":
+            nn.init.kaiming_uniform_(self.poly_weights, nonlinearity="linear")
+        else:
+            nn.init.normal_(self.poly_weights, mean=0.0, std=1 / (input_dim * (degree + 1) * math.prod(ks)))
+
+    def forward(self, x):
+        outs = []
+        for g, xg in enumerate(torch.split(x, self.cg, dim=1)):
+            nw, nb = self._nw(self.layer_norm[g])
+            outs.append(degree_major_polykan_conv(self.family, xg, self.base_conv[g].weight, self.poly_weights[g], self.degree,
+                                                  self.out_act, self.stride, self.padding, self.dilation, self.norm_kind,
+                                                  1e-5, nw, nb, **self.fam))
         return torch.cat(outs, dim=1)
 
 

@@ -1,4 +1,5 @@
 """Shared helpers for the test-suite: golden-fixture loading and oracle construction."""
+import functools
 import glob
 import json
 import os
@@ -15,6 +16,21 @@ ORACLE_CTORS = {"kan": O.OracleKANConv2D, "cheby": O.OracleChebyKANConv2D, "gram
                 "fast": O.OracleFastKANConv2D, "kan1d": O.OracleKANConv1D, "kanlayer": O.OracleKANLayer,
                 "kan3d": O.OracleKANConv3D, "cheby3d": O.OracleChebyKANConv3D, "gram3d": O.OracleGRAMKANConv3D,
                 "fast3d": O.OracleFastKANConv3D}
+# kind -> class name of the layer under test (same names in the reference's ``layers`` package and in kanconv_b200)
+LAYER_NAMES = {"kan": "KANConv2DLayer", "cheby": "ChebyKANConv2DLayer", "gram": "GRAMKANConv2DLayer", "fast": "FastKANConv2DLayer",
+               "kan1d": "KANConv1DLayer", "kanlayer": "KANLayer", "kan3d": "KANConv3DLayer", "cheby3d": "ChebyKANConv3DLayer",
+               "gram3d": "GRAMKANConv3DLayer", "fast3d": "FastKANConv3DLayer"}
+# three-term-recurrence polynomial families: kind = "<family><rank>d"
+RECURRENCE_FAMILIES = ("hermite", "gegenbauer", "laguerre", "lucas", "fibonacci", "bessel", "taylor", "legendre", "jacobi")
+for _f in RECURRENCE_FAMILIES:
+    for _n in (1, 2, 3):
+        _cls = O.OracleDegreeMajorPolyKANConv if _f in ("legendre", "jacobi") else O.OraclePolyKANConv
+        ORACLE_CTORS[f"{_f}{_n}d"] = functools.partial(_cls, _f, _n)
+        LAYER_NAMES[f"{_f}{_n}d"] = f"{_f.capitalize()}KANConv{_n}DLayer"
+
+
+def layer_class(package, kind):
+    return getattr(package, LAYER_NAMES[kind])
 
 
 # whole-model fixtures (make_model_golden.py): a different record layout

@@ -29,7 +29,7 @@ NORMS = {"instance": nn.InstanceNorm2d, "batch": nn.BatchNorm2d, "batch3d": nn.B
 def adversarial_(x, kind):
     """Overwrite a few entries with values at the basis' discontinuities / saturation points."""
     flat = x.view(-1)
-    kind = kind[:-2] if kind.endswith("3d") else kind
+    kind = kind[:-2] if kind[-2:] in ("1d", "2d", "3d") and kind != "kan1d" else kind
     if kind in ("kan", "kan1d", "kanlayer"):
         vals = [-2.2000000477, -1.8000000715, -1.0, -0.6000000238, 0.2000000179, 1.0, 2.2000000477,
                 2.1999998, -2.3, 2.5, 7.0, -9.0, 0.0]
@@ -82,6 +82,31 @@ CASES = [
     ("gram3d_small", "gram3d", dict(input_dim=3, output_dim=4, kernel_size=3, padding=1, degree=3), (2, 3, 4, 6, 5)),
     ("fast3d_small", "fast3d", dict(input_dim=3, output_dim=4, kernel_size=3, padding=1), (2, 3, 4, 6, 5)),
     ("fast3d_s2_nopad", "fast3d", dict(input_dim=4, output_dim=4, kernel_size=3, padding=0, stride=2, groups=2), (2, 4, 7, 7, 9)),
+    # round 2: the three-term-recurrence polynomial families; kind = "<family><rank>d"
+    ("hermite_small", "hermite2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, padding=1), (2, 4, 9, 7)),
+    ("hermite_groups_s2_silu", "hermite2d", dict(input_dim=4, output_dim=4, kernel_size=3, degree=4, padding=1, stride=2, groups=2,
+                                                 base_activation="silu", affine=True), (3, 4, 8, 10)),
+    ("gegenbauer_small", "gegenbauer2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, alpha_param=0.5, padding=1),
+     (2, 4, 9, 7)),
+    ("gegenbauer_d5_1x1", "gegenbauer2d", dict(input_dim=5, output_dim=3, kernel_size=1, degree=5, alpha_param=1.5, padding=0,
+                                               base_activation="silu"), (2, 5, 6, 5)),
+    ("laguerre_small", "laguerre2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, alpha=1.0, padding=1), (2, 4, 9, 7)),
+    ("laguerre_bn_dil2", "laguerre2d", dict(input_dim=3, output_dim=4, kernel_size=3, degree=4, alpha=0.0, padding=2, dilation=2,
+                                            norm_layer="batch"), (3, 3, 8, 8)),
+    ("lucas_small", "lucas2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, padding=1), (2, 4, 9, 7)),
+    ("fibonacci_small", "fibonacci2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=4, padding=1), (2, 4, 9, 7)),
+    ("bessel_small", "bessel2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, padding=1), (2, 4, 9, 7)),
+    ("taylor_small", "taylor2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=4, padding=1), (2, 4, 9, 7)),
+    ("taylor_d1", "taylor2d", dict(input_dim=4, output_dim=4, kernel_size=3, degree=1, padding=1, groups=2), (2, 4, 6, 6)),
+    ("legendre_small", "legendre2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, padding=1), (2, 4, 9, 7)),
+    ("legendre_groups_s2", "legendre2d", dict(input_dim=4, output_dim=4, kernel_size=3, degree=4, padding=1, stride=2, groups=2),
+     (3, 4, 8, 10)),
+    ("jacobi_small", "jacobi2d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, padding=1), (2, 4, 9, 7)),
+    ("jacobi_a2_b05_silu", "jacobi2d", dict(input_dim=4, output_dim=4, kernel_size=3, degree=4, a=2.0, b=0.5, padding=1, groups=2,
+                                            base_activation="silu"), (2, 4, 8, 8)),
+    ("hermite1d_small", "hermite1d", dict(input_dim=4, output_dim=6, kernel_size=3, degree=3, padding=1), (2, 4, 11)),
+    ("bessel3d_small", "bessel3d", dict(input_dim=3, output_dim=4, kernel_size=3, degree=2, padding=1), (2, 3, 4, 6, 5)),
+    ("legendre3d_small", "legendre3d", dict(input_dim=3, output_dim=4, kernel_size=3, degree=2, padding=1), (2, 3, 4, 6, 5)),
     # round 2: non-finite inputs (NaN => NaN, +-Inf => NaN through 0 * Inf in the Cox-de Boor recursion).
     # One poisoned element per image: the fixture records which outputs / gradients the reference turns into NaN.
     ("kan_naninf", "kan", dict(input_dim=4, output_dim=6, kernel_size=3, padding=1, base_activation="silu"), (4, 4, 9, 7),
@@ -96,6 +121,9 @@ CTORS = {"kan": "KANConv2DLayer", "cheby": "ChebyKANConv2DLayer", "gram": "GRAMK
          "fast": "FastKANConv2DLayer", "kan1d": "KANConv1DLayer", "kanlayer": "KANLayer",
          "kan3d": "KANConv3DLayer", "cheby3d": "ChebyKANConv3DLayer", "gram3d": "GRAMKANConv3DLayer",
          "fast3d": "FastKANConv3DLayer"}
+for _f in ("Hermite", "Gegenbauer", "Laguerre", "Lucas", "Fibonacci", "Bessel", "Taylor", "Legendre", "Jacobi"):
+    for _n in (1, 2, 3):
+        CTORS[f"{_f.lower()}{_n}d"] = f"{_f}KANConv{_n}DLayer"
 
 
 def build(kind, kw):

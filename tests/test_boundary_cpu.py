@@ -11,12 +11,10 @@ import torch.nn as nn
 
 import kanconv_b200 as K
 from kanconv_b200 import _lib as L
-from _util import Golden, golden_names
+from _util import LAYER_NAMES, Golden, golden_names
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer,
-         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer, "kan3d": K.KANConv3DLayer, "cheby3d": K.ChebyKANConv3DLayer,
-         "gram3d": K.GRAMKANConv3DLayer, "fast3d": K.FastKANConv3DLayer}
+CTORS = {k: getattr(K, v) for k, v in LAYER_NAMES.items()}
 
 
 def test_library_exports_every_declared_symbol():
@@ -69,7 +67,8 @@ def test_state_dict_compatible_with_reference(name):
 
 
 @pytest.mark.parametrize("name", ["kan_small", "kan_silu_groups_s2", "cheby_small", "fast_small", "kan_c8_16", "kan3d_small",
-                                  "cheby3d_small", "fast3d_small"])
+                                  "cheby3d_small", "fast3d_small", "hermite_small", "gegenbauer_d5_1x1", "laguerre_small",
+                                  "taylor_d1", "legendre_groups_s2", "jacobi_a2_b05_silu", "bessel3d_small"])
 def test_same_seed_same_weights_as_reference(name):
     """Construction consumes the RNG like the reference ctor, so seed 0 reproduces the fixture's weights exactly."""
     gd = Golden(name)
@@ -111,8 +110,21 @@ def test_factory_mirrors_reference():
     # extra kwargs are swallowed by **norm_kwargs and filtered against the norm signature, like upstream
     layer = f["KAN"](3, 8, 3, affine=True, degree=7, base_activation=nn.SiLU)
     assert layer.layer_norm[0].affine
-    with pytest.raises(NotImplementedError):
-        f["LegendreKAN"](3, 8, 3)
+    for key in ("WavKAN", "BersnsteinKAN", "FourierKAN", "ReLUKAN"):         # present, but outside the hot path
+        with pytest.raises(NotImplementedError):
+            f[key](3, 8, 3)
+    # the three-term-recurrence families (kan_conv.py:120-157, 354-724): same defaults and quirks as upstream
+    assert isinstance(f["LegendreKAN"](3, 8, 3), K.LegendreKANConv2DLayer)
+    g = f["GegenbauerKAN"](4, 8, 3, alpha_param=0.5, affine=True, dilation=2)
+    assert isinstance(g, K.GegenbauerKANConv2DLayer) and g.alpha_param == 0.5 and g.layer_norm[0].affine
+    assert g.padding == 2 and g.dilation == 1                                   # upstream's builders drop `dilation`
+    assert f["LaguerreKAN"](4, 8, 3).alpha == 1.0 and f["JacobiKAN"](4, 8, 3, b=2.0).b == 2.0
+    assert f["TaylorKAN"](4, 8, 3, degree=4).poly_conv[0].weight.shape[1] == 4 * 4
+    assert type(f["HermiteKAN"](4, 4, 3, l1_decay=1e-4)).__name__ == "L1"
+    with pytest.raises(ValueError, match="degree must be at least 1"):
+        f["FibonacciKAN"](4, 4, 3, degree=0)
+    with pytest.raises(ValueError, match="alpha_param must be greater than -0.5"):
+        K.GegenbauerKANConv2DLayer(4, 4, 3, 3, -0.5)
     assert isinstance(f["conv"](3, 8, 3), nn.Conv2d)
 
 

@@ -10,12 +10,10 @@ import torch.nn as nn
 import kanconv_b200 as K
 from kanconv_b200 import _lib as L
 from oracle import kan_oracle as O
-from _util import Golden, golden_names, rel_err, run_fwd_bwd, tol_violations
+from _util import LAYER_NAMES, Golden, golden_names, rel_err, run_fwd_bwd, tol_violations
 
 pytestmark = pytest.mark.gpu
-CTORS = {"kan": K.KANConv2DLayer, "cheby": K.ChebyKANConv2DLayer, "gram": K.GRAMKANConv2DLayer, "fast": K.FastKANConv2DLayer,
-         "kan1d": K.KANConv1DLayer, "kanlayer": K.KANLayer, "kan3d": K.KANConv3DLayer, "cheby3d": K.ChebyKANConv3DLayer,
-         "gram3d": K.GRAMKANConv3DLayer, "fast3d": K.FastKANConv3DLayer}
+CTORS = {k: getattr(K, v) for k, v in LAYER_NAMES.items()}
 FP32_TOL = 1e-5
 BF16_TOL = 2e-2
 
@@ -59,6 +57,9 @@ def test_fp32_path_matches_reference_golden(name):
 TC_CASES = ["kan_small", "kan_c8_16", "kan_batchnorm", "cheby_small", "gram_small", "fast_small", "kan_g3k2_1x1",
             "fast_bn_g5_1x1", "kan1d_small", "kan1d_groups_s2", "kanlayer_small", "kanlayer_silu_g3k2",
             "kan3d_small", "kan3d_groups_s2", "cheby3d_small", "gram3d_small", "fast3d_small",
+            "hermite_small", "hermite_groups_s2_silu", "gegenbauer_small", "gegenbauer_d5_1x1", "laguerre_small", "lucas_small",
+            "fibonacci_small", "bessel_small", "taylor_small", "taylor_d1", "legendre_small", "legendre_groups_s2",
+            "jacobi_small", "jacobi_a2_b05_silu", "hermite1d_small", "bessel3d_small", "legendre3d_small",
             "kan_naninf", "cheby_naninf", "gram_naninf"]      # the *_naninf cases: NaN / +-Inf inputs, NaN masks must match
 
 
@@ -239,6 +240,72 @@ def test_bf16_tensor_core_backward_vs_oracle(kind, cin, cout, hw, n):
     for k in go:
         errs[k] = rel_err(gr[k], go[k])
     print(kind, cin, cout, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["y"] < BF16_TOL, errs
+    assert max(errs.values()) < 0.15, errs
+
+
+RECUR_FAMS = {"hermite": {}, "gegenbauer": {"alpha_param": 0.5}, "laguerre": {"alpha": 1.0}, "lucas": {}, "fibonacci": {},
+              "bessel": {}, "taylor": {}, "legendre": {}, "jacobi": {"a": 1.0, "b": 2.0}}
+
+
+@pytest.mark.parametrize("fam,cin,cout,hw,n,degree", [("hermite", 32, 64, 16, 2, 3), ("gegenbauer", 64, 128, 32, 2, 3),
+                                                      ("laguerre", 16, 320, 20, 2, 3), ("lucas", 24, 40, 9, 3, 5),
+                                                      ("fibonacci", 40, 24, 13, 2, 4), ("bessel", 32, 64, 16, 2, 3),
+                                                      ("taylor", 3, 32, 18, 2, 4), ("legendre", 32, 64, 16, 2, 3),
+                                                      ("jacobi", 64, 128, 15, 2, 3), ("hermite", 128, 256, 15, 1, 7)])
+def test_bf16_tensor_core_recurrence_families_conv_op(fam, cin, cout, hw, n, degree):
+    """KC_BASIS_RECUR / RECUR_DM through the tensor-core kernels at model-like channel counts: z, dX (for Legendre also the
+    gradient w.r.t. the pre-normalised basis input), dW_base, dW_poly vs the fp64 oracle's functional pieces, BF16 tolerance."""
+    import torch.nn.functional as F
+    from kanconv_b200 import functional as KF
+    kw = dict(RECUR_FAMS[fam])
+    torch.manual_seed(0)
+    mod = CTORS[fam + "2d"](cin, cout, 3, degree=degree, padding=1, **kw).cuda()
+    dm = fam in ("legendre", "jacobi")
+    wb = mod.base_conv[0].weight
+    wp = mod.poly_weights[0] if dm else mod.poly_conv[0].weight
+    torch.manual_seed(3)
+    x = torch.randn(n, cin, hw, hw + 3)
+    g = torch.randn(n, cout, hw, hw + 3)
+    # oracle (fp64)
+    xx = x.double().requires_grad_(True)
+    wbo, wpo = wb.detach().double().cpu().requires_grad_(True), wp.detach().double().cpu().requires_grad_(True)
+    tt = None
+    if fam == "legendre":
+        tt = (2 * (x.double() - x.double().min()) / (x.double().max() - x.double().min()) - 1).requires_grad_(True)
+        polys = O.recurrence_polys(fam, tt, degree)
+    else:
+        polys = O.recurrence_polys(fam, torch.tanh(xx), degree, **kw)
+    phi = torch.cat(polys, dim=1) if dm else torch.stack(polys, dim=2).flatten(1, 2)
+    base_in = xx if dm else F.gelu(xx)
+    zo = F.conv2d(base_in, wbo, padding=1) + F.conv2d(phi, wpo, padding=1)
+    zo.backward(g.double())
+    # CUDA
+    xg = x.cuda().requires_grad_(True)
+    tg = None if tt is None else tt.detach().float().cuda().requires_grad_(True)
+    z = KF.kan_conv(mod._spec, xg, tg, None, [wb], [wp], "bf16")
+    z.backward(g.cuda())
+    dwp = mod.poly_weights.grad[0] if dm else wp.grad
+    errs = {"z": rel_err(z, zo), "dx": rel_err(xg.grad, xx.grad), "dw_base": rel_err(wb.grad, wbo.grad), "dw_poly": rel_err(dwp, wpo.grad)}
+    if tg is not None:
+        errs["dt"] = rel_err(tg.grad, tt.grad)
+    print(fam, cin, cout, degree, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < BF16_TOL, errs
+
+
+@pytest.mark.parametrize("name", ["hermite_small", "gegenbauer_small", "laguerre_small", "lucas_small", "fibonacci_small",
+                                  "bessel_small", "taylor_small", "legendre_small", "jacobi_small", "jacobi_a2_b05_silu",
+                                  "bessel3d_small", "legendre3d_small"])
+def test_bf16_recurrence_family_layers_fwd_bwd_vs_reference_golden(name):
+    """Whole layers of the recurrence families in BF16 mode against the reference fixtures: y within the BF16 tolerance,
+    gradients within the looser whole-layer bound of test_bf16_tensor_core_backward_vs_oracle (PReLU kink)."""
+    gd = Golden(name)
+    m = _module(gd, "bf16")
+    y, dx, grads = run_fwd_bwd(m, gd.x.cuda(), gd.g.cuda())
+    errs = {"y": rel_err(y, gd.y64), "dx": rel_err(dx, gd.dx64)}
+    for k, v in gd.grad64.items():
+        errs[k] = rel_err(grads[k], v)
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
     assert errs["y"] < BF16_TOL, errs
     assert max(errs.values()) < 0.15, errs
 
