@@ -308,8 +308,9 @@ __device__ inline void kc_gram_dbeta(const KcBasisCtx& B, float x, const float* 
 }
 
 // index of (channel c, basis j) inside the reference's w_basis inner dimension
+__host__ __device__ __forceinline__ bool kc_degree_major(int kind) { return kind == KC_BASIS_GRAM || kind == KC_BASIS_RECUR_DM; }
 __device__ __forceinline__ int kc_wbasis_index(int kind, int c, int j, int cin, int nb) {
-  return (kind == KC_BASIS_GRAM || kind == KC_BASIS_RECUR_DM) ? (j * cin + c) : (c * nb + j);
+  return kc_degree_major(kind) ? (j * cin + c) : (c * nb + j);
 }
 
 __device__ __forceinline__ float kc_warp_sum(float v) {

@@ -1871,7 +1871,7 @@ extern "C" int kc_tc_pack_weights(const kc_desc* d, const float* w_base, const f
   if (blocks > max_blocks) blocks = max_blocks;
   if (packed_fwd != nullptr) {
     const int nchunks = g.nsc + (d->act != KC_ACT_NONE ? g.nbc : 0);
-    if (d->basis != KC_BASIS_GRAM && T <= kPackMaxT && nchunks <= 65535 && g.n_ntiles <= 65535) {
+    if (!kc_degree_major(d->basis) && T <= kPackMaxT && nchunks <= 65535 && g.n_ntiles <= 65535) {
       dim3 pgrid((unsigned)((g.ntile + kPackTileCo - 1) / kPackTileCo), (unsigned)nchunks, (unsigned)g.n_ntiles);
       kc_pack_fwd_tile_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(a);
     } else {
