@@ -42,6 +42,11 @@ _SIGNATURES = {
     "kc_conv_dgrad_f32": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 10),
     "kc_wgrad_workspace_bytes": (c_sz, [_P(KcDesc)]),
     "kc_conv_wgrad_f32": (ctypes.c_int, [_P(KcDesc)] + [c_vp] * 8),
+    "kc_dwconv_supported": (ctypes.c_int, [_P(KcDesc), ctypes.c_int]),
+    "kc_dwconv_fwd_f32": (ctypes.c_int, [_P(KcDesc), ctypes.c_int] + [c_vp] * 6),
+    "kc_dwconv_dgrad_f32": (ctypes.c_int, [_P(KcDesc), ctypes.c_int] + [c_vp] * 8),
+    "kc_dwconv_wgrad_workspace_bytes": (c_sz, [_P(KcDesc), ctypes.c_int]),
+    "kc_dwconv_wgrad_f32": (ctypes.c_int, [_P(KcDesc), ctypes.c_int] + [c_vp] * 7),
     "kc_norm_act_fwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 9),
     "kc_norm_act_bwd": (ctypes.c_int, [_P(KcNormDesc)] + [c_vp] * 12 + [ctypes.c_int, c_vp]),
     "kc_dbeta_floats": (c_sz, [_P(KcDesc), ctypes.c_int]),

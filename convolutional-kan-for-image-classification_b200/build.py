@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(CSRC, "libkanconv.so")
-SOURCES = ["kc_api.cu", "kc_simt.cu", "kc_norm.cu", "kc_norm_cluster.cu", "kc_pool.cu", "kc_tc.cu", "kc_tc_wgrad.cu"]
+SOURCES = ["kc_api.cu", "kc_simt.cu", "kc_dw.cu", "kc_norm.cu", "kc_norm_cluster.cu", "kc_pool.cu", "kc_tc.cu", "kc_tc_wgrad.cu"]
 HEADERS = ["kc_common.cuh", "kc_umma.cuh", "kc_tc_basis.cuh", "kc_norm_common.cuh"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-I" + INCLUDE, "-diag-suppress", "177"]

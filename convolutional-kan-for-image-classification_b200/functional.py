@@ -244,6 +244,28 @@ def clear_pack_cache() -> None:
     _PACKS.clear()
 
 
+# ---- depthwise layers (groups == channels) ---------------------------------------------------------------------------------
+def _dw_desc(lib, spec: ConvSpec, precision: Optional[str], xb, beta, w_basis):
+    """Descriptor of the one-launch depthwise kernels (csrc/kc_dw.cu) when the layer is a stack of single-channel groups they
+    cover, else None.  ``precision == "bf16"`` (tensor cores forced) keeps the per-group route."""
+    G = spec.groups
+    n, c_total, h, w = xb.shape
+    if G < 2 or c_total != G or w_basis[0].shape[0] != 1 or beta is not None or precision == "bf16":
+        return None
+    ho, wo = spec.out_hw(h, w)
+    d = _make_desc(spec, n, 1, h, w, 1, c_total * h * w, G * ho * wo)
+    return d if lib.kc_dwconv_supported(ctypes.byref(d), G) else None
+
+
+def _dw_stack(ws):
+    """Per-group filters [1, rows, kh, kw] -> one [G, rows * kh * kw] matrix in group order."""
+    return torch.cat([w.reshape(1, -1) for w in ws], dim=0)
+
+
+def _dw_bytes(d, G: int, passes_in: int, passes_out: int) -> float:
+    return 4.0 * d.n * G * (passes_in * d.h * d.w + passes_out * d.ho * d.wo)
+
+
 def _split_weights(spec: ConvSpec, weights):
     G = spec.groups
     w_base = list(weights[:G]) if spec.has_base else [None] * G
@@ -266,6 +288,13 @@ def _conv_fwd(spec: ConvSpec, precision: str, xb, xs, beta, weights, want_phi: b
     with torch.cuda.device(dev):
         stream = _stream(dev)
         z = _empty((n, og * G, ho, wo), device=dev, dtype=torch.float32)
+        dw = _dw_desc(lib, spec, precision, xb, beta, w_basis)
+        if dw is not None:          # groups == channels: all groups in one launch
+            wb_all = _dw_stack(w_base) if spec.has_base else None
+            ws_all = _dw_stack(w_basis)
+            L.check(_timed("kc_dw_fwd_kernel", G * _conv_flops(dw), _dw_bytes(dw, G, 1, 1), lambda: lib.kc_dwconv_fwd_f32(
+                ctypes.byref(dw), G, _ptr(xb), _ptr(xs), _ptr(wb_all), _ptr(ws_all), _ptr(z), stream)), "kc_dwconv_fwd_f32")
+            return z, [False] * G, [None] * G, roots
         for g in range(G):
             d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
             xbg, xsg, zg = xb[:, g * cg:(g + 1) * cg], xs[:, g * cg:(g + 1) * cg], z[:, g * og:(g + 1) * og]
@@ -312,6 +341,28 @@ def _conv_bwd(spec: ConvSpec, used_tc, phis, roots, xb, xs, alias: bool, beta, w
         if run_dgrad:
             dx_base = _empty_like(xb)
             dx_basis = dx_base if alias else _empty_like(xs)
+        dw = None if (any(used_tc) or dz is None) else _dw_desc(lib, spec, None, xb, beta, w_basis)
+        if dw is not None:          # groups == channels: dX and dW of all groups in one launch each
+            wb_all = _dw_stack(w_base) if spec.has_base else None
+            ws_all = _dw_stack(w_basis)
+            if run_dgrad:
+                L.check(_timed("kc_dw_dgrad_kernel", G * _conv_flops(dw), _dw_bytes(dw, G, 2, 1), lambda: lib.kc_dwconv_dgrad_f32(
+                    ctypes.byref(dw), G, _ptr(dz), _ptr(xb), _ptr(xs), _ptr(wb_all), _ptr(ws_all), _ptr(dx_base), _ptr(dx_basis),
+                    stream)), "kc_dwconv_dgrad_f32")
+            if any(need_w):
+                dwb_all = _empty_like(wb_all) if wb_all is not None else None
+                dws_all = _empty_like(ws_all)
+                wsp = _empty(max(lib.kc_dwconv_wgrad_workspace_bytes(ctypes.byref(dw), G), 16), device=dev, dtype=torch.uint8)
+                L.check(_timed("kc_dw_wgrad_kernel", G * _conv_flops(dw), _dw_bytes(dw, G, 1, 1), lambda: lib.kc_dwconv_wgrad_f32(
+                    ctypes.byref(dw), G, _ptr(dz), _ptr(xb), _ptr(xs), _ptr(dwb_all), _ptr(dws_all), _ptr(wsp), stream)),
+                    "kc_dwconv_wgrad_f32")
+                for g in range(G):
+                    if spec.has_base:
+                        dws[g] = dwb_all[g].view_as(w_base[g])
+                        dws[G + g] = dws_all[g].view_as(w_basis[g])
+                    else:
+                        dws[g] = dws_all[g].view_as(w_basis[g])
+            return dx_base, dx_basis, dbeta, dws
         for g in range(G):
             d = _make_desc(spec, n, cg, h, w, og, c_total * h * w, og * G * ho * wo)
             sl = slice(g * cg, (g + 1) * cg)

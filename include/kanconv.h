@@ -124,6 +124,21 @@ size_t kc_wgrad_workspace_bytes(const kc_desc* d);
 int kc_conv_wgrad_f32(const kc_desc* d, const float* dz, const float* x_base, const float* x_basis,
                       const float* beta, float* dw_base, float* dw_basis, void* workspace, void* stream);
 
+/* Depthwise KAN convolution: `channels` single-channel groups (desc->cin == desc->cout == 1, batch strides covering all
+ * channels) in one launch each for forward, dX and dW.  Replaces the per-group Python loop of
+ * KANConvNDLayer.forward (layers/kan_layers.py:249-258) for the `replace_depthwise=True` stage of MobileNetV2
+ * (models/kan_mobilenetv2.py:112-124: groups == channels, up to 960 iterations per layer upstream).
+ * w_base [channels][kh*kw] and w_basis [channels][nb][kh*kw] are the per-group filters stacked in group order.  FP32; every
+ * family but GRAM; nb + 1 <= 9, kh*kw <= 9.  kc_dwconv_supported() != 0 iff the three entry points accept the shape. */
+int kc_dwconv_supported(const kc_desc* d, int channels);
+int kc_dwconv_fwd_f32(const kc_desc* d, int channels, const float* x_base, const float* x_basis, const float* w_base,
+                      const float* w_basis, float* z, void* stream);
+int kc_dwconv_dgrad_f32(const kc_desc* d, int channels, const float* dz, const float* x_base, const float* x_basis,
+                        const float* w_base, const float* w_basis, float* dx_base, float* dx_basis, void* stream);
+size_t kc_dwconv_wgrad_workspace_bytes(const kc_desc* d, int channels);
+int kc_dwconv_wgrad_f32(const kc_desc* d, int channels, const float* dz, const float* x_base, const float* x_basis,
+                        float* dw_base, float* dw_basis, void* workspace, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Max pooling between convolution stages (nn.MaxPool2d(k, s), no padding / dilation; models/kan_vgg.py "M" entries).
  * x is [planes][h][w] fp32 (planes = n*c), y / idx are [planes][ho][wo] with ho = (h-k)/s + 1; idx holds the

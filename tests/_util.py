@@ -34,7 +34,7 @@ def layer_class(package, kind):
 
 
 # whole-model fixtures (make_model_golden.py): a different record layout
-MODEL_FIXTURES = {"mbv2_fastkan_forward", "vgg16_kansmall_forward", "vgg16_kansmall_128_forward", "vgg11_forward", "kan_mlp_forward"}
+MODEL_FIXTURES = {"mbv2_fastkan_forward", "mbv2_fastkan_rdw_forward", "vgg16_kansmall_forward", "vgg16_kansmall_128_forward", "vgg11_forward", "kan_mlp_forward"}
 
 
 def golden_names():

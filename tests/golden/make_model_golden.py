@@ -47,10 +47,11 @@ if not sys.argv[1:]:
 # small forward/backward fixture: FastKAN-MobileNetV2 (kan_small, width 0.25) on 4x3x32x32, dropout off.  The model is badly
 # conditioned at initialisation (train-mode BatchNorm over 16 values in the last blocks): the reference's own fp32 run deviates
 # from its fp64 run by ~3e-3 (logits) / ~1e-1 (gradients), so that self-noise is stored next to the fp64 golden.
-def run(dtype):
+def run(dtype, **extra):
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
-        m = mobilenet_v2_kan(num_classes=10, width_mult=0.25, arch="kan_small", kan_conv="FastKAN", classifier_type="Linear", dropout=0.0)
+        m = mobilenet_v2_kan(num_classes=10, width_mult=0.25, arch="kan_small", kan_conv="FastKAN", classifier_type="Linear",
+                             dropout=0.0, **extra)
     m = m.to(dtype).train()
     torch.manual_seed(1)
     x = torch.randn(4, 3, 32, 32)
@@ -67,6 +68,21 @@ if not sys.argv[1:] or "mbv2" in sys.argv[1:]:
     np.savez_compressed(os.path.join(HERE, "mbv2_fastkan_forward.npz"), x=x.numpy(), y=y64.numpy(), loss=l64, y32=y32.numpy(), loss32=l32,
                         **{"grad/" + k: g64[k].numpy() for k in keys}, **{"grad32/" + k: g32[k].numpy() for k in keys})
     print("mbv2 fixture: y", tuple(y64.shape), "loss", l64, "ref fp32 self-noise y", float((y32.double() - y64).abs().max() / y64.abs().max()))
+
+
+# the same model with `replace_depthwise=True` (models/kan_mobilenetv2.py:112-124): the 7 depthwise stages become FastKAN
+# convolutions with groups == channels (up to 48 single-channel groups per layer at this width)
+rdw_keys = ["features.0.spline_conv.0.weight", "features.2.conv.1.spline_conv.5.weight", "features.2.conv.1.base_conv.0.weight",
+            "features.4.conv.1.spline_conv.17.weight", "classifier.fc.weight"]
+if not sys.argv[1:] or "mbv2_rdw" in sys.argv[1:]:
+    x, y64, l64, g64 = run(torch.float64, replace_depthwise=True)
+    _, y32, l32, g32 = run(torch.float32, replace_depthwise=True)
+    rdw_keys = [k for k in rdw_keys if k in g64]
+    np.savez_compressed(os.path.join(HERE, "mbv2_fastkan_rdw_forward.npz"), x=x.numpy(), y=y64.numpy(), loss=l64, y32=y32.numpy(),
+                        loss32=l32, **{"grad/" + k: g64[k].numpy() for k in rdw_keys},
+                        **{"grad32/" + k: g32[k].numpy() for k in rdw_keys})
+    print("mbv2 rdw fixture: y", tuple(y64.shape), "loss", l64, "keys", rdw_keys,
+          "ref fp32 self-noise y", float((y32.double() - y64).abs().max() / y64.abs().max()))
 
 
 # ---- round 2: KAN-VGG (the benched model family) and the KAN MLP head, forward + backward fixtures ------------------------

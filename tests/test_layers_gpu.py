@@ -310,6 +310,55 @@ def test_bf16_recurrence_family_layers_fwd_bwd_vs_reference_golden(name):
     assert max(errs.values()) < 0.15, errs
 
 
+@pytest.mark.parametrize("kind,c,h,w,n,kw", [
+    ("kan", 5, 9, 7, 3, dict(kernel_size=3, padding=1)),
+    ("kan", 24, 20, 21, 2, dict(kernel_size=3, padding=1, stride=2, base_activation="silu")),
+    ("kan", 6, 12, 12, 2, dict(kernel_size=3, padding=2, dilation=2, grid_size=3, spline_order=2)),
+    ("kan", 40, 37, 33, 2, dict(kernel_size=3, padding=1, base_activation="silu")),
+    ("cheby", 7, 10, 11, 2, dict(kernel_size=3, padding=1, degree=3)),
+    ("fast", 12, 14, 15, 3, dict(kernel_size=3, padding=1, stride=2, grid_size=5)),
+    ("fast", 8, 8, 8, 2, dict(kernel_size=1, padding=0)),
+    ("hermite2d", 9, 11, 13, 2, dict(kernel_size=3, padding=1, degree=3)),
+    ("kan", 16, 70, 5, 1, dict(kernel_size=(3, 1), padding=(1, 0))),
+])
+def test_depthwise_layers_run_on_the_one_launch_kernels_and_match_the_oracle(kind, c, h, w, n, kw):
+    """groups == channels (the reference's `replace_depthwise=True` stage, models/kan_mobilenetv2.py:112-124): forward, dX and
+    every parameter gradient of the one-launch depthwise kernels (csrc/kc_dw.cu) vs the fp64 oracle at the FP32 tolerance, and
+    the kernel log shows that the per-group route was not taken."""
+    from kanconv_b200 import functional as KF
+    from _util import ORACLE_CTORS
+    okw = dict(input_dim=c, output_dim=c, groups=c, **kw)
+    mkw = dict(okw)
+    if "base_activation" in mkw:
+        mkw["base_activation"] = {"silu": nn.SiLU, "gelu": nn.GELU}[mkw["base_activation"]]
+    torch.manual_seed(0)
+    mod = CTORS[kind](**mkw)
+    ora = ORACLE_CTORS[kind](**okw)
+    ora.load_state_dict(mod.state_dict())
+    ora, mod = ora.double(), mod.cuda()
+    mod.precision = "fp32"
+    torch.manual_seed(3)
+    x = torch.randn(n, c, h, w) * 1.2
+    g = torch.randn(*ora(x.double()).shape)
+    yo, dxo, go = run_fwd_bwd(ora, x.double(), g.double())
+    KF.profile_begin()
+    y, dx, gr = run_fwd_bwd(mod, x.cuda(), g.cuda())
+    names = set(KF.profile_end())
+    assert {"kc_dw_fwd_kernel", "kc_dw_dgrad_kernel", "kc_dw_wgrad_kernel"} <= names, names
+    assert not any("simt" in k or "kc_tc" in k for k in names), names
+    errs = {"y": rel_err(y, yo), "dx": rel_err(dx, dxo)}
+    assert set(gr) == set(go)
+    for k in go:
+        errs[k] = rel_err(gr[k], go[k])
+    worst = max(errs, key=errs.get)
+    print(kind, c, f"worst {worst}: {errs[worst]:.2e}")
+    assert errs[worst] < FP32_TOL, errs
+    # "auto" precision takes the same route; reruns are bit-identical (fixed-order reductions)
+    mod.precision = "auto"
+    y2, dx2, gr2 = run_fwd_bwd(mod, x.cuda(), g.cuda())
+    assert torch.equal(y, y2) and torch.equal(dx, dx2) and all(torch.equal(gr[k], gr2[k]) for k in gr)
+
+
 @pytest.mark.parametrize("k,pad", [(1, 0), (3, 1)])
 def test_bf16_tensor_core_padded_basis_width(k, pad):
     """Basis widths that are not 4 or 8 run on the tensor cores zero-padded (FastKAN with 5 grid points is the
@@ -356,6 +405,46 @@ def test_fastkan_mobilenetv2_fp32_matches_reference_model():
     finally:
         K.set_precision("auto")
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    y64 = torch.from_numpy(z["y"])
+    mine = {"y": rel_err(y, y64)}
+    ref32 = {"y": rel_err(torch.from_numpy(z["y32"]), y64)}
+    grads = dict(m.named_parameters())
+    for k in z.files:
+        if k.startswith("grad/"):
+            mine[k] = rel_err(grads[k[5:]].grad, torch.from_numpy(z[k]))
+            ref32[k] = rel_err(torch.from_numpy(z["grad32/" + k[5:]]), torch.from_numpy(z[k]))
+    print("mine ", {k: f"{v:.2e}" for k, v in mine.items()})
+    print("ref32", {k: f"{v:.2e}" for k, v in ref32.items()})
+    for k in mine:
+        assert mine[k] <= 3.0 * ref32[k] + 1e-5, (k, mine[k], ref32[k])
+
+
+def test_fastkan_mobilenetv2_replace_depthwise_matches_reference_model():
+    """The same model with `replace_depthwise=True` (models/kan_mobilenetv2.py:112-124): the depthwise stages are FastKAN
+    convolutions with groups == channels, which run on the one-launch depthwise kernels (csrc/kc_dw.cu).  Logits and gradients
+    (incl. single-channel group filters) against the REFERENCE model's fp64 run, same gate as the test above."""
+    import numpy as np, os
+    from _util import GOLDEN
+    from kanconv_b200 import functional as KF
+    from kanconv_b200.models import mobilenet_v2_kan
+    z = np.load(os.path.join(GOLDEN, "mbv2_fastkan_rdw_forward.npz"))
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    K.set_precision("fp32")
+    try:
+        torch.manual_seed(0)
+        m = mobilenet_v2_kan(num_classes=10, width_mult=0.25, arch="kan_small", kan_conv="FastKAN", classifier_type="Linear",
+                             dropout=0.0, replace_depthwise=True).cuda().train()
+        KF.profile_begin()
+        y = m(torch.from_numpy(z["x"]).cuda())
+        loss = y.square().mean()
+        loss.backward()
+        names = KF.profile_end()
+    finally:
+        K.set_precision("auto")
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert names["kc_dw_fwd_kernel"]["calls"] == 7 and names["kc_dw_wgrad_kernel"]["calls"] == 7, {k: v["calls"] for k, v in names.items()}
     y64 = torch.from_numpy(z["y"])
     mine = {"y": rel_err(y, y64)}
     ref32 = {"y": rel_err(torch.from_numpy(z["y32"]), y64)}
