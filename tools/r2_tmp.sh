@@ -1,4 +1,4 @@
 #!/bin/bash
 O=gpurun_out/r2; mkdir -p $O
-timeout 300 python -m pytest tests -m gpu -q -x -k "depthwise" 2>&1 | tail -4
-timeout 300 python tools/dw_bench.py 64 2>&1 | tee $O/dw_bench_v2.txt | tail -11 | cut -c1-420
+timeout 600 python -m pytest tests -m gpu -q -rs -s 2>&1 | grep -v "^$" > $O/gputest_log.txt; tail -3 $O/gputest_log.txt
+bash tools/ncu_round.sh r2 > $O/ncu_round.log 2>&1; tail -3 $O/ncu_round.log
