@@ -22,7 +22,7 @@ Template B - ``base_conv`` / ``layer_norm`` / ``poly_weights``, degree-major exp
 Same constructor signatures, module trees, state_dict keys and RNG consumption as upstream."""
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Tuple
 
 import torch
 import torch.nn as nn
@@ -154,40 +154,36 @@ _CONVS = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}
 _INORMS = {1: nn.InstanceNorm1d, 2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}
 
 
-def _bind(base, ndim: int, name: str, extra: Sequence[str] = ()):
-    """The reference's ``<Family>KANConv{1,2,3}DLayer`` classes: the N-D layer bound to nn.Conv{n}d / nn.InstanceNorm{n}d.
-    ``extra`` = names of the family's own positional parameters that follow ``degree`` (Gegenbauer ``alpha_param``,
-    Laguerre ``alpha``)."""
-    if not extra:
-        def __init__(self, input_dim, output_dim, kernel_size, degree, groups=1, padding=0, stride=1, dilation=1,
-                     base_activation=nn.GELU, dropout=0.0, norm_layer=_INORMS[ndim], **norm_kwargs):
-            base.__init__(self, conv_class=_CONVS[ndim], norm_class=norm_layer, input_dim=input_dim, output_dim=output_dim,
-                          kernel_size=kernel_size, degree=degree, groups=groups, padding=padding, stride=stride,
-                          dilation=dilation, ndim=ndim, base_activation=base_activation, dropout=dropout, **norm_kwargs)
-    else:
-        key = extra[0]
+def _bind(base, ndim: int, name: str):
+    """The reference's ``<Family>KANConv{1,2,3}DLayer`` classes: the N-D layer bound to nn.Conv{n}d / nn.InstanceNorm{n}d."""
+    def __init__(self, input_dim, output_dim, kernel_size, degree, groups=1, padding=0, stride=1, dilation=1,
+                 base_activation=nn.GELU, dropout=0.0, norm_layer=_INORMS[ndim], **norm_kwargs):
+        base.__init__(self, conv_class=_CONVS[ndim], norm_class=norm_layer, input_dim=input_dim, output_dim=output_dim,
+                      kernel_size=kernel_size, degree=degree, groups=groups, padding=padding, stride=stride,
+                      dilation=dilation, ndim=ndim, base_activation=base_activation, dropout=dropout, **norm_kwargs)
+    return type(name, (base,), {"__init__": __init__, "__module__": base.__module__,
+                                "__doc__": f"{base.__name__} bound to nn.Conv{ndim}d / nn.InstanceNorm{ndim}d."})
 
-        def __init__(self, input_dim, output_dim, kernel_size, degree, *args, groups=1, padding=0, stride=1, dilation=1,
-                     base_activation=nn.GELU, dropout=0.0, norm_layer=_INORMS[ndim], **norm_kwargs):
-            # upstream: (input_dim, output_dim, kernel_size, degree, <key>, groups=1, padding=0, stride=1, dilation=1, ...)
-            names = [key, "groups", "padding", "stride", "dilation", "base_activation", "dropout", "norm_layer"]
-            if len(args) > len(names):
-                raise TypeError(f"{name}: too many positional arguments")
-            kw = dict(groups=groups, padding=padding, stride=stride, dilation=dilation, base_activation=base_activation,
-                      dropout=dropout, norm_layer=norm_layer)
-            for n_, v in zip(names, args):
-                if n_ == key and key in norm_kwargs:
-                    raise TypeError(f"{name}: got multiple values for argument {key!r}")
-                if n_ == key:
-                    norm_kwargs[key] = v
-                else:
-                    kw[n_] = v
-            if key not in norm_kwargs:
-                raise TypeError(f"{name}: missing required argument {key!r}")
-            extra_value = norm_kwargs.pop(key)
-            base.__init__(self, conv_class=_CONVS[ndim], norm_class=kw.pop("norm_layer"), input_dim=input_dim,
-                          output_dim=output_dim, kernel_size=kernel_size, degree=degree, ndim=ndim, **{key: extra_value},
-                          **kw, **norm_kwargs)
+
+def _bind_gegenbauer(base, ndim: int, name: str):
+    """Same, with Gegenbauer's positional ``alpha_param`` after ``degree`` (gegenbauer_kan_layers.py:185-246)."""
+    def __init__(self, input_dim, output_dim, kernel_size, degree, alpha_param, groups=1, padding=0, stride=1, dilation=1,
+                 base_activation=nn.GELU, dropout=0.0, norm_layer=_INORMS[ndim], **norm_kwargs):
+        base.__init__(self, conv_class=_CONVS[ndim], norm_class=norm_layer, input_dim=input_dim, output_dim=output_dim,
+                      kernel_size=kernel_size, degree=degree, alpha_param=alpha_param, groups=groups, padding=padding,
+                      stride=stride, dilation=dilation, ndim=ndim, base_activation=base_activation, dropout=dropout,
+                      **norm_kwargs)
+    return type(name, (base,), {"__init__": __init__, "__module__": base.__module__,
+                                "__doc__": f"{base.__name__} bound to nn.Conv{ndim}d / nn.InstanceNorm{ndim}d."})
+
+
+def _bind_laguerre(base, ndim: int, name: str):
+    """Same, with Laguerre's positional ``alpha`` after ``degree`` (laguerre_kan_layers.py:186-212)."""
+    def __init__(self, input_dim, output_dim, kernel_size, degree, alpha, groups=1, padding=0, stride=1, dilation=1,
+                 base_activation=nn.GELU, dropout=0.0, norm_layer=_INORMS[ndim], **norm_kwargs):
+        base.__init__(self, conv_class=_CONVS[ndim], norm_class=norm_layer, input_dim=input_dim, output_dim=output_dim,
+                      kernel_size=kernel_size, degree=degree, alpha=alpha, groups=groups, padding=padding, stride=stride,
+                      dilation=dilation, ndim=ndim, base_activation=base_activation, dropout=dropout, **norm_kwargs)
     return type(name, (base,), {"__init__": __init__, "__module__": base.__module__,
                                 "__doc__": f"{base.__name__} bound to nn.Conv{ndim}d / nn.InstanceNorm{ndim}d."})
 
@@ -272,9 +268,9 @@ BesselKANConv1DLayer, BesselKANConv2DLayer, BesselKANConv3DLayer = (
 TaylorKANConv1DLayer, TaylorKANConv2DLayer, TaylorKANConv3DLayer = (
     _bind(TaylorKANConvNDLayer, n, f"TaylorKANConv{n}DLayer") for n in (1, 2, 3))
 GegenbauerKANConv1DLayer, GegenbauerKANConv2DLayer, GegenbauerKANConv3DLayer = (
-    _bind(GegenbauerKANConvNDLayer, n, f"GegenbauerKANConv{n}DLayer", ("alpha_param",)) for n in (1, 2, 3))
+    _bind_gegenbauer(GegenbauerKANConvNDLayer, n, f"GegenbauerKANConv{n}DLayer") for n in (1, 2, 3))
 LaguerreKANConv1DLayer, LaguerreKANConv2DLayer, LaguerreKANConv3DLayer = (
-    _bind(LaguerreKANConvNDLayer, n, f"LaguerreKANConv{n}DLayer", ("alpha",)) for n in (1, 2, 3))
+    _bind_laguerre(LaguerreKANConvNDLayer, n, f"LaguerreKANConv{n}DLayer") for n in (1, 2, 3))
 
 
 # ---- template B ---------------------------------------------------------------------------------------------------------------
