@@ -26,6 +26,13 @@ CASES = {
     "mbv2_fastkan_kan_small_w025": lambda: mobilenet_v2_kan(num_classes=10, width_mult=0.25, arch="kan_small", kan_conv="FastKAN",
                                                            classifier_type="Linear"),
     "mbv2_kan_default_w025": lambda: mobilenet_v2_kan(num_classes=10, width_mult=0.25, kan_conv="KAN", classifier_type="Linear"),
+    "vgg16_kansmall_hermite": lambda: vggkan(3, 10, arch="VGG16_kansmall", kan_conv="HermiteKAN", classifier_type="Linear"),
+    "vgg16_kansmall_legendre": lambda: vggkan(3, 10, arch="VGG16_kansmall", kan_conv="LegendreKAN", classifier_type="Linear"),
+    "vgg16_kansmall_jacobi": lambda: vggkan(3, 10, arch="VGG16_kansmall", kan_conv="JacobiKAN", classifier_type="Linear"),
+    "mbv2_gegenbauer_kan_small_w025": lambda: mobilenet_v2_kan(num_classes=10, width_mult=0.25, arch="kan_small",
+                                                              kan_conv="GegenbauerKAN", classifier_type="Linear"),
+    "mbv2_fastkan_rdw_kan_small_w025": lambda: mobilenet_v2_kan(num_classes=10, width_mult=0.25, arch="kan_small", kan_conv="FastKAN",
+                                                               classifier_type="Linear", replace_depthwise=True),
 }
 
 
