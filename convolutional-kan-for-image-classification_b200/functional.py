@@ -25,7 +25,7 @@ from __future__ import annotations
 import ctypes
 import os
 import weakref
-from dataclasses import dataclass
+from dataclasses import dataclass, replace as _dc_replace
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -38,6 +38,8 @@ _TC_BACKWARD = os.environ.get("KANCONV_TC_BACKWARD", "1") != "0"   # debug switc
 _SAVE_PHI = os.environ.get("KANCONV_SAVE_PHI", "1") != "0"
 # KANCONV_FUSED_NORM_BWD=0: debug switch, norm backward to fp32 dz + separate conversion to the bf16 flat layout
 _FUSED_NORM_BWD = os.environ.get("KANCONV_FUSED_NORM_BWD", "1") != "0"
+# norm + activation of a grouped layer as ONE launch over all channels instead of one launch per group (A/B switch)
+_MERGE_NORM_GROUPS = os.environ.get("KANCONV_MERGE_NORM_GROUPS", "1") != "0"
 _PRECISION = "auto"      # "auto": tensor cores when the shape is supported, else CUDA-core FP32 | "bf16" | "fp32"
 
 
@@ -477,8 +479,47 @@ def _norm_desc(spec: NormSpec, n, cg, hw, c_total) -> L.KcNormDesc:
     return d
 
 
+# ---- grouped norms in one launch --------------------------------------------------------------------------------------------
+# The norm kernels index CHANNELS; a group is only a separate set of parameter tensors (gamma_g, beta_g) and, for PReLU, one
+# scalar alpha behind a single pointer.  Without PReLU all groups can therefore run as one launch over all channels with the
+# affine parameters concatenated - what makes depthwise layers (hundreds of one-channel groups, each with its own norm module
+# upstream: kan_layers.py:178-182) practical.  The statistics keep the per-group layout [G, ...] towards the callers.
+def _norm_merged(spec: NormSpec) -> bool:
+    return _MERGE_NORM_GROUPS and spec.groups > 1 and spec.out_act != L.OUT_PRELU
+
+
+def _merged_params(spec: NormSpec, params):
+    if not spec.affine:
+        return []
+    G = spec.groups
+    return [torch.cat([params[2 * g].reshape(-1) for g in range(G)]), torch.cat([params[2 * g + 1].reshape(-1) for g in range(G)])]
+
+
+def _stats_to_groups(t, spec: NormSpec, n: int, cg: int):
+    """[1, nstat of all channels] -> [G, nstat of one group] (instance norm: planes are ordered [n][c])."""
+    G = spec.groups
+    if spec.norm == L.NORM_BATCH:
+        return t.reshape(G, cg)
+    if spec.norm == L.NORM_INSTANCE:
+        return t.reshape(n, G, cg).permute(1, 0, 2).reshape(G, n * cg)
+    return t.reshape(1, 1).expand(G, 1)
+
+
+def _stats_from_groups(t, spec: NormSpec, n: int, cg: int):
+    G = spec.groups
+    if spec.norm == L.NORM_BATCH:
+        return t.reshape(1, G * cg)
+    if spec.norm == L.NORM_INSTANCE:
+        return t.reshape(G, n, cg).permute(1, 0, 2).reshape(1, n * G * cg).contiguous()
+    return t[:1].contiguous()
+
+
 def _norm_fwd(spec: NormSpec, z, given_mean, given_rstd, params):
     """-> (y, mean, rstd); z contiguous."""
+    if _norm_merged(spec):
+        n, cg = z.shape[0], z.shape[1] // spec.groups
+        y, mean, rstd = _norm_fwd(_dc_replace(spec, groups=1), z, given_mean, given_rstd, _merged_params(spec, params))
+        return y, _stats_to_groups(mean, spec, n, cg), _stats_to_groups(rstd, spec, n, cg)
     lib = L.load()
     dev = z.device
     G = spec.groups
@@ -511,6 +552,16 @@ def _norm_fwd(spec: NormSpec, z, given_mean, given_rstd, params):
 
 def _norm_bwd(spec: NormSpec, z, mean, rstd, params, dy):
     """-> (dz fp32, grads of params); dy contiguous."""
+    if _norm_merged(spec):
+        G, n, cg = spec.groups, z.shape[0], z.shape[1] // spec.groups
+        dz, g1 = _norm_bwd(_dc_replace(spec, groups=1), z, _stats_from_groups(mean, spec, n, cg),
+                           _stats_from_groups(rstd, spec, n, cg), _merged_params(spec, params), dy)
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        if spec.affine:
+            for g in range(G):
+                grads[2 * g] = g1[0][g * cg:(g + 1) * cg].view_as(params[2 * g])
+                grads[2 * g + 1] = g1[1][g * cg:(g + 1) * cg].view_as(params[2 * g + 1])
+        return dz, grads
     lib = L.load()
     dev = z.device
     given = int(spec.norm == L.NORM_BATCH and not spec.use_batch_stats)

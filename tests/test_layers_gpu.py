@@ -359,6 +359,39 @@ def test_depthwise_layers_run_on_the_one_launch_kernels_and_match_the_oracle(kin
     assert torch.equal(y, y2) and torch.equal(dx, dx2) and all(torch.equal(gr[k], gr2[k]) for k in gr)
 
 
+@pytest.mark.parametrize("kind,kw", [("cheby", dict(degree=3, affine=True)), ("fast", dict(norm_layer=nn.BatchNorm2d)),
+                                     ("gram", dict(degree=3)), ("legendre2d", dict(degree=3, affine=True))])
+def test_grouped_norm_in_one_launch_is_bit_identical_to_per_group_launches(kind, kw, monkeypatch):
+    """Layers without PReLU normalise all groups in ONE launch (functional._norm_merged): same y, dX and parameter gradients, bit
+    for bit, as with one launch per group, and the kernel log shows the single launch."""
+    from kanconv_b200 import functional as KF
+    torch.manual_seed(0)
+    m = CTORS[kind](12, 12, 3, groups=4, padding=1, **kw).cuda().train()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "layer_norm" in k:
+                p.add_(0.1 * torch.randn_like(p))
+    m.precision = "fp32"
+    torch.manual_seed(1)
+    x = torch.randn(3, 12, 10, 9, device="cuda")
+    g = torch.randn(3, 12, 10, 9, device="cuda")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    out, launches = {}, {}
+    for merged in (True, False):
+        monkeypatch.setattr(KF, "_MERGE_NORM_GROUPS", merged)
+        m.load_state_dict(sd)                                   # same BatchNorm running statistics for both runs
+        KF.profile_begin()
+        out[merged] = run_fwd_bwd(m, x, g)
+        launches[merged] = sum(v["calls"] for k, v in KF.profile_end().items() if "norm" in k)
+    print(kind, "norm launches, merged / per group:", launches[True], "/", launches[False])
+    assert launches[True] * 4 == launches[False], launches
+    (y1, dx1, g1), (y0, dx0, g0) = out[True], out[False]
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    assert set(g1) == set(g0)
+    for k in g0:
+        assert torch.equal(g1[k], g0[k]), k
+
+
 @pytest.mark.parametrize("k,pad", [(1, 0), (3, 1)])
 def test_bf16_tensor_core_padded_basis_width(k, pad):
     """Basis widths that are not 4 or 8 run on the tensor cores zero-padded (FastKAN with 5 grid points is the

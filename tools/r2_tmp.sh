@@ -1,3 +1,2 @@
 #!/bin/bash
-O=gpurun_out/r2; mkdir -p $O
-timeout 140 python bench.py --steps 10 --warmup 3 > $O/bench_1gpu_final.json 2> $O/bench_1gpu_final.err; tail -c 600 $O/bench_1gpu_final.json
+timeout 100 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
